@@ -1,0 +1,523 @@
+// Multi-scale deformable attention (MSDA) forward / backward for sm_100a.
+//
+// Semantics follow the reference kernels
+//   <proj>/models/model_utils/ops/src/cuda/ms_deform_im2col_cuda.cuh:33-84   (bilinear fwd)
+//   ...:87-159 (bilinear bwd), :237-299 (im2col fwd), :301-403 (col2im bwd)
+// but the work decomposition is new: a lane owns FOUR channels of one (query, head) pair, so a
+// head of D=16 channels is 4 lanes and a warp covers 8 heads.  Every bilinear corner is one
+// 128-bit read-only load (two full 32-B sectors per head at D=16), the 16 corner loads of a
+// (query, head) pair (P=4) are issued back to back before any use, sampling locations and
+// attention weights are read once per lane group instead of once per channel, backward reduces
+// grad_loc / grad_attn over channels with warp shuffles and accumulates grad_value with 16-byte
+// red.global.add.v4.f32 instead of four scalar atomics.
+//
+// Arithmetic that decides WHICH pixels are touched (h_im, w_im, floor, range test) is kept
+// contraction-free (__fmul_rn/__fsub_rn) so the sampled corners are identical to the
+// reference; the weighted sums may differ in FMA contraction (fp32 parity bar: 1e-3 rel).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxLevels = 32;
+constexpr int kThreads = 256;
+
+struct LevelTable {
+  int H[kMaxLevels];
+  int W[kMaxLevels];
+  int start[kMaxLevels];
+};
+
+__device__ __forceinline__ void load_levels(LevelTable& t, const int64_t* shapes,
+                                            const int64_t* lsi, int L) {
+  if (threadIdx.x < L) {
+    t.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    t.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    t.start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4fma(float a, float4 v, float4 acc) {
+  acc.x = fmaf(a, v.x, acc.x);
+  acc.y = fmaf(a, v.y, acc.y);
+  acc.z = fmaf(a, v.z, acc.z);
+  acc.w = fmaf(a, v.w, acc.w);
+  return acc;
+}
+__device__ __forceinline__ float f4dot(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// One sampling point's geometry: which corners exist and with what bilinear weights.
+struct Corner {
+  bool inr;             // point inside (-1, H) x (-1, W)
+  bool ok1, ok2, ok3, ok4;
+  int o1, o2, o3, o4;   // element offsets (in pixels) of the 4 corners inside the level
+  float lh, lw, hh, hw;
+};
+
+__device__ __forceinline__ Corner make_corner(float loc_x, float loc_y, int H, int W) {
+  Corner c;
+  // reference: h_im = loc_h * spatial_h - 0.5 (ms_deform_im2col_cuda.cuh:285-286), no FMA
+  const float h_im = __fsub_rn(__fmul_rn(loc_y, (float)H), 0.5f);
+  const float w_im = __fsub_rn(__fmul_rn(loc_x, (float)W), 0.5f);
+  c.inr = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  const int h_low = (int)hf, w_low = (int)wf;
+  c.lh = h_im - hf;
+  c.lw = w_im - wf;
+  c.hh = 1.f - c.lh;
+  c.hw = 1.f - c.lw;
+  const bool hl = h_low >= 0, hh_ = h_low + 1 <= H - 1, wl = w_low >= 0, wh = w_low + 1 <= W - 1;
+  c.ok1 = c.inr && hl && wl;
+  c.ok2 = c.inr && hl && wh;
+  c.ok3 = c.inr && hh_ && wl;
+  c.ok4 = c.inr && hh_ && wh;
+  c.o1 = h_low * W + w_low;
+  c.o2 = c.o1 + 1;
+  c.o3 = c.o1 + W;
+  c.o4 = c.o3 + 1;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, fp32, D = 4*TPH.  One lane = 4 channels of one (b, q, m).
+// ---------------------------------------------------------------------------------------------
+template <int TPH>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_vec4_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                     const float* __restrict__ attn, float* __restrict__ out, int S, int M, int L,
+                     int Lq, int P, long long total) {
+  __shared__ LevelTable lv;
+  load_levels(lv, shapes, lsi, L);
+  const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= total) return;
+  constexpr int D = TPH * 4;
+  const int c4 = (int)(idx % TPH);
+  const long long qm = idx / TPH;
+  const int m = (int)(qm % M);
+  const long long b = (qm / M) / Lq;
+  const long long pix = (long long)M * D;  // floats per pixel
+  const float* vb = value + b * S * pix + m * D + c4 * 4;
+  const float2* locp = reinterpret_cast<const float2*>(loc) + qm * L * P;
+  const float* attp = attn + qm * L * P;
+
+  float4 acc = f4zero();
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const float* vl = vb + (long long)lv.start[l] * pix;
+    for (int p0 = 0; p0 < P; p0 += 4) {
+      Corner c[4];
+      float a[4];
+      float4 v[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool live = p0 + j < P;
+        const int pi = l * P + (live ? p0 + j : p0);
+        const float2 xy = __ldg(locp + pi);
+        a[j] = live ? __ldg(attp + pi) : 0.f;
+        c[j] = make_corner(xy.x, xy.y, H, W);
+        if (!live) c[j].ok1 = c[j].ok2 = c[j].ok3 = c[j].ok4 = false;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j][0] = c[j].ok1 ? ldg4(vl + (long long)c[j].o1 * pix) : f4zero();
+        v[j][1] = c[j].ok2 ? ldg4(vl + (long long)c[j].o2 * pix) : f4zero();
+        v[j][2] = c[j].ok3 ? ldg4(vl + (long long)c[j].o3 * pix) : f4zero();
+        v[j][3] = c[j].ok4 ? ldg4(vl + (long long)c[j].o4 * pix) : f4zero();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w1 = c[j].hh * c[j].hw, w2 = c[j].hh * c[j].lw, w3 = c[j].lh * c[j].hw,
+                    w4 = c[j].lh * c[j].lw;
+        float4 val = f4zero();
+        val = f4fma(w1, v[j][0], val);
+        val = f4fma(w2, v[j][1], val);
+        val = f4fma(w3, v[j][2], val);
+        val = f4fma(w4, v[j][3], val);
+        acc = f4fma(a[j], val, acc);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(out + qm * D + c4 * 4) = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward, fp32, D = 4*TPH.  Same decomposition; channel reductions by warp shuffle over the
+// TPH lanes of a head, grad_value by 16-byte vector reductions.
+// ---------------------------------------------------------------------------------------------
+template <int TPH>
+__global__ void __launch_bounds__(kThreads, 2)
+msda_bwd_vec4_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                     const float* __restrict__ attn, const float* __restrict__ gout,
+                     float* __restrict__ gvalue, float* __restrict__ gloc,
+                     float* __restrict__ gattn, int S, int M, int L, int Lq, int P,
+                     long long total) {
+  __shared__ LevelTable lv;
+  load_levels(lv, shapes, lsi, L);
+  long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool active = idx < total;
+  if (!active) idx = total - 1;  // keep the lane alive for the shuffles, suppress its writes
+  constexpr int D = TPH * 4;
+  const int c4 = (int)(idx % TPH);
+  const long long qm = idx / TPH;
+  const int m = (int)(qm % M);
+  const long long b = (qm / M) / Lq;
+  const long long pix = (long long)M * D;
+  const long long voff = b * S * pix + m * D + c4 * 4;
+  const float* vb = value + voff;
+  float* gvb = gvalue + voff;
+  const float2* locp = reinterpret_cast<const float2*>(loc) + qm * L * P;
+  const float* attp = attn + qm * L * P;
+  float4 g = ldg4(gout + qm * D + c4 * 4);
+  if (!active) g = f4zero();
+
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const long long lo = (long long)lv.start[l] * pix;
+    const float* vl = vb + lo;
+    float* gvl = gvb + lo;
+    for (int p0 = 0; p0 < P; p0 += 4) {
+      Corner c[4];
+      float a[4];
+      float4 v[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool live = p0 + j < P;
+        const int pi = l * P + (live ? p0 + j : p0);
+        const float2 xy = __ldg(locp + pi);
+        a[j] = __ldg(attp + pi);
+        c[j] = make_corner(xy.x, xy.y, H, W);
+        if (!live) c[j].ok1 = c[j].ok2 = c[j].ok3 = c[j].ok4 = false;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j][0] = c[j].ok1 ? ldg4(vl + (long long)c[j].o1 * pix) : f4zero();
+        v[j][1] = c[j].ok2 ? ldg4(vl + (long long)c[j].o2 * pix) : f4zero();
+        v[j][2] = c[j].ok3 ? ldg4(vl + (long long)c[j].o3 * pix) : f4zero();
+        v[j][3] = c[j].ok4 ? ldg4(vl + (long long)c[j].o4 * pix) : f4zero();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p0 + j >= P) break;
+        const float lh = c[j].lh, lw = c[j].lw, hh = c[j].hh, hw = c[j].hw;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        const float4 tg = make_float4(g.x * a[j], g.y * a[j], g.z * a[j], g.w * a[j]);
+        if (active) {
+          if (c[j].ok1)
+            red_add_v4(gvl + (long long)c[j].o1 * pix, w1 * tg.x, w1 * tg.y, w1 * tg.z, w1 * tg.w);
+          if (c[j].ok2)
+            red_add_v4(gvl + (long long)c[j].o2 * pix, w2 * tg.x, w2 * tg.y, w2 * tg.z, w2 * tg.w);
+          if (c[j].ok3)
+            red_add_v4(gvl + (long long)c[j].o3 * pix, w3 * tg.x, w3 * tg.y, w3 * tg.z, w3 * tg.w);
+          if (c[j].ok4)
+            red_add_v4(gvl + (long long)c[j].o4 * pix, w4 * tg.x, w4 * tg.y, w4 * tg.z, w4 * tg.w);
+        }
+        // val, d/dw, d/dh per channel (ms_deform_im2col_cuda.cuh:116-158)
+        float4 val = f4zero(), dw = f4zero(), dh = f4zero();
+        val = f4fma(w1, v[j][0], val);
+        val = f4fma(w2, v[j][1], val);
+        val = f4fma(w3, v[j][2], val);
+        val = f4fma(w4, v[j][3], val);
+        dw = f4fma(-hh, v[j][0], dw);
+        dw = f4fma(hh, v[j][1], dw);
+        dw = f4fma(-lh, v[j][2], dw);
+        dw = f4fma(lh, v[j][3], dw);
+        dh = f4fma(-hw, v[j][0], dh);
+        dh = f4fma(-lw, v[j][1], dh);
+        dh = f4fma(hw, v[j][2], dh);
+        dh = f4fma(lw, v[j][3], dh);
+        float ga = f4dot(g, val);
+        float gw = f4dot(tg, dw) * (float)W;
+        float gh = f4dot(tg, dh) * (float)H;
+#pragma unroll
+        for (int o = TPH / 2; o > 0; o >>= 1) {
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+          gw += __shfl_xor_sync(0xffffffffu, gw, o);
+          gh += __shfl_xor_sync(0xffffffffu, gh, o);
+        }
+        if (active && c4 == 0) {
+          const long long pi = qm * L * P + l * P + p0 + j;
+          gattn[pi] = ga;  // exactly 0 when the point is out of range (all corners masked)
+          *reinterpret_cast<float2*>(gloc + 2 * pi) = make_float2(gw, gh);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernels (any D, fp32 or fp64): the reference's one-thread-per-output-channel shape for
+// forward, one warp per (b, q, m) for backward.  Used for the reference's own unit-test shapes
+// (D = 2, 30, 71, 1025, ... ; fp64 gradcheck) — not on the configured hot path (D = 8 / 16).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct CornerT {
+  bool inr, ok1, ok2, ok3, ok4;
+  long long o1, o2, o3, o4;
+  T lh, lw, hh, hw;
+};
+
+template <typename T>
+__device__ __forceinline__ T mul_rn(T a, T b);
+template <>
+__device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <>
+__device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T sub_rn(T a, T b);
+template <>
+__device__ __forceinline__ float sub_rn<float>(float a, float b) { return __fsub_rn(a, b); }
+template <>
+__device__ __forceinline__ double sub_rn<double>(double a, double b) { return __dsub_rn(a, b); }
+
+template <typename T>
+__device__ __forceinline__ CornerT<T> make_corner_t(T loc_x, T loc_y, int H, int W) {
+  CornerT<T> c;
+  const T h_im = sub_rn<T>(mul_rn<T>(loc_y, (T)H), (T)0.5);
+  const T w_im = sub_rn<T>(mul_rn<T>(loc_x, (T)W), (T)0.5);
+  c.inr = (h_im > (T)-1) && (w_im > (T)-1) && (h_im < (T)H) && (w_im < (T)W);
+  const T hf = floor(h_im), wf = floor(w_im);
+  const int h_low = (int)hf, w_low = (int)wf;
+  c.lh = h_im - hf;
+  c.lw = w_im - wf;
+  c.hh = (T)1 - c.lh;
+  c.hw = (T)1 - c.lw;
+  const bool hl = h_low >= 0, hh_ = h_low + 1 <= H - 1, wl = w_low >= 0, wh = w_low + 1 <= W - 1;
+  c.ok1 = c.inr && hl && wl;
+  c.ok2 = c.inr && hl && wh;
+  c.ok3 = c.inr && hh_ && wl;
+  c.ok4 = c.inr && hh_ && wh;
+  c.o1 = (long long)h_low * W + w_low;
+  c.o2 = c.o1 + 1;
+  c.o3 = c.o1 + W;
+  c.o4 = c.o3 + 1;
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                        const T* __restrict__ attn, T* __restrict__ out, int S, int M, int D,
+                        int L, int Lq, int P, long long total) {
+  __shared__ LevelTable lv;
+  load_levels(lv, shapes, lsi, L);
+  const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % D);
+  const long long qm = idx / D;
+  const int m = (int)(qm % M);
+  const long long b = (qm / M) / Lq;
+  const long long pix = (long long)M * D;
+  const T* vb = value + b * S * pix + m * D + c;
+  const T* locp = loc + qm * L * P * 2;
+  const T* attp = attn + qm * L * P;
+  T acc = 0;
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const T* vl = vb + (long long)lv.start[l] * pix;
+    for (int p = 0; p < P; ++p) {
+      const int pi = l * P + p;
+      const CornerT<T> k = make_corner_t<T>(locp[2 * pi], locp[2 * pi + 1], H, W);
+      if (!k.inr) continue;
+      const T v1 = k.ok1 ? vl[k.o1 * pix] : (T)0, v2 = k.ok2 ? vl[k.o2 * pix] : (T)0,
+              v3 = k.ok3 ? vl[k.o3 * pix] : (T)0, v4 = k.ok4 ? vl[k.o4 * pix] : (T)0;
+      const T w1 = k.hh * k.hw, w2 = k.hh * k.lw, w3 = k.lh * k.hw, w4 = k.lh * k.lw;
+      acc += (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4) * attp[pi];
+    }
+  }
+  out[idx] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                        const T* __restrict__ attn, const T* __restrict__ gout,
+                        T* __restrict__ gvalue, T* __restrict__ gloc, T* __restrict__ gattn, int S,
+                        int M, int D, int L, int Lq, int P, long long n_qm) {
+  __shared__ LevelTable lv;
+  load_levels(lv, shapes, lsi, L);
+  const int lane = threadIdx.x & 31;
+  const long long qm = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;  // warp-uniform
+  if (qm >= n_qm) return;
+  const int m = (int)(qm % M);
+  const long long b = (qm / M) / Lq;
+  const long long pix = (long long)M * D;
+  const long long voff = b * S * pix + m * D;
+  const T* locp = loc + qm * L * P * 2;
+  const T* attp = attn + qm * L * P;
+  const T* gp = gout + qm * D;
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const long long lo = voff + (long long)lv.start[l] * pix;
+    for (int p = 0; p < P; ++p) {
+      const int pi = l * P + p;
+      const CornerT<T> k = make_corner_t<T>(locp[2 * pi], locp[2 * pi + 1], H, W);
+      const T a = attp[pi];
+      T ga = 0, gw = 0, gh = 0;
+      if (k.inr) {
+        const T w1 = k.hh * k.hw, w2 = k.hh * k.lw, w3 = k.lh * k.hw, w4 = k.lh * k.lw;
+        for (int c = lane; c < D; c += 32) {
+          const T g = gp[c];
+          const T tg = g * a;
+          T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+          if (k.ok1) { v1 = value[lo + k.o1 * pix + c]; atomicAdd(gvalue + lo + k.o1 * pix + c, w1 * tg); }
+          if (k.ok2) { v2 = value[lo + k.o2 * pix + c]; atomicAdd(gvalue + lo + k.o2 * pix + c, w2 * tg); }
+          if (k.ok3) { v3 = value[lo + k.o3 * pix + c]; atomicAdd(gvalue + lo + k.o3 * pix + c, w3 * tg); }
+          if (k.ok4) { v4 = value[lo + k.o4 * pix + c]; atomicAdd(gvalue + lo + k.o4 * pix + c, w4 * tg); }
+          ga += g * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+          gw += tg * (-k.hh * v1 + k.hh * v2 - k.lh * v3 + k.lh * v4);
+          gh += tg * (-k.hw * v1 - k.lw * v2 + k.hw * v3 + k.lw * v4);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        gw += __shfl_xor_sync(0xffffffffu, gw, o);
+        gh += __shfl_xor_sync(0xffffffffu, gh, o);
+      }
+      if (lane == 0) {
+        const long long o = qm * L * P + pi;
+        gattn[o] = ga;
+        gloc[2 * o] = gw * (T)W;
+        gloc[2 * o + 1] = gh * (T)H;
+      }
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_common(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                 const void* attn, int64_t N, int64_t S, int64_t M, int64_t D, int64_t L,
+                 int64_t Lq, int64_t P, int64_t im2col_step, int dtype) {
+  DDF_CHECK_ARG(dtype == 0 || dtype == 1, "ms_deform_attn: dtype must be 0 (f32) or 1 (f64)");
+  DDF_CHECK_ARG(N >= 0 && S >= 0 && M > 0 && D > 0 && L > 0 && Lq >= 0 && P > 0,
+                "ms_deform_attn: bad sizes N=%lld S=%lld M=%lld D=%lld L=%lld Lq=%lld P=%lld",
+                (long long)N, (long long)S, (long long)M, (long long)D, (long long)L,
+                (long long)Lq, (long long)P);
+  DDF_CHECK_ARG(L <= kMaxLevels, "ms_deform_attn: at most %d levels supported, got %lld",
+                kMaxLevels, (long long)L);
+  DDF_CHECK_ARG(im2col_step > 0, "ms_deform_attn: im2col_step must be positive");
+  if (N > 0) {
+    const int64_t step = N < im2col_step ? N : im2col_step;
+    // reference: ms_deform_attn_cuda.cu:52
+    DDF_CHECK_ARG(N % step == 0, "batch(%lld) must divide im2col_step(%lld)", (long long)N,
+                  (long long)step);
+  }
+  if (N * Lq > 0)
+    DDF_CHECK_ARG(value && shapes && lsi && loc && attn, "ms_deform_attn: null input pointer");
+  DDF_CHECK_ARG(N * S * M * D < (1ll << 40) && N * Lq * M * L * P < (1ll << 40),
+                "ms_deform_attn: problem too large");
+  return DDF_OK;
+}
+
+}  // namespace
+
+#define MSDA_DISPATCH_TPH(tph, CALL)      \
+  switch (tph) {                          \
+    case 1: { constexpr int TPH = 1; CALL; } break;   \
+    case 2: { constexpr int TPH = 2; CALL; } break;   \
+    case 4: { constexpr int TPH = 4; CALL; } break;   \
+    case 8: { constexpr int TPH = 8; CALL; } break;   \
+    case 16: { constexpr int TPH = 16; CALL; } break; \
+    case 32: { constexpr int TPH = 32; CALL; } break; \
+  }
+
+extern "C" int ddf_ms_deform_attn_forward(const void* value, const int64_t* spatial_shapes,
+                                          const int64_t* level_start_index,
+                                          const void* sampling_loc, const void* attn_weight,
+                                          void* output, int64_t N, int64_t S, int64_t M, int64_t D,
+                                          int64_t L, int64_t Lq, int64_t P, int64_t im2col_step,
+                                          int dtype, void* stream_) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S,
+                        M, D, L, Lq, P, im2col_step, dtype);
+  if (rc) return rc;
+  if (N * Lq == 0) return DDF_OK;
+  DDF_CHECK_ARG(output != nullptr, "ms_deform_attn_forward: null output");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int tph = (int)(D / 4);
+  const bool fast = dtype == 0 && D % 4 == 0 && (tph & (tph - 1)) == 0 && tph <= 32 &&
+                    aligned16(value) && aligned16(output) && aligned16(sampling_loc);
+  if (fast) {
+    const long long total = N * Lq * M * tph;
+    const unsigned grid = (unsigned)ddf::cdiv(total, kThreads);
+    MSDA_DISPATCH_TPH(tph, (msda_fwd_vec4_kernel<TPH><<<grid, kThreads, 0, stream>>>(
+                               (const float*)value, spatial_shapes, level_start_index,
+                               (const float*)sampling_loc, (const float*)attn_weight,
+                               (float*)output, (int)S, (int)M, (int)L, (int)Lq, (int)P, total)));
+  } else {
+    const long long total = N * Lq * M * D;
+    const unsigned grid = (unsigned)ddf::cdiv(total, kThreads);
+    if (dtype == 0)
+      msda_fwd_generic_kernel<float><<<grid, kThreads, 0, stream>>>(
+          (const float*)value, spatial_shapes, level_start_index, (const float*)sampling_loc,
+          (const float*)attn_weight, (float*)output, (int)S, (int)M, (int)D, (int)L, (int)Lq,
+          (int)P, total);
+    else
+      msda_fwd_generic_kernel<double><<<grid, kThreads, 0, stream>>>(
+          (const double*)value, spatial_shapes, level_start_index, (const double*)sampling_loc,
+          (const double*)attn_weight, (double*)output, (int)S, (int)M, (int)D, (int)L, (int)Lq,
+          (int)P, total);
+  }
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+extern "C" int ddf_ms_deform_attn_backward(const void* value, const int64_t* spatial_shapes,
+                                           const int64_t* level_start_index,
+                                           const void* sampling_loc, const void* attn_weight,
+                                           const void* grad_output, void* grad_value,
+                                           void* grad_sampling_loc, void* grad_attn_weight,
+                                           int64_t N, int64_t S, int64_t M, int64_t D, int64_t L,
+                                           int64_t Lq, int64_t P, int64_t im2col_step, int dtype,
+                                           void* stream_) {
+  int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S,
+                        M, D, L, Lq, P, im2col_step, dtype);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t esz = dtype == 0 ? 4 : 8;
+  if (N * S > 0) {
+    DDF_CHECK_ARG(grad_value != nullptr, "ms_deform_attn_backward: null grad_value");
+    DDF_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)(N * S * M * D) * esz, stream));
+  }
+  if (N * Lq == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_output && grad_sampling_loc && grad_attn_weight,
+                "ms_deform_attn_backward: null pointer");
+  const int tph = (int)(D / 4);
+  const bool fast = dtype == 0 && D % 4 == 0 && (tph & (tph - 1)) == 0 && tph <= 32 &&
+                    aligned16(value) && aligned16(grad_output) && aligned16(grad_value) &&
+                    aligned16(sampling_loc) && aligned16(grad_sampling_loc);
+  if (fast) {
+    const long long total = N * Lq * M * tph;
+    const unsigned grid = (unsigned)ddf::cdiv(total, kThreads);
+    MSDA_DISPATCH_TPH(tph, (msda_bwd_vec4_kernel<TPH><<<grid, kThreads, 0, stream>>>(
+                               (const float*)value, spatial_shapes, level_start_index,
+                               (const float*)sampling_loc, (const float*)attn_weight,
+                               (const float*)grad_output, (float*)grad_value,
+                               (float*)grad_sampling_loc, (float*)grad_attn_weight, (int)S, (int)M,
+                               (int)L, (int)Lq, (int)P, total)));
+  } else {
+    const long long n_qm = N * Lq * M;
+    const unsigned grid = (unsigned)ddf::cdiv(n_qm * 32, kThreads);
+    if (dtype == 0)
+      msda_bwd_generic_kernel<float><<<grid, kThreads, 0, stream>>>(
+          (const float*)value, spatial_shapes, level_start_index, (const float*)sampling_loc,
+          (const float*)attn_weight, (const float*)grad_output, (float*)grad_value,
+          (float*)grad_sampling_loc, (float*)grad_attn_weight, (int)S, (int)M, (int)D, (int)L,
+          (int)Lq, (int)P, n_qm);
+    else
+      msda_bwd_generic_kernel<double><<<grid, kThreads, 0, stream>>>(
+          (const double*)value, spatial_shapes, level_start_index, (const double*)sampling_loc,
+          (const double*)attn_weight, (const double*)grad_output, (double*)grad_value,
+          (double*)grad_sampling_loc, (double*)grad_attn_weight, (int)S, (int)M, (int)D, (int)L,
+          (int)Lq, (int)P, n_qm);
+  }
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}

@@ -1,0 +1,71 @@
+"""ctypes loader for the C-ABI library ``libddf_b200.so`` (see include/ddf_b200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails, a RuntimeError is raised,
+mirroring the reference's AT_ASSERTM / TORCH_CHECK behaviour at the pybind boundary.
+"""
+import ctypes
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libddf_b200.so")
+
+_lib = None
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+
+# name -> argtypes; restype is int (error code) unless listed in _RESTYPES
+_SIGNATURES = {
+    "ddf_abi_version": [],
+    "ddf_compiled_arch": [],
+    "ddf_ms_deform_attn_forward": [c_ptr] * 6 + [c_i64] * 8 + [c_int, c_ptr],
+    "ddf_ms_deform_attn_backward": [c_ptr] * 9 + [c_i64] * 8 + [c_int, c_ptr],
+}
+_RESTYPES = {}
+
+
+def exported_symbols():
+    """Every symbol include/ddf_b200.h declares (tests check the library exports them all)."""
+    return ["ddf_last_error"] + sorted(_SIGNATURES)
+
+
+def get_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "ddf_b200: %s not found - build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'`. There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.ddf_last_error.restype = ctypes.c_char_p
+        lib.ddf_last_error.argtypes = []
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = get_lib().ddf_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")  # reference: ms_deform_attn.h:38

@@ -1,0 +1,89 @@
+"""Multi-scale deformable attention op: the reference's ``MSDeformAttnFunction`` name and call
+signature (``<proj>/models/model_utils/ops/functions/ms_deform_attn_func.py:21-38``) on top of
+``ddf_ms_deform_attn_forward/backward`` (include/ddf_b200.h).
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import lib as _lib
+
+_DTYPES = {torch.float32: 0, torch.float64: 1}
+
+
+def _check_inputs(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    # reference asserts: ms_deform_attn_cuda.cu:28-38
+    names = ("value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight")
+    for n, t in zip(names, (value, spatial_shapes, level_start_index, sampling_locations,
+                            attention_weights)):
+        if not t.is_contiguous():
+            raise RuntimeError("%s tensor has to be contiguous" % n)
+        if not t.is_cuda:
+            raise RuntimeError("%s must be a CUDA tensor" % n)
+    if value.dtype not in _DTYPES:
+        raise RuntimeError("ms_deform_attn: unsupported dtype %s" % value.dtype)
+    if sampling_locations.dtype != value.dtype or attention_weights.dtype != value.dtype:
+        raise RuntimeError("ms_deform_attn: value / sampling_loc / attn_weight dtypes differ")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("ms_deform_attn: spatial_shapes / level_start_index must be int64")
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                           im2col_step):
+    """Same contract as ``MSDA.ms_deform_attn_forward`` (ops/src/ms_deform_attn.h:20-39)."""
+    _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.get_lib().ddf_ms_deform_attn_forward(
+            _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
+            _lib.ptr(sampling_loc), _lib.ptr(attn_weight), _lib.ptr(out), N, S, M, D, L, Lq, P,
+            int(im2col_step), _DTYPES[value.dtype], _lib.current_stream())
+    _lib.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                            grad_output, im2col_step):
+    """Same contract as ``MSDA.ms_deform_attn_backward`` (ops/src/ms_deform_attn.h:41-62)."""
+    _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    if not grad_output.is_contiguous():
+        raise RuntimeError("grad_output tensor has to be contiguous")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    grad_value = torch.empty_like(value)  # zeroed inside the library call
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        rc = _lib.get_lib().ddf_ms_deform_attn_backward(
+            _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
+            _lib.ptr(sampling_loc), _lib.ptr(attn_weight), _lib.ptr(grad_output),
+            _lib.ptr(grad_value), _lib.ptr(grad_loc), _lib.ptr(grad_attn), N, S, M, D, L, Lq, P,
+            int(im2col_step), _DTYPES[value.dtype], _lib.current_stream())
+    _lib.check(rc, "ms_deform_attn_backward")
+    return grad_value, grad_loc, grad_attn
+
+
+class MSDeformAttnFunction(Function):
+    """Drop-in for the reference autograd Function (ms_deform_attn_func.py:21-38)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                        sampling_locations, attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = ms_deform_attn_backward(
+            value, shapes, lsi, loc, attn, grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None

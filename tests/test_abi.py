@@ -1,0 +1,48 @@
+"""CPU-side checks of the C-ABI boundary: the library loads and exports every symbol that
+include/ddf_b200.h declares; argument validation that needs no GPU returns error codes."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ddf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    from ddf_b200 import build, lib
+    build.build()
+    L = lib.get_lib()
+    syms = _header_symbols()
+    assert len(syms) >= 5
+    for s in syms:
+        assert hasattr(L, s), "libddf_b200.so does not export %s" % s
+    assert sorted(lib.exported_symbols()) == syms, "lib.py signatures out of sync with the header"
+    assert L.ddf_compiled_arch() == 100
+
+
+def test_msda_argument_validation_without_gpu():
+    from ddf_b200 import lib
+    L = lib.get_lib()
+    # batch 6 with im2col_step 4 -> reference asserts batch % min(batch, step) == 0
+    rc = L.ddf_ms_deform_attn_forward(None, None, None, None, None, None, 6, 10, 8, 16, 1, 0, 4, 4, 0, None)
+    assert rc == 1 and b"must divide" in L.ddf_last_error()
+    rc = L.ddf_ms_deform_attn_forward(None, None, None, None, None, None, 6, 10, 8, 16, 1, 0, 4, 64, 7, None)
+    assert rc == 1 and b"dtype" in L.ddf_last_error()
+    # empty query set is a no-op
+    rc = L.ddf_ms_deform_attn_forward(None, None, None, None, None, None, 6, 10, 8, 16, 1, 0, 4, 64, 0, None)
+    assert rc == 0
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from ddf_b200.ops.msda import MSDeformAttnFunction
+    v = torch.zeros(1, 6, 2, 4)
+    with pytest.raises(RuntimeError):
+        MSDeformAttnFunction.apply(v, torch.tensor([[2, 3]]), torch.tensor([0]),
+                                   torch.zeros(1, 2, 2, 1, 4, 2), torch.zeros(1, 2, 2, 1, 4), 64)
