@@ -1,0 +1,399 @@
+// Sparse 3-D convolution (SubM / regular / inverse) forward, dgrad, wgrad for sm_100a — fp32 SIMT
+// implicit-GEMM kernels (the tcgen05 tf32 path for wide layers lives in sparse_conv_tc.cu).
+//
+// Replaces indiceConv / indiceConvBackward
+//   <TF>/ops/spconv/include/spconv/spconv_ops.h:260-361, 363-456
+// which run, per kernel offset, gather kernel -> cuBLAS mm_out -> scatter-add kernel (<=27 x 3
+// launches, every intermediate through HBM, plus an indiceNum D2H sync).  Here one launch per
+// conv: an output-stationary kernel walks the gather table G[N_out, K] built with the rulebook
+// (rulebook.cu), stages the gathered input rows and the filter slice of each offset in shared
+// memory and keeps the [rows x Cout] accumulator tile in registers; the output is written once.
+//   forward : out[o,:]  = sum_k in[G[o,k],:]   . W[k]        (W[k]: Cin x Cout)
+//   dgrad   : gin[i,:]  = sum_k gout[GT[i,k],:]. W[k]^T      (same kernel, transposed filters)
+//   wgrad   : gW[k]     = sum_{(i,o) in pairs[k]} in[i,:]^T gout[o,:]   (walks the pair lists)
+// The SubM centre tap needs no special case here (the reference treats arg-max offset as identity,
+// spconv_ops.h:271-303): its gather-table column is simply the identity.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int TM = 128;  // output rows per CTA
+constexpr int KC = 16;   // input channels per smem chunk
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel.  CO = padded output-channel tile (16/32/64/128), thread tile RM x 4.
+// ------------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(kThreads)
+spconv_gather_gemm_kernel(const float* __restrict__ feat, const float* __restrict__ filt,
+                          const int* __restrict__ table, const float* __restrict__ bias,
+                          float* __restrict__ out, int n_out, int kvol, int cin, int cout,
+                          int co_base) {
+  constexpr int TX = CO / 4;          // threads along channels
+  constexpr int TY = kThreads / TX;   // threads along rows
+  constexpr int RM = TM / TY;         // rows per thread
+  __shared__ float sA[TM][KC + 1];
+  __shared__ __align__(16) float sB[KC][CO];
+  __shared__ int sIdx[TM];
+  __shared__ int sAny;
+
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int row0 = blockIdx.x * TM;
+  float acc[RM][4];
+#pragma unroll
+  for (int r = 0; r < RM; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (int k = 0; k < kvol; ++k) {
+    __syncthreads();  // previous offset's sA/sB/sIdx fully consumed
+    if (threadIdx.x == 0) sAny = 0;
+    __syncthreads();
+    if (threadIdx.x < TM) {
+      const int o = row0 + threadIdx.x;
+      const int j = o < n_out ? table[(long long)o * kvol + k] : -1;
+      sIdx[threadIdx.x] = j;
+      if (j >= 0) sAny = 1;
+    }
+    __syncthreads();
+    if (!sAny) continue;  // no row of this tile has a neighbour at offset k
+    const float* wk = filt + (long long)k * cin * cout;
+    for (int c0 = 0; c0 < cin; c0 += KC) {
+      if (c0) __syncthreads();
+      // stage A: TM x KC gathered features (zeros for missing neighbours / channel tail)
+      for (int e = threadIdx.x; e < TM * KC; e += kThreads) {
+        const int r = e / KC, c = e % KC;
+        const int j = sIdx[r];
+        sA[r][c] = (j >= 0 && c0 + c < cin) ? __ldg(feat + (long long)j * cin + c0 + c) : 0.f;
+      }
+      // stage B: KC x CO filter slice
+      for (int e = threadIdx.x; e < KC * CO; e += kThreads) {
+        const int c = e / CO, n = e % CO;
+        sB[c][n] = (c0 + c < cin && co_base + n < cout)
+                       ? __ldg(wk + (long long)(c0 + c) * cout + co_base + n)
+                       : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        const float4 b = *reinterpret_cast<const float4*>(&sB[c][tx * 4]);
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          const float a = sA[ty * RM + r][c];
+          acc[r][0] = fmaf(a, b.x, acc[r][0]);
+          acc[r][1] = fmaf(a, b.y, acc[r][1]);
+          acc[r][2] = fmaf(a, b.z, acc[r][2]);
+          acc[r][3] = fmaf(a, b.w, acc[r][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RM; ++r) {
+    const int o = row0 + ty * RM + r;
+    if (o >= n_out) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = co_base + tx * 4 + c;
+      if (n < cout) out[(long long)o * cout + n] = acc[r][c] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: grid (kvol, S).  CTA (k, s) reduces its slice of pair list k into a Cin x Cout register
+// tile (in CI_T x CO_T blocks) and adds it to gW[k] with red.global.
+// ------------------------------------------------------------------------------------------------
+constexpr int WP = 32;  // pairs per smem stage
+
+template <int CI_T, int CO_T>
+__global__ void __launch_bounds__(kThreads)
+spconv_wgrad_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
+                    const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
+                    int cin, int cout, int inverse, float* __restrict__ gw) {
+  // thread tile: (CI_T*CO_T)/256 outputs, laid out TI x TJ
+  constexpr int TJ = 4;
+  constexpr int TXN = CO_T / TJ;           // threads along cout
+  constexpr int TYN = kThreads / TXN;      // threads along cin
+  constexpr int TI = CI_T / TYN;
+  static_assert(TI >= 1, "tile too small");
+  __shared__ float sX[WP][CI_T + 1];
+  __shared__ __align__(16) float sG[WP][CO_T];
+  const int k = blockIdx.x;
+  const int nk = num[k];
+  if (nk <= 0) return;
+  const int S = gridDim.y;
+  const int per = (nk + S - 1) / S;
+  const int s0 = blockIdx.y * per, s1 = min(nk, s0 + per);
+  if (s0 >= s1) return;
+  const int* pin = pairs + ((long long)k * 2 + (inverse ? 1 : 0)) * pair_stride;
+  const int* pout = pairs + ((long long)k * 2 + (inverse ? 0 : 1)) * pair_stride;
+  const int tx = threadIdx.x % TXN, ty = threadIdx.x / TXN;
+
+  for (int ci0 = 0; ci0 < cin; ci0 += CI_T) {
+    for (int co0 = 0; co0 < cout; co0 += CO_T) {
+      float acc[TI][TJ];
+#pragma unroll
+      for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j] = 0.f;
+      for (int p0 = s0; p0 < s1; p0 += WP) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < WP * CI_T; e += kThreads) {
+          const int p = e / CI_T, c = e % CI_T;
+          float v = 0.f;
+          if (p0 + p < s1 && ci0 + c < cin) v = __ldg(feat + (long long)pin[p0 + p] * cin + ci0 + c);
+          sX[p][c] = v;
+        }
+        for (int e = threadIdx.x; e < WP * CO_T; e += kThreads) {
+          const int p = e / CO_T, c = e % CO_T;
+          float v = 0.f;
+          if (p0 + p < s1 && co0 + c < cout) v = __ldg(gout + (long long)pout[p0 + p] * cout + co0 + c);
+          sG[p][c] = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int p = 0; p < WP; ++p) {
+          const float4 g = *reinterpret_cast<const float4*>(&sG[p][tx * TJ]);
+#pragma unroll
+          for (int i = 0; i < TI; ++i) {
+            const float x = sX[p][ty * TI + i];
+            acc[i][0] = fmaf(x, g.x, acc[i][0]);
+            acc[i][1] = fmaf(x, g.y, acc[i][1]);
+            acc[i][2] = fmaf(x, g.z, acc[i][2]);
+            acc[i][3] = fmaf(x, g.w, acc[i][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TI; ++i) {
+        const int ci = ci0 + ty * TI + i;
+        if (ci >= cin) continue;
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+          const int co = co0 + tx * TJ + j;
+          if (co < cout) atomicAdd(gw + ((long long)k * cin + ci) * cout + co, acc[i][j]);
+        }
+      }
+    }
+  }
+}
+
+// filters [K, Cin, Cout] -> [K, Cout, Cin]
+__global__ void __launch_bounds__(kThreads)
+transpose_filters_kernel(const float* __restrict__ w, float* __restrict__ wt, int kvol, int cin,
+                         int cout) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long per = (long long)cin * cout;
+  if (t >= per * kvol) return;
+  const int k = (int)(t / per);
+  const int r = (int)(t % per);
+  const int co = r / cin, ci = r % cin;
+  wt[t] = w[(long long)k * per + (long long)ci * cout + co];
+}
+
+// pair lists -> row-major table: table[row_of(col_sel)][k] = row_of(1-col_sel)
+__global__ void __launch_bounds__(kThreads)
+pairs_to_table_kernel(const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
+                      int kvol, int key_col, int* __restrict__ table) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= (long long)kvol * pair_stride) return;
+  const int k = (int)(t / pair_stride), s = (int)(t % pair_stride);
+  if (s >= num[k]) return;
+  const int key = pairs[((long long)k * 2 + key_col) * pair_stride + s];
+  const int val = pairs[((long long)k * 2 + (1 - key_col)) * pair_stride + s];
+  table[(long long)key * kvol + k] = val;
+}
+
+int launch_gather_gemm(const float* feat, const float* filt, const int* table, const float* bias,
+                       float* out, int64_t n_out, int kvol, int cin, int cout,
+                       cudaStream_t stream) {
+  if (n_out == 0) return DDF_OK;
+  const unsigned grid = (unsigned)ddf::cdiv(n_out, TM);
+  for (int co_base = 0; co_base < cout; co_base += 128) {
+    const int rem = cout - co_base;
+    if (rem > 64)
+      spconv_gather_gemm_kernel<128><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+                                                                    (int)n_out, kvol, cin, cout, co_base);
+    else if (rem > 32)
+      spconv_gather_gemm_kernel<64><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+                                                                   (int)n_out, kvol, cin, cout, co_base);
+    else if (rem > 16)
+      spconv_gather_gemm_kernel<32><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+                                                                   (int)n_out, kvol, cin, cout, co_base);
+    else
+      spconv_gather_gemm_kernel<16><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+                                                                   (int)n_out, kvol, cin, cout, co_base);
+  }
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+}  // namespace
+
+// ---- fast path (tables from the rulebook build) ------------------------------------------------
+// out [n_out, cout] = conv(features [n_in, cin], filters [K, cin, cout]) through gather_table
+// [n_out, K]; bias optional ([cout] or NULL).  Fully overwrites out.
+extern "C" int ddf_sparse_conv_forward(const float* features, const float* filters,
+                                       const int* gather_table, const float* bias, float* out,
+                                       int64_t n_out, int64_t kvol, int64_t cin, int64_t cout,
+                                       void* stream) {
+  DDF_CHECK_ARG(n_out >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_forward: bad sizes");
+  if (n_out == 0) return DDF_OK;
+  DDF_CHECK_ARG(features && filters && gather_table && out, "sparse_conv_forward: null pointer");
+  return launch_gather_gemm(features, filters, gather_table, bias, out, n_out, (int)kvol, (int)cin,
+                            (int)cout, (cudaStream_t)stream);
+}
+
+// grad_in [n_in, cin] = sum_k grad_out[scatter_table[i,k]] . W[k]^T ; filters_t_ws: device scratch
+// of K*cin*cout floats (receives the transposed filters).
+extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters,
+                                     const int* scatter_table, float* grad_in, float* filters_t_ws,
+                                     int64_t n_in, int64_t kvol, int64_t cin, int64_t cout,
+                                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_dgrad: bad sizes");
+  if (n_in == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_out && filters && scatter_table && grad_in && filters_t_ws,
+                "sparse_conv_dgrad: null pointer");
+  const long long nw = kvol * cin * cout;
+  transpose_filters_kernel<<<(unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream>>>(
+      filters, filters_t_ws, (int)kvol, (int)cin, (int)cout);
+  // dgrad is a conv with Cin<->Cout swapped through the transposed table
+  return launch_gather_gemm(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in,
+                            (int)kvol, (int)cout, (int)cin, stream);
+}
+
+// grad_filters [K, cin, cout] (zeroed inside) from the reference-format pair lists.
+extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_out,
+                                     const int* indice_pairs, const int* indice_num,
+                                     int64_t pair_stride, float* grad_filters, int64_t kvol,
+                                     int64_t cin, int64_t cout, int inverse, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(kvol > 0 && cin > 0 && cout > 0 && pair_stride >= 0, "sparse_conv_wgrad: bad sizes");
+  DDF_CHECK_ARG(grad_filters != nullptr, "sparse_conv_wgrad: null grad_filters");
+  DDF_CUDA(cudaMemsetAsync(grad_filters, 0, sizeof(float) * (size_t)(kvol * cin * cout), stream));
+  if (pair_stride == 0) return DDF_OK;
+  DDF_CHECK_ARG(features && grad_out && indice_pairs && indice_num, "sparse_conv_wgrad: null pointer");
+  // enough (k, slice) CTAs for ~4 waves; slices bounded so each still has >= ~256 pairs
+  int S = (int)ddf::cdiv(4 * ddf::kNumSM, kvol);
+  const int maxS = (int)ddf::cdiv(pair_stride, 256);
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  dim3 grid((unsigned)kvol, (unsigned)S);
+  if (cin <= 32 && cout <= 32)
+    spconv_wgrad_kernel<32, 32><<<grid, kThreads, 0, stream>>>(
+        features, grad_out, indice_pairs, indice_num, (int)pair_stride, (int)cin, (int)cout, inverse, grad_filters);
+  else
+    spconv_wgrad_kernel<64, 64><<<grid, kThreads, 0, stream>>>(
+        features, grad_out, indice_pairs, indice_num, (int)pair_stride, (int)cin, (int)cout, inverse, grad_filters);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// ---- drop-in path (reference-format rulebook only) ---------------------------------------------
+// Same contract as sparse_conv_ext.indice_conv_fp32 (spconv_ops.h:260-361): the gather table is
+// rebuilt from the pair lists into table_ws ([n_out, K] int32 scratch).
+extern "C" int ddf_indice_conv(const float* features, const float* filters, const int* indice_pairs,
+                               const int* indice_num, int64_t pair_stride, float* out,
+                               int64_t n_out, int64_t kvol, int64_t cin, int64_t cout, int inverse,
+                               int subm, int* table_ws, void* stream_) {
+  (void)subm;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n_out >= 0 && kvol > 0 && cin > 0 && cout > 0, "indice_conv: bad sizes");
+  if (n_out == 0) return DDF_OK;
+  DDF_CHECK_ARG(features && filters && indice_pairs && indice_num && out && table_ws,
+                "indice_conv: null pointer");
+  DDF_CUDA(cudaMemsetAsync(table_ws, 0xff, sizeof(int) * (size_t)(n_out * kvol), stream));
+  const long long np = kvol * pair_stride;
+  if (np > 0)
+    pairs_to_table_kernel<<<(unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream>>>(
+        indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 0 : 1, table_ws);
+  return launch_gather_gemm(features, filters, table_ws, nullptr, out, n_out, (int)kvol, (int)cin,
+                            (int)cout, stream);
+}
+
+// Same contract as sparse_conv_ext.indice_conv_backward_fp32 (spconv_ops.h:363-456).
+// table_ws: [n_in, K] int32 scratch; filters_t_ws: K*cin*cout floats scratch.
+extern "C" int ddf_indice_conv_backward(const float* features, const float* filters,
+                                        const float* grad_out, const int* indice_pairs,
+                                        const int* indice_num, int64_t pair_stride, float* grad_in,
+                                        float* grad_filters, int64_t n_in, int64_t kvol,
+                                        int64_t cin, int64_t cout, int inverse, int subm,
+                                        int* table_ws, float* filters_t_ws, void* stream_) {
+  (void)subm;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "indice_conv_backward: bad sizes");
+  int rc = ddf_sparse_conv_wgrad(features, grad_out, indice_pairs, indice_num, pair_stride,
+                                 grad_filters, kvol, cin, cout, inverse, stream_);
+  if (rc || n_in == 0) return rc;
+  DDF_CHECK_ARG(grad_in && table_ws && filters_t_ws, "indice_conv_backward: null pointer");
+  DDF_CUDA(cudaMemsetAsync(table_ws, 0xff, sizeof(int) * (size_t)(n_in * kvol), stream));
+  const long long np = kvol * pair_stride;
+  if (np > 0)
+    pairs_to_table_kernel<<<(unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream>>>(
+        indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 1 : 0, table_ws);
+  return ddf_sparse_conv_dgrad(grad_out, filters, table_ws, grad_in, filters_t_ws, n_in, kvol, cin,
+                               cout, stream_);
+}
+
+// ---- dense(): sparse [N, C] + indices [N, 4] -> dense NCDHW ------------------------------------
+// Replaces SparseConvTensor.dense() = scatter_nd + permute(...).contiguous()
+//   <TF>/ops/spconv/structure.py:5-18, 55-64 (zeros + index_put + a full permute copy).
+namespace {
+__global__ void __launch_bounds__(kThreads)
+dense_scatter_kernel(const float* __restrict__ feat, const int* __restrict__ indices, int n, int C,
+                     int D, int H, int W, float* __restrict__ out) {
+  // one warp per voxel row keeps the feature read coalesced; the NCDHW write is a C-strided scatter
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int row = (int)(t >> 5), lane = (int)(t & 31);
+  if (row >= n) return;
+  const int4 c = reinterpret_cast<const int4*>(indices)[row];
+  const long long plane = (long long)D * H * W;
+  const long long base = (long long)c.x * C * plane + ((long long)c.y * H + c.z) * W + c.w;
+  for (int ch = lane; ch < C; ch += 32) out[base + ch * plane] = feat[(long long)row * C + ch];
+}
+
+__global__ void __launch_bounds__(kThreads)
+dense_gather_kernel(const float* __restrict__ gdense, const int* __restrict__ indices, int n, int C,
+                    int D, int H, int W, float* __restrict__ gfeat) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int row = (int)(t >> 5), lane = (int)(t & 31);
+  if (row >= n) return;
+  const int4 c = reinterpret_cast<const int4*>(indices)[row];
+  const long long plane = (long long)D * H * W;
+  const long long base = (long long)c.x * C * plane + ((long long)c.y * H + c.z) * W + c.w;
+  for (int ch = lane; ch < C; ch += 32) gfeat[(long long)row * C + ch] = gdense[base + ch * plane];
+}
+}  // namespace
+
+// out [B, C, D, H, W] (zeroed inside, then scattered).
+extern "C" int ddf_sparse_to_dense(const float* features, const int* indices, float* out,
+                                   int64_t n, int64_t C, int64_t B, int64_t D, int64_t H,
+                                   int64_t W, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "sparse_to_dense: bad sizes");
+  DDF_CHECK_ARG(out != nullptr, "sparse_to_dense: null out");
+  DDF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(B * C * D * H * W), stream));
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(features && indices, "sparse_to_dense: null pointer");
+  dense_scatter_kernel<<<(unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream>>>(
+      features, indices, (int)n, (int)C, (int)D, (int)H, (int)W, out);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// backward of dense(): grad_features [n, C] = grad_dense at the active cells.
+extern "C" int ddf_dense_to_sparse(const float* grad_dense, const int* indices,
+                                   float* grad_features, int64_t n, int64_t C, int64_t B,
+                                   int64_t D, int64_t H, int64_t W, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "dense_to_sparse: bad sizes");
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_dense && indices && grad_features, "dense_to_sparse: null pointer");
+  dense_gather_kernel<<<(unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream>>>(
+      grad_dense, indices, (int)n, (int)C, (int)D, (int)H, (int)W, grad_features);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}

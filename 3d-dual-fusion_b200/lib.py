@@ -22,8 +22,22 @@ _SIGNATURES = {
     "ddf_compiled_arch": [],
     "ddf_ms_deform_attn_forward": [c_ptr] * 6 + [c_i64] * 8 + [c_int, c_ptr],
     "ddf_ms_deform_attn_backward": [c_ptr] * 9 + [c_i64] * 8 + [c_int, c_ptr],
+    "ddf_hard_voxelize_workspace_bytes": [c_i64] * 3,
+    "ddf_hard_voxelize": [c_ptr] * 7 + [c_i64] * 4 + [c_ptr, c_i64, c_ptr],
+    "ddf_dynamic_voxelize": [c_ptr] * 4 + [c_i64] * 2 + [c_ptr],
+    "ddf_indice_pairs_workspace_bytes": [c_i64, c_i64] + [c_ptr] * 6 + [c_int],
+    "ddf_subm_indice_pairs": [c_ptr, c_i64, c_i64] + [c_ptr] * 8 + [c_i64, c_ptr],
+    "ddf_conv_count_outputs": [c_ptr, c_i64, c_i64] + [c_ptr] * 8 + [c_i64, c_ptr],
+    "ddf_conv_indice_pairs": [c_ptr, c_i64, c_i64] + [c_ptr] * 6 + [c_i64] + [c_ptr] * 6 + [c_i64, c_ptr],
+    "ddf_indice_conv": [c_ptr] * 4 + [c_i64, c_ptr] + [c_i64] * 4 + [c_int, c_int, c_ptr, c_ptr],
+    "ddf_indice_conv_backward": [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i64] * 4 + [c_int, c_int, c_ptr, c_ptr, c_ptr],
+    "ddf_sparse_conv_forward": [c_ptr] * 5 + [c_i64] * 4 + [c_ptr],
+    "ddf_sparse_conv_dgrad": [c_ptr] * 5 + [c_i64] * 4 + [c_ptr],
+    "ddf_sparse_conv_wgrad": [c_ptr] * 4 + [c_i64, c_ptr] + [c_i64] * 3 + [c_int, c_ptr],
+    "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
+    "ddf_dense_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
 }
-_RESTYPES = {}
+_RESTYPES = {"ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64}
 
 
 def exported_symbols():

@@ -1,0 +1,96 @@
+"""autograd Functions with the reference's names (TransFusion/mmdet3d/ops/spconv/functional.py:20-98)
+plus the table-driven Function the SparseConvolution module uses on the hot path."""
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+class _PairConv(Function):
+    INVERSE = False
+    SUBM = False
+
+    @classmethod
+    def _fwd(cls, ctx, features, filters, indice_pairs, indice_pair_num, num_activate_out):
+        ctx.save_for_backward(indice_pairs, indice_pair_num, features, filters)
+        return ops.indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out,
+                               cls.INVERSE, cls.SUBM)
+
+    @classmethod
+    def _bwd(cls, ctx, grad_output):
+        indice_pairs, indice_pair_num, features, filters = ctx.saved_tensors
+        input_bp, filters_bp = ops.indice_conv_backward(features, filters, grad_output, indice_pairs,
+                                                        indice_pair_num, cls.INVERSE, cls.SUBM)
+        return input_bp, filters_bp, None, None, None
+
+
+class SparseConvFunction(_PairConv):
+    @staticmethod
+    def forward(ctx, features, filters, indice_pairs, indice_pair_num, num_activate_out):
+        return SparseConvFunction._fwd(ctx, features, filters, indice_pairs, indice_pair_num,
+                                       num_activate_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return SparseConvFunction._bwd(ctx, grad_output)
+
+
+class SparseInverseConvFunction(_PairConv):
+    INVERSE = True
+
+    @staticmethod
+    def forward(ctx, features, filters, indice_pairs, indice_pair_num, num_activate_out):
+        return SparseInverseConvFunction._fwd(ctx, features, filters, indice_pairs, indice_pair_num,
+                                              num_activate_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return SparseInverseConvFunction._bwd(ctx, grad_output)
+
+
+class SubMConvFunction(_PairConv):
+    SUBM = True
+
+    @staticmethod
+    def forward(ctx, features, filters, indice_pairs, indice_pair_num, num_activate_out):
+        return SubMConvFunction._fwd(ctx, features, filters, indice_pairs, indice_pair_num,
+                                     num_activate_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return SubMConvFunction._bwd(ctx, grad_output)
+
+
+class TableConvFunction(Function):
+    """Hot-path conv: forward through the gather table, dgrad through the scatter table, wgrad over
+    the pair lists. ``bias`` may be None."""
+
+    @staticmethod
+    def forward(ctx, features, filters, bias, rulebook, num_activate_out):
+        features = features.contiguous()
+        filters = filters.contiguous()
+        ctx.rulebook = rulebook
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(features, filters)
+        return ops.sparse_conv_forward(features, filters, rulebook.gather_table, bias, num_activate_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        features, filters = ctx.saved_tensors
+        rb = ctx.rulebook
+        grad_output = grad_output.contiguous()
+        gin, gw = ops.sparse_conv_backward(features, filters, grad_output, rb.scatter_table,
+                                           rb.indice_pairs, rb.indice_pair_num,
+                                           ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        gb = grad_output.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gin, gw, gb, None, None
+
+
+indice_conv = SparseConvFunction.apply
+indice_inverse_conv = SparseInverseConvFunction.apply
+indice_subm_conv = SubMConvFunction.apply
+table_conv = TableConvFunction.apply

@@ -72,6 +72,126 @@ int ddf_ms_deform_attn_backward(const void* value, const int64_t* spatial_shapes
                                 int64_t D, int64_t L, int64_t Lq, int64_t P,
                                 int64_t im2col_step, int dtype, void* stream);
 
+/* ---- Voxelization ---------------------------------------------------------------------
+ * Replaces mmdet3d.ops.voxel.voxel_layer.hard_voxelize / dynamic_voxelize
+ *   reference: TransFusion/mmdet3d/ops/voxel/src/voxelization.h:51-69 (hard), :71-86 (dynamic)
+ *              GPU path voxelization_cuda.cu:184-326, CPU path voxelization_cpu.cpp:105-142
+ *   Python caller: TransFusion/mmdet3d/ops/voxel/voxelize.py:41-58 (_Voxelization.forward)
+ *
+ *   points                [N, F] float32, F >= 3, xyz first
+ *   voxels                [max_voxels, max_points, F] float32  rows [0, voxel_num) fully written
+ *   coors                 [max_voxels, 3] int32 (z, y, x)      rows [0, voxel_num) written
+ *   num_points_per_voxel  [max_voxels] int32                   rows [0, voxel_num) written
+ *   voxel_num             [1] int32 DEVICE  (the reference returns it as a host int after a sync;
+ *                         here the caller decides when to read it)
+ *   voxel_size_host[3] (x,y,z), coors_range_host[6] (xyz min, xyz max): HOST float arrays
+ *   workspace: device scratch of ddf_hard_voxelize_workspace_bytes(N, max_points, max_voxels) bytes
+ * Voxel order = first-seen order of the points, in-voxel order = input order, processing stops at
+ * the first point that would open voxel number max_voxels (bit-exact with the reference).
+ * dynamic_voxelize writes (-1,-1,-1) for out-of-range points (CPU semantics, cpu.cpp:33-38).
+ */
+int64_t ddf_hard_voxelize_workspace_bytes(int64_t num_points, int64_t max_points,
+                                          int64_t max_voxels);
+
+int ddf_hard_voxelize(const float* points, float* voxels, int* coors, int* num_points_per_voxel,
+                      int* voxel_num, const float* voxel_size_host, const float* coors_range_host,
+                      int64_t num_points, int64_t num_features, int64_t max_points,
+                      int64_t max_voxels, void* workspace, int64_t workspace_bytes, void* stream);
+
+int ddf_dynamic_voxelize(const float* points, int* coors, const float* voxel_size_host,
+                         const float* coors_range_host, int64_t num_points, int64_t num_features,
+                         void* stream);
+
+/* ---- Sparse-convolution rulebook -------------------------------------------------------
+ * Replaces sparse_conv_ext.get_indice_pairs_3d
+ *   reference: TransFusion/mmdet3d/ops/spconv/include/spconv/spconv_ops.h:27-141 (getIndicePair<3>),
+ *              kernels include/spconv/indice.cu.h:24-234, CPU semantics include/spconv/geometry.h:24-297
+ *   Python caller: TransFusion/mmdet3d/ops/spconv/ops.py:46-105 (get_indice_pairs)
+ *
+ *   indices        [N, 4] int32 (b, z, y, x), 16-byte aligned
+ *   geometry       HOST int64[3] arrays (z, y, x order) exactly as the reference passes them; for
+ *                  SubM stride is forced to 1 and padding to ksize/2 (spconv_ops.h:76-79)
+ *   indice_pairs   [K, 2, N] int32: row 0 = input rows (ASCENDING inside an offset), row 1 = output
+ *                  rows, tail filled with -1;  indice_num [K] int32
+ *   out_indices    [num_act_out, 4] int32, sorted by flat (b,z,y,x) (reference GPU order)
+ *   gather_table   optional [N_out, K] int32: input row feeding output o through offset k, or -1
+ *   scatter_table  optional [N_in,  K] int32: output row fed by input j through offset k, or -1
+ * Regular convs are two calls on the same stream + workspace: ddf_conv_count_outputs (candidate
+ * cells -> bitmap -> count, written to a DEVICE int), then — after the caller sized its outputs —
+ * ddf_conv_indice_pairs.  Transposed (deconv) rulebooks are not generated (no 3D-DF backbone uses
+ * them); SparseInverseConv reuses a saved rulebook with inverse=1 below.
+ */
+int64_t ddf_indice_pairs_workspace_bytes(int64_t num_in, int64_t batch_size,
+                                         const int64_t* out_spatial_shape,
+                                         const int64_t* spatial_shape, const int64_t* ksize,
+                                         const int64_t* stride, const int64_t* padding,
+                                         const int64_t* dilation, int subm);
+
+int ddf_subm_indice_pairs(const int* indices, int64_t num_in, int64_t batch_size,
+                          const int64_t* spatial_shape, const int64_t* ksize,
+                          const int64_t* dilation, int* indice_pairs, int* indice_num,
+                          int* gather_table, int* scatter_table, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+int ddf_conv_count_outputs(const int* indices, int64_t num_in, int64_t batch_size,
+                           const int64_t* out_spatial_shape, const int64_t* spatial_shape,
+                           const int64_t* ksize, const int64_t* stride, const int64_t* padding,
+                           const int64_t* dilation, int* num_act_out, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+
+int ddf_conv_indice_pairs(const int* indices, int64_t num_in, int64_t batch_size,
+                          const int64_t* out_spatial_shape, const int64_t* spatial_shape,
+                          const int64_t* ksize, const int64_t* stride, const int64_t* padding,
+                          const int64_t* dilation, int64_t num_act_out, int* out_indices,
+                          int* indice_pairs, int* indice_num, int* gather_table,
+                          int* scatter_table, void* workspace, int64_t workspace_bytes,
+                          void* stream);
+
+/* ---- Sparse convolution ----------------------------------------------------------------
+ * Replaces sparse_conv_ext.indice_conv_fp32 / indice_conv_backward_fp32
+ *   reference: spconv_ops.h:260-361 (indiceConv), :363-456 (indiceConvBackward)
+ *   Python callers: TransFusion/mmdet3d/ops/spconv/functional.py:20-98
+ * features [N_in, Cin], filters [K, Cin, Cout] (= the reference's [kd,kh,kw,Cin,Cout] viewed flat),
+ * out [N_out, Cout]; all float32, fully overwritten.
+ * Drop-in entry points (ddf_indice_conv*) take the reference-format rulebook and the same
+ * inverse / subm flags; scratch: table_ws = int32 [rows, K], filters_t_ws = float [K*Cin*Cout].
+ * Fast entry points (ddf_sparse_conv_*) take the row-major tables of the rulebook build directly.
+ */
+int ddf_indice_conv(const float* features, const float* filters, const int* indice_pairs,
+                    const int* indice_num, int64_t pair_stride, float* out, int64_t n_out,
+                    int64_t kvol, int64_t cin, int64_t cout, int inverse, int subm, int* table_ws,
+                    void* stream);
+
+int ddf_indice_conv_backward(const float* features, const float* filters, const float* grad_out,
+                             const int* indice_pairs, const int* indice_num, int64_t pair_stride,
+                             float* grad_in, float* grad_filters, int64_t n_in, int64_t kvol,
+                             int64_t cin, int64_t cout, int inverse, int subm, int* table_ws,
+                             float* filters_t_ws, void* stream);
+
+int ddf_sparse_conv_forward(const float* features, const float* filters, const int* gather_table,
+                            const float* bias, float* out, int64_t n_out, int64_t kvol,
+                            int64_t cin, int64_t cout, void* stream);
+
+int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters, const int* scatter_table,
+                          float* grad_in, float* filters_t_ws, int64_t n_in, int64_t kvol,
+                          int64_t cin, int64_t cout, void* stream);
+
+int ddf_sparse_conv_wgrad(const float* features, const float* grad_out, const int* indice_pairs,
+                          const int* indice_num, int64_t pair_stride, float* grad_filters,
+                          int64_t kvol, int64_t cin, int64_t cout, int inverse, void* stream);
+
+/* ---- dense(): sparse -> dense NCDHW ----------------------------------------------------
+ * Replaces SparseConvTensor.dense() / scatter_nd (TransFusion/mmdet3d/ops/spconv/structure.py:5-18,
+ * 55-64): out [B, C, D, H, W] zeroed inside then written directly in NCDHW (no permute copy);
+ * ddf_dense_to_sparse is its backward (gather of grad_dense at the active cells).
+ */
+int ddf_sparse_to_dense(const float* features, const int* indices, float* out, int64_t n,
+                        int64_t C, int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
+
+int ddf_dense_to_sparse(const float* grad_dense, const int* indices, float* grad_features,
+                        int64_t n, int64_t C, int64_t B, int64_t D, int64_t H, int64_t W,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

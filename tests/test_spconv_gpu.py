@@ -1,0 +1,182 @@
+"""GPU parity for the sparse-conv path through the C-ABI: rulebooks bit-exact vs the oracle
+(canonical order: outputs sorted by flat index = reference GPU order, pair slots ascending in the
+input row = reference CPU order), conv fwd / dgrad / wgrad and dense() within 1e-3 rel (fp32),
+plus size-independent properties at nuScenes scale."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from test_oracle_spconv import GEOMS, random_voxels
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_rulebook_bit_exact(geom):
+    from ddf_b200.ops.spconv import ops
+    from oracle import spconv as osp
+    shape, ks, st, pad, dil, subm = geom
+    idx = random_voxels(900, 2, shape, seed=3)
+    o_out, o_pairs, o_num, o_shape = osp.get_indice_pairs(idx, 2, shape, ks, st, pad, dil, subm, order="gpu")
+    rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, dil, 0, subm, False)
+    assert rb.out_spatial_shape == o_shape
+    assert np.array_equal(rb.indice_pair_num.cpu().numpy(), o_num)
+    assert np.array_equal(rb.outids.cpu().numpy(), o_out)
+    assert np.array_equal(rb.indice_pairs.cpu().numpy(), o_pairs)
+    # the reference-named wrapper returns the same three tensors
+    outids, pairs, num = ops.get_indice_pairs(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, dil, 0, subm)
+    assert np.array_equal(pairs.cpu().numpy(), o_pairs) and np.array_equal(num.cpu().numpy(), o_num)
+    # row-major tables agree with the pair lists
+    G = rb.gather_table.cpu().numpy()
+    GT = rb.scatter_table.cpu().numpy()
+    G2 = np.full_like(G, -1)
+    GT2 = np.full_like(GT, -1)
+    for k in range(o_pairs.shape[0]):
+        i, o = o_pairs[k, 0, :o_num[k]], o_pairs[k, 1, :o_num[k]]
+        G2[o, k] = i
+        GT2[i, k] = o
+    assert np.array_equal(G, G2) and np.array_equal(GT, GT2)
+
+
+@pytest.mark.parametrize("geom", GEOMS[:6])
+@pytest.mark.parametrize("chan", [(5, 16), (16, 32), (64, 64), (128, 128), (20, 136)])
+def test_conv_fwd_bwd_vs_oracle(geom, chan):
+    from ddf_b200.ops.spconv import functional as Fsp, ops
+    from oracle import spconv as osp
+    shape, ks, st, pad, dil, subm = geom
+    cin, cout = chan
+    rng = np.random.default_rng(11)
+    idx = random_voxels(1500, 2, shape, seed=4)
+    o_out, o_pairs, o_num, _ = osp.get_indice_pairs(idx, 2, shape, ks, st, pad, dil, subm, order="gpu")
+    feat = rng.standard_normal((len(idx), cin)).astype(np.float32)
+    w = (rng.standard_normal((*ks, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    go = rng.standard_normal((len(o_out), cout)).astype(np.float32)
+    ref = osp.indice_conv(feat, w, o_pairs, o_num, len(o_out))
+    ref_gi, ref_gw = osp.indice_conv_backward(feat, w, go, o_pairs, o_num)
+
+    rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, dil, 0, subm, False)
+    # (a) hot path: table-driven Function
+    f = torch.from_numpy(feat).cuda().requires_grad_()
+    wt = torch.from_numpy(w).cuda().requires_grad_()
+    out = Fsp.table_conv(f, wt, None, rb, len(o_out))
+    out.backward(torch.from_numpy(go).cuda())
+    assert rel_err(out.detach().cpu().numpy(), ref) < 1e-4
+    assert rel_err(f.grad.cpu().numpy(), ref_gi) < 1e-4
+    assert rel_err(wt.grad.cpu().numpy(), ref_gw) < 1e-4
+    # (b) drop-in path: reference-named Functions on the reference-format rulebook
+    f2 = torch.from_numpy(feat).cuda().requires_grad_()
+    w2 = torch.from_numpy(w).cuda().requires_grad_()
+    fn = Fsp.indice_subm_conv if subm else Fsp.indice_conv
+    out2 = fn(f2, w2, rb.indice_pairs, rb.indice_pair_num, len(o_out))
+    out2.backward(torch.from_numpy(go).cuda())
+    assert rel_err(out2.detach().cpu().numpy(), ref) < 1e-4
+    assert rel_err(f2.grad.cpu().numpy(), ref_gi) < 1e-4
+    assert rel_err(w2.grad.cpu().numpy(), ref_gw) < 1e-4
+
+
+def test_inverse_conv_roundtrip_shapes_and_values():
+    """SparseInverseConv3d reuses the saved rulebook with the roles swapped (conv.py:156-163)."""
+    import ddf_b200.ops.spconv as sp
+    from oracle import spconv as osp
+    shape = [11, 40, 40]
+    idx = random_voxels(800, 2, shape, seed=9)
+    rng = np.random.default_rng(2)
+    feat = rng.standard_normal((len(idx), 16)).astype(np.float32)
+    x = sp.SparseConvTensor(torch.from_numpy(feat).cuda(), torch.from_numpy(idx).cuda(), shape, 2)
+    down = sp.SparseConv3d(16, 32, 3, 2, padding=1, bias=False, indice_key="cp1").cuda()
+    up = sp.SparseInverseConv3d(32, 16, 3, indice_key="cp1", bias=False).cuda()
+    y = down(x)
+    z = up(y)
+    assert z.features.shape == (len(idx), 16) and z.spatial_shape == shape
+    assert torch.equal(z.indices, x.indices)
+    o_out, o_pairs, o_num, _ = osp.get_indice_pairs(idx, 2, shape, [3] * 3, [2] * 3, [1] * 3, [1] * 3, False, order="gpu")
+    ref_y = osp.indice_conv(feat, down.weight.detach().cpu().numpy(), o_pairs, o_num, len(o_out))
+    ref_z = osp.indice_conv(ref_y, up.weight.detach().cpu().numpy(), o_pairs, o_num, len(idx), inverse=True)
+    assert rel_err(z.features.detach().cpu().numpy(), ref_z) < 1e-4
+
+
+def test_dense_matches_oracle_and_backward():
+    import ddf_b200.ops.spconv as sp
+    from oracle import spconv as osp
+    shape = [2, 18, 18]
+    idx = random_voxels(300, 2, shape, seed=5)
+    feat = np.random.default_rng(1).standard_normal((len(idx), 128)).astype(np.float32)
+    f = torch.from_numpy(feat).cuda().requires_grad_()
+    x = sp.SparseConvTensor(f, torch.from_numpy(idx).cuda(), shape, 2)
+    d = x.dense()
+    assert np.array_equal(d.detach().cpu().numpy(), osp.dense(feat, idx, shape, 2))
+    g = torch.randn_like(d)
+    d.backward(g)
+    want = g.cpu().numpy()[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]]
+    assert np.array_equal(f.grad.cpu().numpy(), want)
+    # scatter_nd keeps the reference contract too
+    s = sp.scatter_nd(torch.from_numpy(idx).cuda().long(), f.detach(), [2, *shape, 128])
+    assert torch.equal(s.permute(0, 4, 1, 2, 3), d.detach())
+
+
+def test_empty_sparse_tensor():
+    import ddf_b200.ops.spconv as sp
+    x = sp.SparseConvTensor(torch.zeros(0, 16).cuda(), torch.zeros(0, 4, dtype=torch.int32).cuda(), [11, 40, 40], 2)
+    y = sp.SubMConv3d(16, 16, 3, bias=False).cuda()(x)
+    assert y.features.shape == (0, 16)
+    z = sp.SparseConv3d(16, 32, 3, 2, padding=1, bias=False).cuda()(x)
+    assert z.features.shape == (0, 32) and z.indices.shape == (0, 4)
+
+
+def test_full_size_properties_nuscenes_grid():
+    """~100k voxels on the [41,1440,1440] grid, batch 2: properties that need no oracle."""
+    import ddf_b200.ops.spconv as sp
+    from ddf_b200.ops.spconv import ops
+    from ddf_b200.ops.voxel import Voxelization
+    vox = Voxelization(synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 120000).eval()
+    coors = []
+    for b in range(2):
+        _, c, _ = vox(torch.from_numpy(synth.lidar_points(250000, seed=20 + b)).cuda())
+        coors.append(torch.nn.functional.pad(c, (1, 0), value=b))
+    idx = torch.cat(coors).contiguous()
+    n = idx.shape[0]
+    shape = [41, 1440, 1440]
+    rb = ops.build_rulebook(idx, 2, shape, 3, 1, 1, 1, 0, True, False)
+    num = rb.indice_pair_num.cpu().numpy()
+    assert num[13] == n                       # centre tap = identity (spconv_ops.h:271-303 relies on it)
+    assert np.array_equal(num, num[::-1])     # SubM pair sets are mirror-symmetric
+    p = rb.indice_pairs
+    for k in (0, 5, 12):
+        a = p[k, :, :num[k]]
+        b = p[26 - k, :, :num[k]].flip(0)     # swapped roles
+        sa = a[:, torch.argsort(a[0] * (n + 1) + a[1])]
+        sb = b[:, torch.argsort(b[0] * (n + 1) + b[1])]
+        assert torch.equal(sa, sb)
+        assert bool((a[0][1:] > a[0][:-1]).all())  # ascending input rows
+    # identity kernel returns the input; all-ones 1->1 kernel counts neighbours
+    x = sp.SparseConvTensor(torch.randn(n, 16, device="cuda"), idx, shape, 2)
+    conv = sp.SubMConv3d(16, 16, 3, bias=False).cuda()
+    with torch.no_grad():
+        conv.weight.zero_()
+        conv.weight[1, 1, 1] = torch.eye(16)
+    y = conv(x)
+    assert torch.equal(y.features, x.features)
+    ones = sp.SparseConvTensor(torch.ones(n, 1, device="cuda"), idx, shape, 2)
+    c1 = sp.SubMConv3d(1, 1, 3, bias=False).cuda()
+    with torch.no_grad():
+        c1.weight.fill_(1.0)
+    cnt = c1(ones).features[:, 0]
+    assert torch.equal(cnt, (rb.gather_table >= 0).sum(1).float())
+    # strided conv: outputs sorted & unique, every input reaches >= 1 output, linearity
+    down = sp.SparseConv3d(16, 32, 3, 2, padding=1, bias=False).cuda()
+    z = down(x)
+    o = z.indices.long()
+    flat = ((o[:, 0] * 21 + o[:, 1]) * 720 + o[:, 2]) * 720 + o[:, 3]
+    assert z.spatial_shape == [21, 720, 720] and bool((flat[1:] > flat[:-1]).all())
+    x2 = sp.SparseConvTensor(torch.randn(n, 16, device="cuda"), idx, shape, 2)
+    x12 = sp.SparseConvTensor(x.features + 3 * x2.features, idx, shape, 2)
+    lhs = down(x12).features
+    rhs = z.features + 3 * down(x2).features
+    assert (lhs - rhs).abs().max() < 1e-3 * rhs.abs().max()

@@ -1,0 +1,84 @@
+"""GPU parity (bit-exact): ddf_hard_voxelize / ddf_dynamic_voxelize through the reference-named
+Voxelization module vs the C oracle, plus properties at full nuScenes / 200k-point sizes."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(pts, voxel_size, pc_range, max_points, max_voxels):
+    from ddf_b200.ops.voxel import Voxelization
+    m = Voxelization(voxel_size, pc_range, max_points, max_voxels).eval()
+    v, c, n = m(torch.from_numpy(pts).cuda())
+    return v.cpu().numpy(), c.cpu().numpy(), n.cpu().numpy()
+
+
+CASES = [
+    dict(n=20000, kind="lidar", max_points=10, max_voxels=120000),
+    dict(n=20000, kind="uniform", max_points=10, max_voxels=120000),
+    dict(n=60000, kind="lidar", max_points=3, max_voxels=5000),
+    dict(n=5000, kind="uniform", max_points=1, max_voxels=100),
+    dict(n=1, kind="lidar", max_points=10, max_voxels=10),
+    dict(n=2049, kind="lidar", max_points=10, max_voxels=2049),
+    dict(n=262144, kind="lidar", max_points=10, max_voxels=120000),  # nuScenes 10-sweep size
+]
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_hard_voxelize_bit_exact_vs_oracle(c):
+    from oracle import voxel
+    pts = synth.lidar_points(c["n"], seed=1) if c["kind"] == "lidar" else synth.uniform_points(c["n"], synth.NUSC_RANGE, seed=2)
+    v, co, n = run_cuda(pts, synth.NUSC_VOXEL, synth.NUSC_RANGE, c["max_points"], c["max_voxels"])
+    ov, oc, on = voxel.hard_voxelize(pts, synth.NUSC_VOXEL, synth.NUSC_RANGE, c["max_points"], c["max_voxels"])
+    assert len(co) == len(oc)
+    assert np.array_equal(co, oc)
+    assert np.array_equal(n, on)
+    assert np.array_equal(v, ov)
+
+
+def test_known_answer_vector_of_reference_test():
+    np.random.seed(0)
+    pts = np.random.rand(1000, 4).astype(np.float32)
+    v, c, n = run_cuda(pts, [0.5, 0.5, 0.5], [0, -40, -3, 70.4, 40, 1], 1000, 20000)
+    expected = np.array([[7, 81, 1], [6, 81, 0], [7, 80, 1], [6, 81, 1], [7, 81, 0], [6, 80, 1], [7, 80, 0], [6, 80, 0]])
+    assert np.array_equal(c, expected)
+    assert np.array_equal(n, [120, 121, 127, 134, 115, 127, 125, 131])
+
+
+def test_dynamic_voxelize_and_kitti_grid():
+    from ddf_b200.ops.voxel import Voxelization
+    from oracle import voxel
+    pts = synth.uniform_points(16384, synth.KITTI_RANGE, seed=4, nfeat=4)
+    co = Voxelization(synth.KITTI_VOXEL, synth.KITTI_RANGE, -1)(torch.from_numpy(pts).cuda()).cpu().numpy()
+    assert np.array_equal(co, voxel.dynamic_voxelize(pts, synth.KITTI_VOXEL, synth.KITTI_RANGE))
+    v, c, n = run_cuda(pts, synth.KITTI_VOXEL, synth.KITTI_RANGE, 5, 16000)
+    ov, oc, on = voxel.hard_voxelize(pts, synth.KITTI_VOXEL, synth.KITTI_RANGE, 5, 16000)
+    assert np.array_equal(c, oc) and np.array_equal(n, on) and np.array_equal(v, ov)
+
+
+def test_full_size_properties_200k():
+    """BASELINE config 5 (200k-point sweep): size-independent properties."""
+    pts = synth.lidar_points(200000, seed=7)
+    v, c, n = run_cuda(pts, synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 160000)
+    # every voxel coordinate unique, counts in [1, 10], stored points fall in their voxel
+    keys = (c[:, 0].astype(np.int64) * 1440 + c[:, 1]) * 1440 + c[:, 2]
+    assert len(np.unique(keys)) == len(keys)
+    assert n.min() >= 1 and n.max() <= 10
+    lo = np.array(synth.NUSC_RANGE[:3], np.float32)
+    vs = np.array(synth.NUSC_VOXEL, np.float32)
+    first = v[:, 0, :3]
+    cc = np.floor((first - lo) / vs).astype(np.int32)[:, ::-1]
+    assert np.array_equal(cc, c)
+    # unused slots are zero, idempotence: voxelizing the stored first points reproduces coors order
+    mask = np.arange(10)[None, :] >= n[:, None]
+    assert not v[mask].any()
+    v2, c2, n2 = run_cuda(np.ascontiguousarray(v[:, 0, :]), synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 160000)
+    assert np.array_equal(c2, c) and (n2 == 1).all()
+
+
+def test_empty_input():
+    v, c, n = run_cuda(np.zeros((0, 5), np.float32), synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 100)
+    assert v.shape == (0, 10, 5) and c.shape == (0, 3) and n.shape == (0,)
