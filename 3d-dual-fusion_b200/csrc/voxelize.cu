@@ -123,7 +123,7 @@ vox_rank_kernel(const int* __restrict__ is_first, const int* __restrict__ rank, 
   if (i == 0) {
     const int total = rank[n];
     *voxel_num = total < max_voxels ? total : max_voxels;
-    if (total <= max_voxels) *cut = INT_MAX;
+    if (total <= max_voxels) *cut = n;  // no cut-off: every real index (< n) passes, the empty-slot sentinel does not
   }
   if (i >= n || !is_first[i]) return;
   const int r = rank[i];
