@@ -1,6 +1,8 @@
 // Library-level entry points: error string, ABI version.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ddf {
@@ -13,10 +15,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace ddf
 
 extern "C" {
 const char* ddf_last_error(void) { return ddf::get_error(); }
 int ddf_abi_version(void) { return 1; }
 int ddf_compiled_arch(void) { return 100; }
+int64_t ddf_launch_count(int reset) {
+  long long v = ddf::g_launches.load();
+  if (reset) ddf::g_launches.store(0);
+  return v;
+}
 }

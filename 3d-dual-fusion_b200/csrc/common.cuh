@@ -16,6 +16,9 @@ constexpr int kNumSM = 148;  // B200
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// bookkeeping for bench.py's gpu_launches: every kernel launch of this library is counted
+void note_launches(int n);
+
 }  // namespace ddf
 
 #define DDF_CHECK_ARG(cond, ...)   \
@@ -36,6 +39,12 @@ static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b;
   } while (0)
 
 #define DDF_LAUNCH_CHECK() DDF_CUDA(cudaGetLastError())
+// launch a kernel and count it:  DDF_LAUNCH(kernel<T>, grid, block, smem, stream, args...)
+#define DDF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  do {                                                     \
+    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);    \
+    ddf::note_launches(1);                                 \
+  } while (0)
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) {

@@ -447,20 +447,20 @@ extern "C" int ddf_ms_deform_attn_forward(const void* value, const int64_t* spat
   if (fast) {
     const long long total = N * Lq * M * tph;
     const unsigned grid = (unsigned)ddf::cdiv(total, kThreads);
-    MSDA_DISPATCH_TPH(tph, (msda_fwd_vec4_kernel<TPH><<<grid, kThreads, 0, stream>>>(
+    MSDA_DISPATCH_TPH(tph, DDF_LAUNCH(msda_fwd_vec4_kernel<TPH>, grid, kThreads, 0, stream, 
                                (const float*)value, spatial_shapes, level_start_index,
                                (const float*)sampling_loc, (const float*)attn_weight,
-                               (float*)output, (int)S, (int)M, (int)L, (int)Lq, (int)P, total)));
+                               (float*)output, (int)S, (int)M, (int)L, (int)Lq, (int)P, total));
   } else {
     const long long total = N * Lq * M * D;
     const unsigned grid = (unsigned)ddf::cdiv(total, kThreads);
     if (dtype == 0)
-      msda_fwd_generic_kernel<float><<<grid, kThreads, 0, stream>>>(
+      DDF_LAUNCH(msda_fwd_generic_kernel<float>, grid, kThreads, 0, stream, 
           (const float*)value, spatial_shapes, level_start_index, (const float*)sampling_loc,
           (const float*)attn_weight, (float*)output, (int)S, (int)M, (int)D, (int)L, (int)Lq,
           (int)P, total);
     else
-      msda_fwd_generic_kernel<double><<<grid, kThreads, 0, stream>>>(
+      DDF_LAUNCH(msda_fwd_generic_kernel<double>, grid, kThreads, 0, stream, 
           (const double*)value, spatial_shapes, level_start_index, (const double*)sampling_loc,
           (const double*)attn_weight, (double*)output, (int)S, (int)M, (int)D, (int)L, (int)Lq,
           (int)P, total);
@@ -496,23 +496,23 @@ extern "C" int ddf_ms_deform_attn_backward(const void* value, const int64_t* spa
   if (fast) {
     const long long total = N * Lq * M * tph;
     const unsigned grid = (unsigned)ddf::cdiv(total, kThreads);
-    MSDA_DISPATCH_TPH(tph, (msda_bwd_vec4_kernel<TPH><<<grid, kThreads, 0, stream>>>(
+    MSDA_DISPATCH_TPH(tph, DDF_LAUNCH(msda_bwd_vec4_kernel<TPH>, grid, kThreads, 0, stream, 
                                (const float*)value, spatial_shapes, level_start_index,
                                (const float*)sampling_loc, (const float*)attn_weight,
                                (const float*)grad_output, (float*)grad_value,
                                (float*)grad_sampling_loc, (float*)grad_attn_weight, (int)S, (int)M,
-                               (int)L, (int)Lq, (int)P, total)));
+                               (int)L, (int)Lq, (int)P, total));
   } else {
     const long long n_qm = N * Lq * M;
     const unsigned grid = (unsigned)ddf::cdiv(n_qm * 32, kThreads);
     if (dtype == 0)
-      msda_bwd_generic_kernel<float><<<grid, kThreads, 0, stream>>>(
+      DDF_LAUNCH(msda_bwd_generic_kernel<float>, grid, kThreads, 0, stream, 
           (const float*)value, spatial_shapes, level_start_index, (const float*)sampling_loc,
           (const float*)attn_weight, (const float*)grad_output, (float*)grad_value,
           (float*)grad_sampling_loc, (float*)grad_attn_weight, (int)S, (int)M, (int)D, (int)L,
           (int)Lq, (int)P, n_qm);
     else
-      msda_bwd_generic_kernel<double><<<grid, kThreads, 0, stream>>>(
+      DDF_LAUNCH(msda_bwd_generic_kernel<double>, grid, kThreads, 0, stream, 
           (const double*)value, spatial_shapes, level_start_index, (const double*)sampling_loc,
           (const double*)attn_weight, (const double*)grad_output, (double*)grad_value,
           (double*)grad_sampling_loc, (double*)grad_attn_weight, (int)S, (int)M, (int)D, (int)L,

@@ -294,7 +294,7 @@ int emit_pairs(const RbWs& w, const int* scatter_t, long long n, int kvol, int* 
   if (rc) return rc;
   // reference fills indicePairs with -1 (spconv_ops.h:55-57)
   DDF_CUDA(cudaMemsetAsync(indice_pairs, 0xff, (size_t)nk * 2 * sizeof(int), stream));
-  pairs_compact_kernel<<<(unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(pairs_compact_kernel, (unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream, 
       scatter_t, w.prefix, (int)n, kvol, indice_pairs, indice_num);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -341,11 +341,11 @@ extern "C" int ddf_subm_indice_pairs(const int* indices, int64_t num_in, int64_t
   DDF_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)slots * 8, stream));
   DDF_CUDA(cudaMemsetAsync(w.vals, 0xff, (size_t)slots * 4, stream));
   const int n = (int)num_in;
-  hash_insert_kernel<<<(unsigned)ddf::cdiv(n, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(hash_insert_kernel, (unsigned)ddf::cdiv(n, kThreads), kThreads, 0, stream, 
       indices, n, g, w.keys, w.vals, slots - 1);
   int* st = scatter_table ? scatter_table : w.scatter_t;
   const long long nk = (long long)n * g.kvol;
-  subm_tables_kernel<<<(unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(subm_tables_kernel, (unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream, 
       indices, n, g, w.keys, w.vals, slots - 1, st, gather_table, w.flags);
   DDF_LAUNCH_CHECK();
   return emit_pairs(w, st, n, g.kvol, indice_pairs, indice_num, stream);
@@ -373,9 +373,9 @@ extern "C" int ddf_conv_count_outputs(const int* indices, int64_t num_in, int64_
   DDF_CUDA(cudaMemsetAsync(w.bitmap, 0, (size_t)nwords * 4, stream));
   const long long nk = num_in * g.kvol;
   if (nk > 0)
-    conv_mark_kernel<<<(unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream>>>(
+    DDF_LAUNCH(conv_mark_kernel, (unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream, 
         indices, (int)num_in, g, w.bitmap);
-  popc_kernel<<<(unsigned)ddf::cdiv(nwords, kThreads), kThreads, 0, stream>>>(w.bitmap, nwords,
+  DDF_LAUNCH(popc_kernel, (unsigned)ddf::cdiv(nwords, kThreads), kThreads, 0, stream, w.bitmap, nwords,
                                                                                w.word_counts);
   rc = ddf::exclusive_scan_i32(w.word_counts, w.word_prefix, nwords, w.scan_ws, stream);
   if (rc) return rc;
@@ -413,12 +413,12 @@ extern "C" int ddf_conv_indice_pairs(const int* indices, int64_t num_in, int64_t
   const long long nk = (long long)n * g.kvol;
   if (gather_table && num_act_out > 0) {
     const long long ng = num_act_out * g.kvol;
-    fill_i32_kernel<<<(unsigned)ddf::cdiv(ng, kThreads), kThreads, 0, stream>>>(gather_table, ng, -1);
+    DDF_LAUNCH(fill_i32_kernel, (unsigned)ddf::cdiv(ng, kThreads), kThreads, 0, stream, gather_table, ng, -1);
   }
   int* st = scatter_table ? scatter_table : w.scatter_t;
-  conv_tables_kernel<<<(unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(conv_tables_kernel, (unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream, 
       indices, n, g, w.bitmap, w.word_prefix, st, gather_table, w.flags);
-  conv_outids_kernel<<<(unsigned)ddf::cdiv(nwords, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(conv_outids_kernel, (unsigned)ddf::cdiv(nwords, kThreads), kThreads, 0, stream, 
       w.bitmap, w.word_prefix, nwords, g, out_indices);
   DDF_LAUNCH_CHECK();
   return emit_pairs(w, st, n, g.kvol, indice_pairs, indice_num, stream);

@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int* __r
 
 int exclusive_scan_i32(const int* in, int* out, long long n, int* block_sums, cudaStream_t stream) {
   const int nb = (int)cdiv(n > 0 ? n : 1, kScanTile);
-  scan_reduce_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, block_sums);
-  scan_spine_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, nb);
-  scan_apply_kernel<<<nb, kScanThreads, 0, stream>>>(in, out, n, block_sums, nb);
+  DDF_LAUNCH(scan_reduce_kernel, nb, kScanThreads, 0, stream, in, n, block_sums);
+  DDF_LAUNCH(scan_spine_kernel, 1, kScanThreads, 0, stream, block_sums, nb);
+  DDF_LAUNCH(scan_apply_kernel, nb, kScanThreads, 0, stream, in, out, n, block_sums, nb);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }

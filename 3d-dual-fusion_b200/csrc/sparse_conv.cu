@@ -214,16 +214,16 @@ int launch_gather_gemm(const float* feat, const float* filt, const int* table, c
   for (int co_base = 0; co_base < cout; co_base += 128) {
     const int rem = cout - co_base;
     if (rem > 64)
-      spconv_gather_gemm_kernel<128><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+      DDF_LAUNCH(spconv_gather_gemm_kernel<128>, grid, kThreads, 0, stream, feat, filt, table, bias, out,
                                                                     (int)n_out, kvol, cin, cout, co_base);
     else if (rem > 32)
-      spconv_gather_gemm_kernel<64><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+      DDF_LAUNCH(spconv_gather_gemm_kernel<64>, grid, kThreads, 0, stream, feat, filt, table, bias, out,
                                                                    (int)n_out, kvol, cin, cout, co_base);
     else if (rem > 16)
-      spconv_gather_gemm_kernel<32><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+      DDF_LAUNCH(spconv_gather_gemm_kernel<32>, grid, kThreads, 0, stream, feat, filt, table, bias, out,
                                                                    (int)n_out, kvol, cin, cout, co_base);
     else
-      spconv_gather_gemm_kernel<16><<<grid, kThreads, 0, stream>>>(feat, filt, table, bias, out,
+      DDF_LAUNCH(spconv_gather_gemm_kernel<16>, grid, kThreads, 0, stream, feat, filt, table, bias, out,
                                                                    (int)n_out, kvol, cin, cout, co_base);
   }
   DDF_LAUNCH_CHECK();
@@ -258,7 +258,7 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
   DDF_CHECK_ARG(grad_out && filters && scatter_table && grad_in && filters_t_ws,
                 "sparse_conv_dgrad: null pointer");
   const long long nw = kvol * cin * cout;
-  transpose_filters_kernel<<<(unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, 
       filters, filters_t_ws, (int)kvol, (int)cin, (int)cout);
   // dgrad is a conv with Cin<->Cout swapped through the transposed table
   return launch_gather_gemm(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in,
@@ -283,10 +283,10 @@ extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_ou
   if (S < 1) S = 1;
   dim3 grid((unsigned)kvol, (unsigned)S);
   if (cin <= 32 && cout <= 32)
-    spconv_wgrad_kernel<32, 32><<<grid, kThreads, 0, stream>>>(
+    DDF_LAUNCH((spconv_wgrad_kernel<32, 32>), grid, kThreads, 0, stream, 
         features, grad_out, indice_pairs, indice_num, (int)pair_stride, (int)cin, (int)cout, inverse, grad_filters);
   else
-    spconv_wgrad_kernel<64, 64><<<grid, kThreads, 0, stream>>>(
+    DDF_LAUNCH((spconv_wgrad_kernel<64, 64>), grid, kThreads, 0, stream, 
         features, grad_out, indice_pairs, indice_num, (int)pair_stride, (int)cin, (int)cout, inverse, grad_filters);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -308,7 +308,7 @@ extern "C" int ddf_indice_conv(const float* features, const float* filters, cons
   DDF_CUDA(cudaMemsetAsync(table_ws, 0xff, sizeof(int) * (size_t)(n_out * kvol), stream));
   const long long np = kvol * pair_stride;
   if (np > 0)
-    pairs_to_table_kernel<<<(unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream>>>(
+    DDF_LAUNCH(pairs_to_table_kernel, (unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream, 
         indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 0 : 1, table_ws);
   return launch_gather_gemm(features, filters, table_ws, nullptr, out, n_out, (int)kvol, (int)cin,
                             (int)cout, stream);
@@ -332,7 +332,7 @@ extern "C" int ddf_indice_conv_backward(const float* features, const float* filt
   DDF_CUDA(cudaMemsetAsync(table_ws, 0xff, sizeof(int) * (size_t)(n_in * kvol), stream));
   const long long np = kvol * pair_stride;
   if (np > 0)
-    pairs_to_table_kernel<<<(unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream>>>(
+    DDF_LAUNCH(pairs_to_table_kernel, (unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream, 
         indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 1 : 0, table_ws);
   return ddf_sparse_conv_dgrad(grad_out, filters, table_ws, grad_in, filters_t_ws, n_in, kvol, cin,
                                cout, stream_);
@@ -378,7 +378,7 @@ extern "C" int ddf_sparse_to_dense(const float* features, const int* indices, fl
   DDF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(B * C * D * H * W), stream));
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(features && indices, "sparse_to_dense: null pointer");
-  dense_scatter_kernel<<<(unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(dense_scatter_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, 
       features, indices, (int)n, (int)C, (int)D, (int)H, (int)W, out);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -392,7 +392,7 @@ extern "C" int ddf_dense_to_sparse(const float* grad_dense, const int* indices,
   DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "dense_to_sparse: bad sizes");
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_dense && indices && grad_features, "dense_to_sparse: null pointer");
-  dense_gather_kernel<<<(unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(dense_gather_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, 
       grad_dense, indices, (int)n, (int)C, (int)D, (int)H, (int)W, grad_features);
   DDF_LAUNCH_CHECK();
   return DDF_OK;

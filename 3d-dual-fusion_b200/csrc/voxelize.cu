@@ -230,8 +230,7 @@ extern "C" int ddf_dynamic_voxelize(const float* points, int* coors, const float
   DDF_CHECK_ARG(num_points >= 0 && num_features >= 3, "dynamic_voxelize: need (N, >=3) points");
   if (num_points == 0) return DDF_OK;
   DDF_CHECK_ARG(points && coors, "dynamic_voxelize: null pointer");
-  dynamic_voxelize_kernel<<<(unsigned)ddf::cdiv(num_points, kThreads), kThreads, 0,
-                            (cudaStream_t)stream_>>>(points, coors, g, (int)num_points,
+  DDF_LAUNCH(dynamic_voxelize_kernel, (unsigned)ddf::cdiv(num_points, kThreads), kThreads, 0, (cudaStream_t)stream_, points, coors, g, (int)num_points,
                                                      (int)num_features);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -266,17 +265,17 @@ extern "C" int ddf_hard_voxelize(const float* points, float* voxels, int* coors,
   DDF_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)slots * sizeof(int), stream));
   DDF_CUDA(cudaMemsetAsync(w.lists, 0x7f, (size_t)slots * T * sizeof(int), stream));
   const unsigned nb = (unsigned)ddf::cdiv(n, kThreads);
-  vox_insert_kernel<<<nb, kThreads, 0, stream>>>(points, g, n, F, T, w.keys, slots - 1, w.lists,
+  DDF_LAUNCH(vox_insert_kernel, nb, kThreads, 0, stream, points, g, n, F, T, w.keys, slots - 1, w.lists,
                                                  w.slot);
-  vox_flag_first_kernel<<<nb, kThreads, 0, stream>>>(w.slot, w.lists, T, n, w.is_first);
+  DDF_LAUNCH(vox_flag_first_kernel, nb, kThreads, 0, stream, w.slot, w.lists, T, n, w.is_first);
   rc = ddf::exclusive_scan_i32(w.is_first, w.rank, n, w.scan_ws, stream);
   if (rc) return rc;
-  vox_rank_kernel<<<nb, kThreads, 0, stream>>>(w.is_first, w.rank, n, (int)max_voxels,
+  DDF_LAUNCH(vox_rank_kernel, nb, kThreads, 0, stream, w.is_first, w.rank, n, (int)max_voxels,
                                                w.first_point, w.cut, voxel_num);
   // upper bound on voxels = min(n, max_voxels); threads beyond the device-side voxel_num exit
   const long long vmax = n < max_voxels ? n : max_voxels;
   const long long total = vmax * T * F;
-  vox_gather_kernel<<<(unsigned)ddf::cdiv(total, kThreads), kThreads, 0, stream>>>(
+  DDF_LAUNCH(vox_gather_kernel, (unsigned)ddf::cdiv(total, kThreads), kThreads, 0, stream, 
       points, g, F, T, w.first_point, w.slot, w.keys, w.lists, w.cut, voxel_num, voxels, coors,
       num_points_per_voxel, total);
   DDF_LAUNCH_CHECK();

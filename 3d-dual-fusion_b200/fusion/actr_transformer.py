@@ -1,0 +1,231 @@
+"""Deformable fusion transformer of 3D-DF (<proj>/models/model_utils/actr_transformer.py):
+``DeformableTransformerACTR`` (:22-141), single-query encoder layer (:275-336), dual-query fusion
+encoder layer (:338-426; Voxel-RCNN applies the gate BEFORE the FFNs,
+VoxelRCNN/pcdet/models/model_utils/actr_transformer.py:497-513), encoder with the optional
+3D local self-attention in front of every layer (:428-511)."""
+import copy
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.init import normal_
+
+from .attentions import attn_dict
+from .ms_deform_attn import MSDeformAttn
+
+
+def _get_clones(module, N):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
+
+
+def _get_activation_fn(activation):
+    if activation == "relu":
+        return F.relu
+    if activation == "gelu":
+        return F.gelu
+    if activation == "glu":
+        return F.glu
+    raise RuntimeError("activation should be relu/gelu, not {}.".format(activation))
+
+
+def _with_pos(t, pos):
+    return t if pos is None else t + pos
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    """Single query stream ('lidar' / 'image' feature_modal)."""
+
+    def __init__(self, d_model=256, q_model=256, d_ffn=1024, dropout=0.1, activation="relu",
+                 n_levels=4, n_heads=8, n_points=4, hybrid_cfg=None):
+        super().__init__()
+        self.d_model = d_model
+        self.self_attn = MSDeformAttn(d_model, q_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _get_activation_fn(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    with_pos_embed = staticmethod(_with_pos)
+
+    def forward_ffn(self, src):
+        src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        return self.norm2(src + self.dropout3(src2))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
+                padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None):
+        src2 = self.self_attn(_with_pos(q_feat, q_pos), reference_points, src, spatial_shapes,
+                              level_start_index, padding_mask)
+        q_feat = self.norm1(q_feat + self.dropout1(src2))
+        return self.forward_ffn(q_feat), q_i_feat
+
+
+class DeformableTransformerFusionEncoderLayer(nn.Module):
+    """Dual query streams: MSDA updates the image stream, each stream has its FFN, then the
+    bi-directional gate mixes them. ``gate_first`` selects the Voxel-RCNN ordering."""
+
+    def __init__(self, d_model=256, q_model=256, d_ffn=1024, dropout=0.1, activation="relu",
+                 n_levels=4, n_heads=8, n_points=4, hybrid_cfg=None, gate_first=False):
+        super().__init__()
+        self.attn_layer = hybrid_cfg["attn_layer"]
+        self.q_method = hybrid_cfg.get("q_method", None)
+        self.q_rep_place = hybrid_cfg.get("q_rep_place", None)
+        self.gate_first = gate_first
+        self.d_model = d_model
+        self.self_attn = MSDeformAttn(d_model, q_model, n_levels, n_heads, n_points,
+                                      q_method=self.q_method, q_rep_place=self.q_rep_place)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        # image-stream FFN
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _get_activation_fn(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        # LiDAR-stream FFN
+        self.linear3 = nn.Linear(d_model, d_ffn)
+        self.dropout4 = nn.Dropout(dropout)
+        self.linear4 = nn.Linear(d_ffn, d_model)
+        self.dropout5 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.fusion_layer = attn_dict[self.attn_layer](q_model, q_model)
+
+    with_pos_embed = staticmethod(_with_pos)
+
+    def forward_i_ffn(self, src):
+        src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        return self.norm2(src + self.dropout3(src2))
+
+    def forward_p_ffn(self, src):
+        src2 = self.linear4(self.dropout4(self.activation(self.linear3(src))))
+        return self.norm3(src + self.dropout5(src2))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
+                padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None):
+        src2 = self.self_attn(_with_pos(q_feat, q_pos), reference_points, src, spatial_shapes,
+                              level_start_index, padding_mask, i_query=_with_pos(q_i_feat, q_pos))
+        q_i_feat = self.norm1(q_i_feat + self.dropout1(src2))
+        if self.gate_first:
+            q_feat, q_i_feat = self.fusion_layer(q_feat, q_i_feat)
+            return self.forward_p_ffn(q_feat), self.forward_i_ffn(q_i_feat)
+        q_i_feat = self.forward_i_ffn(q_i_feat)
+        q_feat = self.forward_p_ffn(q_feat)
+        return self.fusion_layer(q_feat, q_i_feat)
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers, model_name="ACTR", lt_cfg=None):
+        super().__init__()
+        self.layers = _get_clones(encoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.model_name = model_name
+        if model_name == "ACTRv2":
+            from .pointformer import LocalTransformer
+            get = lt_cfg.get if hasattr(lt_cfg, "get") else lambda k, d=None: getattr(lt_cfg, k, d)
+            self.lidar_attns = _get_clones(
+                LocalTransformer(get("npoint"), get("radius"), get("nsample"), encoder_layer.d_model,
+                                 encoder_layer.d_model, num_layers=get("num_layers"),
+                                 attn_feat_agg_method=get("attn_feat_agg_method", "unique"),
+                                 feat_agg_method=get("feat_agg_method", "replace")), num_layers)
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None,
+                padding_mask=None, q_feat=None, q_pos=None, q_reference_points=None,
+                q_lidar_grid=None, q_i_feat=None):
+        if q_reference_points is None:
+            raise NotImplementedError("image->point direction (IACTR) is not part of the 3D-DF hot path")
+        reference_points = q_reference_points[:, :, None] * valid_ratios[:, None]
+        for idx, layer in enumerate(self.layers):
+            if self.model_name == "ACTRv2":
+                q_feat = self.lidar_attns[idx](q_lidar_grid, q_feat.permute(0, 2, 1))
+            q_feat, q_i_feat = layer(src, pos, reference_points, spatial_shapes, level_start_index,
+                                     padding_mask, q_pos=q_pos, q_feat=q_feat, q_i_feat=q_i_feat)
+        return q_feat
+
+
+class DeformableTransformerACTR(nn.Module):
+    def __init__(self, d_model=256, query_num_feat=256, nhead=8, num_encoder_layers=6,
+                 dim_feedforward=1024, dropout=0.1, activation="relu", return_intermediate_dec=False,
+                 num_feature_levels=4, enc_n_points=4, two_stage=False, two_stage_num_proposals=300,
+                 model_name="ACTR", lt_cfg=None, feature_modal="lidar", hybrid_cfg=None,
+                 gate_first=False):
+        super().__init__()
+        self.d_model = d_model
+        self.q_model = query_num_feat
+        self.nhead = nhead
+        self.two_stage = two_stage
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.feature_modal = feature_modal
+        if feature_modal in ["hybrid"]:
+            encoder_layer = DeformableTransformerFusionEncoderLayer(
+                d_model, self.q_model, dim_feedforward, dropout, activation, num_feature_levels, nhead,
+                enc_n_points, hybrid_cfg, gate_first=gate_first)
+        else:
+            encoder_layer = DeformableTransformerEncoderLayer(
+                d_model, self.q_model, dim_feedforward, dropout, activation, num_feature_levels, nhead,
+                enc_n_points, hybrid_cfg)
+        self.encoder = DeformableTransformerEncoder(encoder_layer, num_encoder_layers,
+                                                    model_name=model_name, lt_cfg=lt_cfg)
+        self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        normal_(self.level_embed)
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        valid_H = torch.sum(~mask[:, :, 0], 1)
+        valid_W = torch.sum(~mask[:, 0, :], 1)
+        return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
+
+    def forward(self, srcs, masks, pos_embeds, q_feat_flatten, q_pos, q_ref_coors, q_lidar_grid=None,
+                q_i_feat_flatten=None):
+        """srcs: per-level (B', C, H, W) projected camera maps. ``masks`` may be None (= no padding,
+        which is what ACTR always passes: all-False masks, actr.py:172-176) — then valid ratios are 1
+        and no masked_fill is issued. ``pos_embeds`` is accepted for signature parity; the encoder
+        layers never read it (actr_transformer.py:399-426), so it may be None."""
+        src_flatten, spatial_shapes, mask_flatten = [], [], []
+        for lvl, src in enumerate(srcs):
+            bs, c, h, w = src.shape
+            spatial_shapes.append((h, w))
+            src_flatten.append(src.flatten(2).transpose(1, 2))
+            if masks is not None:
+                mask_flatten.append(masks[lvl].flatten(1))
+        src_flatten = torch.cat(src_flatten, 1) if len(src_flatten) > 1 else src_flatten[0]
+        device = src_flatten.device
+        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)),
+                                       spatial_shapes.prod(1).cumsum(0)[:-1]))
+        if masks is not None:
+            valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+            mask_flatten = torch.cat(mask_flatten, 1)
+        else:
+            valid_ratios = src_flatten.new_ones((src_flatten.shape[0], len(srcs), 2))
+            mask_flatten = None
+        return self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, None,
+                            mask_flatten, q_pos=q_pos, q_feat=q_feat_flatten,
+                            q_reference_points=q_ref_coors, q_lidar_grid=q_lidar_grid,
+                            q_i_feat=q_i_feat_flatten)
+
+
+def build_deformable_transformer(args, model_name="ACTR", lt_cfg=None):
+    if "IACTR" in model_name:
+        raise NotImplementedError("IACTR* variants are dead code for every shipped 3D-DF config")
+    return DeformableTransformerACTR(
+        d_model=args.hidden_dim, query_num_feat=args.query_num_feat, nhead=args.nheads,
+        num_encoder_layers=args.enc_layers, dim_feedforward=args.dim_feedforward, dropout=args.dropout,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=args.num_feature_levels,
+        enc_n_points=args.enc_n_points, two_stage=args.two_stage,
+        two_stage_num_proposals=args.num_queries, model_name=model_name, lt_cfg=lt_cfg,
+        feature_modal=args.feature_modal, hybrid_cfg=args.hybrid_cfg,
+        gate_first=getattr(args, "gate_first", False))

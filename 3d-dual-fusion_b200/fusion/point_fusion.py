@@ -1,0 +1,176 @@
+"""mmdet3d ``FUSION_LAYERS['ACTR']``: the TransFusion-side wrapper of the 3D-DF encoder
+(TransFusion/mmdet3d/models/fusion_layers/point_fusion.py:315-507, projection :509-643).
+
+What is different from the reference:
+  * projection runs on the GPU from ``img_metas[b]['lidar2img']`` (one (n_cam, 4, 4) matrix stack per
+    sample) instead of a host NumPy chain through the nuScenes devkit (point_fusion.py:408-409,
+    551-643, D2H at :585).  Same visibility rule (depth > 1 m, 1 < u < W_ori-1, 1 < v < H_ori-1 in
+    ORIGINAL image pixels), same post-processing (scale -> crop -> flip -> divide by the padded
+    size), same assignment ("the last camera that sees a voxel wins", unseen voxels become camera-0
+    queries at reference point (0, 0), :516-517,544-547);
+  * the per-(sample, camera) split / zero-pad / un-pad (split_param :342-382, agg_param :384-394)
+    is one stable sort + index arithmetic on the device instead of B x 6 Python loops of boolean
+    masks with host syncs; the padded layout (B*n_cam, max_pts_per_cam, .) is bit-identical, which
+    matters because GroupNorm statistics include the padded rows.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..registry import FUSION_LAYERS
+from .actr import build as build_actr
+
+
+def reverse_3d_transformation(points, img_meta):
+    """apply_3d_transformation(..., reverse=True) for LiDAR coordinates
+    (TransFusion/mmdet3d/models/fusion_layers/coord_transform.py:8-75)."""
+    flow = img_meta.get("transformation_3d_flow", [])
+    if not flow:
+        return points
+    pts = points.clone()
+    dtype, device = pts.dtype, pts.device
+    for op in flow[::-1]:
+        if op == "T":
+            pts = pts - torch.as_tensor(img_meta.get("pcd_trans", [0., 0., 0.]), dtype=dtype, device=device)
+        elif op == "S":
+            pts = pts * (1.0 / img_meta.get("pcd_scale_factor", 1.))
+        elif op == "R":
+            rot = torch.as_tensor(img_meta.get("pcd_rotation", torch.eye(3)), dtype=dtype, device=device)
+            pts = pts @ rot.inverse()
+        elif op == "HF":
+            if img_meta.get("pcd_horizontal_flip", False):
+                pts = pts * pts.new_tensor([1., -1., 1.])
+        elif op == "VF":
+            if img_meta.get("pcd_vertical_flip", False):
+                pts = pts * pts.new_tensor([-1., 1., 1.])
+        else:
+            raise KeyError("unknown transformation_3d_flow op %r" % (op,))
+    return pts
+
+
+def project_to_cameras(points, img_meta):
+    """points (n, 3) LiDAR xyz.  Returns cam (n,) int64 in [0, n_cam) (0 for unseen voxels),
+    grid (n, 2) normalised (x / W_pad, y / H_pad), grid_o (n, 2) padded-image pixels; rows of unseen
+    voxels are zero.  Follows get_2d_coor_multi (point_fusion.py:509-549) + projection (:551-643)."""
+    n = points.shape[0]
+    dev, dtype = points.device, points.dtype
+    pts = reverse_3d_transformation(points, img_meta)
+    l2i = torch.as_tensor(img_meta["lidar2img"], dtype=dtype, device=dev).reshape(-1, 4, 4)
+    n_cam = l2i.shape[0]
+    ori_h, ori_w = img_meta["ori_shape"][:2]
+    homo = torch.cat([pts[:, :3], pts.new_ones(n, 1)], 1)                    # (n, 4)
+    cam_pts = torch.einsum("cij,nj->cni", l2i[:, :3, :], homo)                # (n_cam, n, 3)
+    depth = cam_pts[..., 2]
+    uv = cam_pts[..., :2] / depth[..., None]
+    seen = ((depth > 1.0) & (uv[..., 0] > 1) & (uv[..., 0] < ori_w - 1)
+            & (uv[..., 1] > 1) & (uv[..., 1] < ori_h - 1))                    # (n_cam, n)
+    # image transformation: scale -> crop -> flip (by default horizontal, on the un-padded shape)
+    scale = img_meta.get("scale_factor", None)
+    scale = uv.new_tensor(scale[:2]) if scale is not None else 1
+    crop = img_meta.get("img_crop_offset", None)
+    crop = uv.new_tensor(crop) if crop is not None else 0
+    xy = uv * scale - crop
+    if img_meta.get("flip", False):
+        xy = torch.stack([img_meta["img_shape"][1] - xy[..., 0], xy[..., 1]], -1)
+    pad_h, pad_w = img_meta["input_shape"][:2]
+    # last camera that sees the voxel wins
+    order = torch.arange(1, n_cam + 1, device=dev)[:, None]
+    cam = (seen * order).max(0)[0] - 1                                        # -1 = unseen
+    visible = cam >= 0
+    cam = cam.clamp(min=0)
+    sel = xy.gather(0, cam[None, :, None].expand(1, n, 2))[0]
+    grid_o = torch.where(visible[:, None], sel, torch.zeros_like(sel))
+    grid = grid_o / grid_o.new_tensor([pad_w, pad_h])
+    return cam, grid, grid_o
+
+
+class BasicGate(nn.Module):
+    """Gate of the (unfinished) 'gating_v1' fusion method (point_fusion.py:334-338)."""
+
+    def __init__(self, g_channel):
+        super().__init__()
+        self.g_channel = g_channel
+        self.spatial_basic = nn.Conv1d(g_channel, 1, kernel_size=1, stride=1)
+
+    def forward(self, pts_feat, enh_feat):
+        return enh_feat * torch.sigmoid(self.spatial_basic(pts_feat))
+
+
+@FUSION_LAYERS.register_module()
+class ACTR(nn.Module):
+    def __init__(self, pfat_cfg, init_cfg=None, lt_cfg=None, coord_type="LIDAR", activate_out=False,
+                 data_version="v1.0-trainval", data_root="./data/nuscenes", model_name="ACTR"):
+        super(ACTR, self).__init__()
+        self.fusion_method = pfat_cfg["fusion_method"]
+        # the reference hard-codes model_name='ACTR' here (point_fusion.py:328): lt_cfg is passed
+        # but the LocalTransformer is only built for 'ACTRv2' 
+        self.actr = build_actr(pfat_cfg, model_name=model_name, lt_cfg=lt_cfg)
+        self.coord_type = coord_type
+        self.activate_out = activate_out
+        if self.fusion_method == "gating_v1":
+            n_channel = pfat_cfg["query_num_feat"]
+            self.trg_gating = BasicGate(n_channel)
+            self.trg_channel_reduce = nn.Conv1d(n_channel * 2, n_channel, kernel_size=1, stride=1)
+        self.data_version = data_version
+        self.data_root = data_root
+        self.img_stride = 4  # nearest image feature = feat[:, v // 4, u // 4] (point_fusion.py:375-378)
+
+    def split_param(self, pts_feats, cam, grid, grid_o, img_feats, pts_xyz, sample_id, n_cam):
+        """Group the concatenated voxel queries by (sample, camera) and zero-pad to the largest
+        group. Returns the padded tensors and (row, col) of every query inside them."""
+        group = sample_id * n_cam + cam
+        n_groups = img_feats[0].shape[0]
+        order = torch.sort(group, stable=True)[1]
+        g_sorted = group[order]
+        counts = torch.bincount(group, minlength=n_groups)
+        starts = torch.cumsum(counts, 0) - counts
+        col_sorted = torch.arange(group.numel(), device=group.device) - starts[g_sorted]
+        max_points = int(counts.max().item())
+        row = torch.empty_like(group)
+        col = torch.empty_like(group)
+        row[order] = g_sorted
+        col[order] = col_sorted
+
+        def pad(x):
+            out = x.new_zeros((n_groups, max_points) + tuple(x.shape[1:]))
+            out[row, col] = x
+            return out
+
+        stride = self.img_stride
+        ix = grid_o[:, 0].to(torch.long) // stride
+        iy = grid_o[:, 1].to(torch.long) // stride
+        img_at_query = img_feats[0][group, :, iy, ix]                        # (n, C_img)
+        return (pad(pts_feats), pad(img_at_query), pad(grid), pad(pts_xyz), row, col, max_points)
+
+    def forward(self, img_feats, pts, pts_feats, img_metas, imgs=None):
+        """img_feats: list of (B*n_cam, C, H, W); pts: list of (n_b, 3) voxel centres; pts_feats
+        (sum n_b, C).  Returns fused (sum n_b, C)."""
+        img_feats = img_feats[:self.actr.num_backbone_outs]
+        batch_size = len(pts)
+        n_cam = img_feats[0].shape[0] // batch_size
+        self.actr.max_num_ne_voxel = max(p.shape[0] for p in pts)
+        cams, grids, grids_o, sids = [], [], [], []
+        for b in range(batch_size):
+            cam, grid, grid_o = project_to_cameras(pts[b][:, :3], img_metas[b])
+            cams.append(cam)
+            grids.append(grid)
+            grids_o.append(grid_o)
+            sids.append(torch.full_like(cam, b))
+        cam, grid, grid_o, sid = (torch.cat(x) for x in (cams, grids, grids_o, sids))
+        xyz = torch.cat([p[:, :3] for p in pts])
+        feats_n, img_n, grid_n, xyz_n, row, col, _ = self.split_param(
+            pts_feats, cam, grid, grid_o, img_feats, xyz, sid, n_cam)
+        enh_n = self.actr(v_feat=feats_n, grid=grid_n, i_feats=img_feats, lidar_grid=xyz_n, v_i_feat=img_n)
+        enh = enh_n[row, col]                                                  # agg_param + concat
+        if self.fusion_method == "replace":
+            fuse_out = enh
+        elif self.fusion_method == "concat":
+            fuse_out = torch.cat((pts_feats, enh), dim=1)
+        elif self.fusion_method in ("sum", "gating_v1"):
+            # the reference's gating_v1 computes the gate but returns the plain sum (:492-497)
+            fuse_out = pts_feats + enh
+        else:
+            raise NotImplementedError("Invalid ACTR fusion method")
+        if self.activate_out:
+            fuse_out = F.relu(fuse_out)
+        return fuse_out

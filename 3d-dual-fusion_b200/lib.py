@@ -20,6 +20,7 @@ c_ptr = ctypes.c_void_p
 _SIGNATURES = {
     "ddf_abi_version": [],
     "ddf_compiled_arch": [],
+    "ddf_launch_count": [c_int],
     "ddf_ms_deform_attn_forward": [c_ptr] * 6 + [c_i64] * 8 + [c_int, c_ptr],
     "ddf_ms_deform_attn_backward": [c_ptr] * 9 + [c_i64] * 8 + [c_int, c_ptr],
     "ddf_hard_voxelize_workspace_bytes": [c_i64] * 3,
@@ -37,7 +38,7 @@ _SIGNATURES = {
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_dense_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
 }
-_RESTYPES = {"ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64}
+_RESTYPES = {"ddf_launch_count": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64}
 
 
 def exported_symbols():

@@ -83,9 +83,11 @@ class TableConvFunction(Function):
         features, filters = ctx.saved_tensors
         rb = ctx.rulebook
         grad_output = grad_output.contiguous()
-        gin, gw = ops.sparse_conv_backward(features, filters, grad_output, rb.scatter_table,
-                                           rb.indice_pairs, rb.indice_pair_num,
-                                           ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        gin = gw = None
+        if ctx.needs_input_grad[0]:
+            gin = ops.sparse_conv_dgrad(filters, grad_output, rb.scatter_table, features.shape[0])
+        if ctx.needs_input_grad[1]:
+            gw = ops.sparse_conv_wgrad(features, filters, grad_output, rb.indice_pairs, rb.indice_pair_num)
         gb = grad_output.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gin, gw, gb, None, None
 

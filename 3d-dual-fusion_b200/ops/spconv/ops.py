@@ -173,25 +173,27 @@ def sparse_conv_forward(features, filters, gather_table, bias, n_out):
     return out
 
 
-def sparse_conv_backward(features, filters, grad_out, scatter_table, indice_pairs, indice_pair_num,
-                         need_gin=True, need_gw=True):
+def sparse_conv_dgrad(filters, grad_out, scatter_table, n_in):
+    cin, cout = filters.shape[-2], filters.shape[-1]
+    kvol = filters.numel() // (cin * cout)
+    gin = torch.empty((n_in, cin), dtype=grad_out.dtype, device=grad_out.device)
+    wt_ws = torch.empty_like(filters)
+    with torch.cuda.device(grad_out.device):
+        rc = _lib.get_lib().ddf_sparse_conv_dgrad(_lib.ptr(grad_out), _lib.ptr(filters),
+                                                  _lib.ptr(scatter_table), _lib.ptr(gin), _lib.ptr(wt_ws),
+                                                  n_in, kvol, cin, cout, _lib.current_stream())
+    _lib.check(rc, "sparse_conv_dgrad")
+    return gin
+
+
+def sparse_conv_wgrad(features, filters, grad_out, indice_pairs, indice_pair_num):
     cin, cout = filters.shape[-2], filters.shape[-1]
     kvol = indice_pairs.shape[0]
-    n_in = features.shape[0]
-    L = _lib.get_lib()
-    gin = gw = None
+    gw = torch.empty_like(filters)
     with torch.cuda.device(features.device):
-        if need_gin:
-            gin = torch.empty_like(features)
-            wt_ws = torch.empty_like(filters)
-            rc = L.ddf_sparse_conv_dgrad(_lib.ptr(grad_out), _lib.ptr(filters), _lib.ptr(scatter_table),
-                                         _lib.ptr(gin), _lib.ptr(wt_ws), n_in, kvol, cin, cout,
-                                         _lib.current_stream())
-            _lib.check(rc, "sparse_conv_dgrad")
-        if need_gw:
-            gw = torch.empty_like(filters)
-            rc = L.ddf_sparse_conv_wgrad(_lib.ptr(features), _lib.ptr(grad_out), _lib.ptr(indice_pairs),
-                                         _lib.ptr(indice_pair_num), indice_pairs.shape[2], _lib.ptr(gw),
-                                         kvol, cin, cout, 0, _lib.current_stream())
-            _lib.check(rc, "sparse_conv_wgrad")
-    return gin, gw
+        rc = _lib.get_lib().ddf_sparse_conv_wgrad(_lib.ptr(features), _lib.ptr(grad_out),
+                                                  _lib.ptr(indice_pairs), _lib.ptr(indice_pair_num),
+                                                  indice_pairs.shape[2], _lib.ptr(gw), kvol, cin, cout, 0,
+                                                  _lib.current_stream())
+    _lib.check(rc, "sparse_conv_wgrad")
+    return gw

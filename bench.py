@@ -1,0 +1,339 @@
+"""Headline benchmark: TransFusion-L + 3D-DF hot path, forward + backward + optimizer step, samples/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic nuScenes-shaped input per rank
+(BASELINE.json configs[2]: TransFusion-L+3D-DF, bs=2/GPU): hard voxelization -> HardSimpleVFE ->
+SparseEncoderFusion (21 sparse convs + BN/ReLU, 3D-DF fusion hook: GPU projection, per-camera
+split, ACTR encoder with dual-query MSDA, FFNs, bi-gate) -> dense BEV map; loss = mean(out^2);
+backward; grad-clip 0.1; AdamW step (the reference's optimizer_config / optimizer,
+TransFusion/configs/transfusion_nusc_voxel_F.py:302-303).  Camera backbone, BEV backbone and head
+are outside the path: camera features are synthetic N(0,1) maps.
+
+Multi-GPU: pure data parallel (DDP over NCCL, gradients only), weak scaling, launched by
+torch.distributed.run. `--impl reference` times the reference's own CPU implementation of the
+same path (oracle/_ref extensions + PyTorch CPU) on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "TransFusion-L+3D-DF hot path fwd+bwd samples/sec"
+UNIT = "samples/s"
+BATCH_PER_GPU = 2
+POINTS_PER_SAMPLE = 260000   # nuScenes 10-sweep cloud
+N_CAM = 6
+FEAT_HW = (112, 200)         # FPN level 0 of a 448x800 input
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "TransFusion-L+3D-DF (transfusion_nusc_voxel_F) hot path: voxelize+VFE+SparseEncoderFusion"
+                    "(ACTR hybrid, 2 enc layers)+dense BEV, fwd+bwd+clip+AdamW",
+        "per_gpu_batch": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
+        "points_per_sample": POINTS_PER_SAMPLE, "cams": N_CAM, "cam_feat": [256, *FEAT_HW],
+        "sparse_shape": [41, 1440, 1440], "parallelism": "dp%d" % n_gpus,
+        "l2": "inputs larger than L2 (285 MB of points + camera features per step)",
+    }
+
+
+def build_model(device):
+    import configs
+    import ddf_b200.fusion.point_fusion  # noqa: F401  (registers FUSION_LAYERS['ACTR'])
+    import ddf_b200.fusion.sparse_encoder  # noqa: F401
+    import ddf_b200.fusion.voxel_encoder  # noqa: F401
+    from ddf_b200.fusion import structurally_unused_parameters
+    from ddf_b200.fusion.detector import TransFusionPtsBranch
+    torch.manual_seed(0)
+    model = TransFusionPtsBranch(**configs.transfusion_f()).to(device).train()
+    frozen = set(structurally_unused_parameters(model))
+    for n, p in model.named_parameters():
+        if n in frozen:
+            p.requires_grad_(False)
+    return model
+
+
+def host_batch(rank, batch):
+    import synth
+    pts = [torch.from_numpy(synth.lidar_points(POINTS_PER_SAMPLE, seed=1000 * rank + b)) for b in range(batch)]
+    feats = torch.from_numpy(synth.camera_features(batch, N_CAM, FEAT_HW, seed=rank))
+    metas = [synth.nusc_img_meta(N_CAM) for _ in range(batch)]
+    return pts, feats, metas
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_reference_run(steps, warmup, batch=1):
+    """The reference's own CPU implementation of the path (oracle/cpu_path.py) on the host cores."""
+    from oracle import cpu_path
+    torch.set_num_threads(os.cpu_count())
+    model = build_model("cpu")
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01)
+    pts, feats, metas = host_batch(0, batch)
+    times = []
+    with cpu_path.reference_cpu_ops():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = model(pts, [feats], metas)
+            loss = out.square().mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+            opt.step()
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    t = float(np.mean(times))
+    return {"value": batch / t, "unit": UNIT, "cores": os.cpu_count(), "kind": cpu_path.kind(),
+            "sample": "%d frame(s) x %d points + %d cam maps, fwd+bwd+clip+AdamW, %d timed step(s) after %d warm-up; "
+                      "%.1f s/step" % (batch, POINTS_PER_SAMPLE, N_CAM, steps, warmup, t)}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    base, t = cpu_reference_run(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["config"]["reference_sample"] = "1 frame per step on the host cores (bounded sample of the bs=2/GPU workload)"
+    print(json.dumps(line))
+
+
+class ConvTimer(object):
+    """Per-launch CUDA-event timing of the dominant kernel family (fused gather-GEMM sparse conv,
+    forward and dgrad launches) on the launching stream, plus its algorithmic FLOPs / bytes."""
+
+    def __init__(self):
+        self.records = []
+
+    def install(self):
+        from ddf_b200.ops.spconv import ops
+        self._ops, self._fwd, self._dgrad = ops, ops.sparse_conv_forward, ops.sparse_conv_dgrad
+        timer = self
+
+        def fwd(features, filters, gather_table, bias, n_out):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = timer._fwd(features, filters, gather_table, bias, n_out)
+            b.record()
+            timer.records.append((a, b, gather_table, features.shape[0], n_out, filters.shape[-2], filters.shape[-1]))
+            return out
+
+        def dgrad(filters, grad_out, scatter_table, n_in):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = timer._dgrad(filters, grad_out, scatter_table, n_in)
+            b.record()
+            # includes the small filter transpose launch that precedes the conv kernel
+            timer.records.append((a, b, scatter_table, grad_out.shape[0], n_in, filters.shape[-1], filters.shape[-2]))
+            return out
+
+        ops.sparse_conv_forward, ops.sparse_conv_dgrad = fwd, dgrad
+
+    def remove(self):
+        self._ops.sparse_conv_forward, self._ops.sparse_conv_dgrad = self._fwd, self._dgrad
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = flops = byts = 0.0
+        for a, b, table, n_src, n_dst, cin, cout in self.records:
+            pairs = int((table >= 0).sum().item())
+            kvol = table.shape[1]
+            ms += a.elapsed_time(b)
+            flops += 2.0 * pairs * cin * cout
+            byts += 4.0 * (n_src * cin + n_dst * cout + kvol * cin * cout) + 8.0 * pairs
+        return len(self.records), ms, flops, byts
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ddf_b200 import lib
+    L = lib.get_lib()
+    model = build_model(dev)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01)
+
+    h_pts, h_feats, metas = host_batch(rank, BATCH_PER_GPU)
+    h_pts = [p.pin_memory() for p in h_pts]
+    h_feats = h_feats.pin_memory()
+    h_loss = torch.zeros(1).pin_memory()
+    d_pts = [p.to(dev) for p in h_pts]
+    d_feats = h_feats.to(dev)
+
+    def step(pts, feats):
+        out = net(pts, [feats], metas)
+        loss = out.square().mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step(d_pts, d_feats)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # (1) device-resident inputs
+    L.ddf_launch_count(1)
+    ms_dev = timed(lambda: step(d_pts, d_feats), args.steps)
+    launches = int(L.ddf_launch_count(1))
+
+    # (2) end to end through the public module call: pinned host inputs -> device, loss -> host
+    def e2e_step():
+        pts = [p.to(dev, non_blocking=True) for p in h_pts]
+        feats = h_feats.to(dev, non_blocking=True)
+        loss = step(pts, feats)
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+
+    # (3) dominant-kernel roofline, timed live with CUDA events on the launching stream
+    ct = ConvTimer()
+    ct.install()
+    step(d_pts, d_feats)
+    n_launch, conv_ms, conv_flops, conv_bytes = ct.summary()
+    ct.remove()
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        peaks, how = measured_peaks()
+        global_batch = BATCH_PER_GPU * world
+        value = global_batch * args.steps / (ms_dev / 1e3)
+        e2e = global_batch * args.steps / (ms_e2e / 1e3)
+        h2d = sum(p.numel() * 4 for p in h_pts) + h_feats.numel() * 4
+        tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {
+                "kernel": "sparse-conv fused gather-GEMM (forward + dgrad launches of one step)",
+                "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": tf / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); kernel computes in tf32/fp32" % how,
+                "launches_per_step": n_launch, "avg_launch_ms": conv_ms / max(n_launch, 1),
+                "share_of_step": conv_ms / (ms_dev / args.steps),
+                "algorithmic_GFLOP_per_step": conv_flops / 1e9, "algorithmic_MB_per_step": conv_bytes / 1e6,
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"], _ = cpu_reference_run(1, 0)
+            except Exception as e:  # the oracle is a checker; its absence must not fake a number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "failed: %r" % (e,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

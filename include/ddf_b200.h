@@ -36,6 +36,9 @@ const char* ddf_last_error(void);
 int ddf_abi_version(void);
 /* Compiled SM architecture (100 for sm_100a). */
 int ddf_compiled_arch(void);
+/* Number of kernels this library has launched so far in this process (all threads); reset != 0
+ * zeroes the counter after reading. Used by bench.py's gpu_launches. */
+int64_t ddf_launch_count(int reset);
 
 /* ---- Multi-scale deformable attention (MSDA) ------------------------------------------
  * Replaces MultiScaleDeformableAttention.ms_deform_attn_forward / _backward

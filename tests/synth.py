@@ -35,3 +35,37 @@ def uniform_points(n, pc_range, seed=0, nfeat=5, margin=1.0):
     xyz = rng.uniform(lo, hi, (n, 3))
     rest = rng.random((n, nfeat - 3))
     return np.ascontiguousarray(np.concatenate([xyz, rest], 1).astype(np.float32))
+
+
+def camera_rig(n_cam=6, ori_hw=(900, 1600), focal=1266.0, cam_z=-0.3):
+    """Pinhole rig: yaw {0, +-55, 180, +-110} deg, principal point at the centre; returns lidar2img
+    (n_cam, 4, 4) float64 mapping LiDAR xyz1 -> (u*d, v*d, d, 1) in ORIGINAL image pixels."""
+    yaws = np.deg2rad([0.0, 55.0, -55.0, 180.0, 110.0, -110.0])[:n_cam]
+    H, W = ori_hw
+    K = np.array([[focal, 0, W / 2.0, 0], [0, focal, H / 2.0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float64)
+    out = []
+    for th in yaws:
+        fwd = np.array([np.cos(th), np.sin(th), 0.0])
+        right = np.array([np.sin(th), -np.cos(th), 0.0])
+        down = np.array([0.0, 0.0, -1.0])
+        R = np.stack([right, down, fwd])
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = -R @ np.array([0.0, 0.0, cam_z])
+        out.append(K @ T)
+    return np.stack(out)
+
+
+def nusc_img_meta(n_cam=6, ori_hw=(900, 1600), input_hw=(448, 800)):
+    """img_metas entry the TransFusion fusion layer reads (SURVEY.md section 8(b) metadata contract)."""
+    scale = min(input_hw[1] / ori_hw[1], input_hw[0] / ori_hw[0])
+    img_hw = (int(ori_hw[0] * scale + 0.5), int(ori_hw[1] * scale + 0.5))
+    return dict(lidar2img=camera_rig(n_cam, ori_hw), ori_shape=(ori_hw[0], ori_hw[1], 3),
+                img_shape=(img_hw[0], img_hw[1], 3), input_shape=input_hw,
+                scale_factor=np.array([scale, scale, scale, scale], np.float32), flip=False,
+                filename=["CAM_%d" % i for i in range(n_cam)], sample_idx="synthetic")
+
+
+def camera_features(batch, n_cam, hw, channels=256, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((batch * n_cam, channels, hw[0], hw[1]), dtype=np.float32)
