@@ -13,9 +13,32 @@
 //   wgrad   : gW[k]     = sum_{(i,o) in pairs[k]} in[i,:]^T gout[o,:]   (walks the pair lists)
 // The SubM centre tap needs no special case here (the reference treats arg-max offset as identity,
 // spconv_ops.h:271-303): its gather-table column is simply the identity.
+#include <stdlib.h>
+
 #include "common.cuh"
 
+namespace ddf {
+// tcgen05 path (sparse_conv_tc.cu)
+bool spconv_tc_supported(int kvol, int cin, int cout);
+int spconv_tc_launch(const float* feat, const float* wt, const int* table, const float* bias,
+                     float* out, int64_t n_out, int kvol, int cin, int cout, cudaStream_t stream);
+bool spconv_wgrad_tc_supported(int cin, int cout);
+int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pairs, const int* num,
+                           int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
+                           cudaStream_t stream);
+}  // namespace ddf
+
 namespace {
+
+// DDF_DISABLE_TC=1 forces the fp32 SIMT kernels (A/B testing, bit-for-bit fp32 accumulation)
+bool tc_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DDF_DISABLE_TC");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 
 constexpr int kThreads = 256;
 constexpr int TM = 128;  // output rows per CTA
@@ -180,17 +203,42 @@ spconv_wgrad_kernel(const float* __restrict__ feat, const float* __restrict__ go
   }
 }
 
-// filters [K, Cin, Cout] -> [K, Cout, Cin]
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// filters [K, Cin, Cout] -> [K, Cout, Cin] (optionally rounded to tf32)
 __global__ void __launch_bounds__(kThreads)
 transpose_filters_kernel(const float* __restrict__ w, float* __restrict__ wt, int kvol, int cin,
-                         int cout) {
+                         int cout, bool round_tf32) {
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const long long per = (long long)cin * cout;
   if (t >= per * kvol) return;
   const int k = (int)(t / per);
   const int r = (int)(t % per);
   const int co = r / cin, ci = r % cin;
-  wt[t] = w[(long long)k * per + (long long)ci * cout + co];
+  const float v = w[(long long)k * per + (long long)ci * cout + co];
+  wt[t] = round_tf32 ? tf32_rn(v) : v;
+}
+
+// dst = round-to-nearest-tf32(src): operands of the tensor-core path are made exactly
+// representable, so the hardware's truncation of the low 13 mantissa bits is a no-op (unbiased
+// 2^-12 relative rounding instead of a systematic 2^-11 shrink per operand)
+__global__ void __launch_bounds__(kThreads)
+round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4, long long n) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t < n4) {
+    float4 v = reinterpret_cast<const float4*>(src)[t];
+    v.x = tf32_rn(v.x);
+    v.y = tf32_rn(v.y);
+    v.z = tf32_rn(v.z);
+    v.w = tf32_rn(v.w);
+    reinterpret_cast<float4*>(dst)[t] = v;
+  }
+  if (t == 0)
+    for (long long i = n4 * 4; i < n; ++i) dst[i] = tf32_rn(src[i]);
 }
 
 // pair lists -> row-major table: table[row_of(col_sel)][k] = row_of(1-col_sel)
@@ -237,13 +285,22 @@ int launch_gather_gemm(const float* feat, const float* filt, const int* table, c
 // [n_out, K]; bias optional ([cout] or NULL).  Fully overwrites out.
 extern "C" int ddf_sparse_conv_forward(const float* features, const float* filters,
                                        const int* gather_table, const float* bias, float* out,
-                                       int64_t n_out, int64_t kvol, int64_t cin, int64_t cout,
-                                       void* stream) {
+                                       float* filters_t_ws, int64_t n_out, int64_t kvol,
+                                       int64_t cin, int64_t cout, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   DDF_CHECK_ARG(n_out >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_forward: bad sizes");
   if (n_out == 0) return DDF_OK;
   DDF_CHECK_ARG(features && filters && gather_table && out, "sparse_conv_forward: null pointer");
+  if (filters_t_ws && tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) {
+    // tensor-core path wants the filter slice K-major: Wt[k] = [cout, cin]
+    const long long nw = kvol * cin * cout;
+    DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+               filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, true);
+    return ddf::spconv_tc_launch(features, filters_t_ws, gather_table, bias, out, n_out, (int)kvol,
+                                 (int)cin, (int)cout, stream);
+  }
   return launch_gather_gemm(features, filters, gather_table, bias, out, n_out, (int)kvol, (int)cin,
-                            (int)cout, (cudaStream_t)stream);
+                            (int)cout, stream);
 }
 
 // grad_in [n_in, cin] = sum_k grad_out[scatter_table[i,k]] . W[k]^T ; filters_t_ws: device scratch
@@ -257,9 +314,16 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
   if (n_in == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_out && filters && scatter_table && grad_in && filters_t_ws,
                 "sparse_conv_dgrad: null pointer");
+  // dgrad contracts over Cout; filters [K, cin, cout] are already the K-major B operand [N=cin, K=cout]
   const long long nw = kvol * cin * cout;
-  DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, 
-      filters, filters_t_ws, (int)kvol, (int)cin, (int)cout);
+  if (tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cout, (int)cin)) {
+    DDF_LAUNCH(round_tf32_kernel, (unsigned)ddf::cdiv(nw / 4 + 1, kThreads), kThreads, 0, stream, filters,
+               filters_t_ws, nw / 4, nw);
+    return ddf::spconv_tc_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, (int)kvol,
+                                 (int)cout, (int)cin, stream);
+  }
+  DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+             filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, false);
   // dgrad is a conv with Cin<->Cout swapped through the transposed table
   return launch_gather_gemm(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in,
                             (int)kvol, (int)cout, (int)cin, stream);
@@ -276,6 +340,9 @@ extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_ou
   DDF_CUDA(cudaMemsetAsync(grad_filters, 0, sizeof(float) * (size_t)(kvol * cin * cout), stream));
   if (pair_stride == 0) return DDF_OK;
   DDF_CHECK_ARG(features && grad_out && indice_pairs && indice_num, "sparse_conv_wgrad: null pointer");
+  if (tc_enabled() && ddf::spconv_wgrad_tc_supported((int)cin, (int)cout))
+    return ddf::spconv_wgrad_tc_launch(features, grad_out, indice_pairs, indice_num, pair_stride,
+                                       grad_filters, (int)kvol, (int)cin, (int)cout, inverse, stream);
   // enough (k, slice) CTAs for ~4 waves; slices bounded so each still has >= ~256 pairs
   int S = (int)ddf::cdiv(4 * ddf::kNumSM, kvol);
   const int maxS = (int)ddf::cdiv(pair_stride, 256);
@@ -288,6 +355,28 @@ extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_ou
   else
     DDF_LAUNCH((spconv_wgrad_kernel<64, 64>), grid, kThreads, 0, stream, 
         features, grad_out, indice_pairs, indice_num, (int)pair_stride, (int)cin, (int)cout, inverse, grad_filters);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// Which of the three conv kernels of a (kvol, cin, cout) layer run on the tensor cores:
+// bit 0 forward, bit 1 dgrad, bit 2 wgrad.  Callers use it to decide which operands to pre-round.
+extern "C" int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout) {
+  if (!tc_enabled()) return 0;
+  int m = 0;
+  if (ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) m |= 1;
+  if (ddf::spconv_tc_supported((int)kvol, (int)cout, (int)cin)) m |= 2;
+  if (ddf::spconv_wgrad_tc_supported((int)cin, (int)cout)) m |= 4;
+  return m;
+}
+
+// dst[i] = src[i] rounded to the nearest tf32 (dst may alias src); 16-byte aligned pointers.
+extern "C" int ddf_round_tf32(const float* src, float* dst, int64_t n, void* stream_) {
+  DDF_CHECK_ARG(n >= 0, "round_tf32: bad size");
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(src && dst, "round_tf32: null pointer");
+  DDF_LAUNCH(round_tf32_kernel, (unsigned)ddf::cdiv(n / 4 + 1, kThreads), kThreads, 0,
+             (cudaStream_t)stream_, src, dst, n / 4, n);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }

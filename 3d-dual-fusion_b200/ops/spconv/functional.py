@@ -72,6 +72,11 @@ class TableConvFunction(Function):
     def forward(ctx, features, filters, bias, rulebook, num_activate_out):
         features = features.contiguous()
         filters = filters.contiguous()
+        cin, cout = filters.shape[-2], filters.shape[-1]
+        ctx.mode = mode = ops.tc_mode(rulebook.indice_pairs.shape[0], cin, cout)
+        if mode & 5 and features.shape[0]:
+            # tensor-core operands are made exact tf32 once; forward and wgrad share the copy
+            features = ops.round_tf32(features)
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
         ctx.save_for_backward(features, filters)
@@ -83,12 +88,14 @@ class TableConvFunction(Function):
         features, filters = ctx.saved_tensors
         rb = ctx.rulebook
         grad_output = grad_output.contiguous()
+        gb = grad_output.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        if ctx.mode & 6 and grad_output.shape[0]:
+            grad_output = ops.round_tf32(grad_output)  # shared by dgrad and wgrad
         gin = gw = None
         if ctx.needs_input_grad[0]:
             gin = ops.sparse_conv_dgrad(filters, grad_output, rb.scatter_table, features.shape[0])
         if ctx.needs_input_grad[1]:
             gw = ops.sparse_conv_wgrad(features, filters, grad_output, rb.indice_pairs, rb.indice_pair_num)
-        gb = grad_output.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gin, gw, gb, None, None
 
 

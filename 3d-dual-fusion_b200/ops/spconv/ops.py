@@ -160,15 +160,31 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     return gin, gw
 
 
+def tc_mode(kvol, cin, cout):
+    """Bit mask of the conv kernels of this layer that run on the tensor cores (1 fwd, 2 dgrad, 4 wgrad)."""
+    return int(_lib.get_lib().ddf_sparse_conv_tc_mode(int(kvol), int(cin), int(cout)))
+
+
+def round_tf32(x):
+    """Copy of ``x`` rounded to the nearest tf32 (operand preparation for the tensor-core kernels)."""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.get_lib().ddf_round_tf32(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.current_stream())
+    _lib.check(rc, "round_tf32")
+    return out
+
+
 def sparse_conv_forward(features, filters, gather_table, bias, n_out):
     _check_conv_args(features, filters)
     cin, cout = filters.shape[-2], filters.shape[-1]
     kvol = gather_table.shape[1] if gather_table.numel() else filters.numel() // (cin * cout)
     out = torch.empty((n_out, cout), dtype=features.dtype, device=features.device)
+    wt_ws = torch.empty_like(filters)
     with torch.cuda.device(features.device):
         rc = _lib.get_lib().ddf_sparse_conv_forward(
             _lib.ptr(features), _lib.ptr(filters), _lib.ptr(gather_table), _lib.ptr(bias), _lib.ptr(out),
-            n_out, kvol, cin, cout, _lib.current_stream())
+            _lib.ptr(wt_ws), n_out, kvol, cin, cout, _lib.current_stream())
     _lib.check(rc, "sparse_conv_forward")
     return out
 

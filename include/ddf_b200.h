@@ -171,9 +171,19 @@ int ddf_indice_conv_backward(const float* features, const float* filters, const 
                              int64_t cin, int64_t cout, int inverse, int subm, int* table_ws,
                              float* filters_t_ws, void* stream);
 
+/* filters_t_ws: optional float [K*Cin*Cout] scratch; when given (and Cin % 32 == 0, Cout <= 128,
+ * K <= 27) the tcgen05 tf32 implicit-GEMM kernel runs, otherwise the fp32 SIMT kernel. */
 int ddf_sparse_conv_forward(const float* features, const float* filters, const int* gather_table,
-                            const float* bias, float* out, int64_t n_out, int64_t kvol,
-                            int64_t cin, int64_t cout, void* stream);
+                            const float* bias, float* out, float* filters_t_ws, int64_t n_out,
+                            int64_t kvol, int64_t cin, int64_t cout, void* stream);
+
+/* Tensor-core bookkeeping: ddf_sparse_conv_tc_mode returns a bit mask of the kernels of a layer
+ * that run as tcgen05 tf32 implicit GEMMs (1 forward, 2 dgrad, 4 wgrad; 0 with DDF_DISABLE_TC=1).
+ * tf32 keeps 10 mantissa bits and the hardware TRUNCATES fp32 operands; ddf_round_tf32 rounds a
+ * tensor to the nearest tf32 first (dst may alias src) so the error is unbiased. Filters are
+ * rounded inside the conv calls. */
+int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout);
+int ddf_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 
 int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters, const int* scatter_table,
                           float* grad_in, float* filters_t_ws, int64_t n_in, int64_t kvol,

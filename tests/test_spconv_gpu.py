@@ -62,23 +62,26 @@ def test_conv_fwd_bwd_vs_oracle(geom, chan):
     ref_gi, ref_gw = osp.indice_conv_backward(feat, w, go, o_pairs, o_num)
 
     rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, dil, 0, subm, False)
+    # fp32 SIMT kernels: 1e-4.  Layers that run as tcgen05 implicit GEMMs multiply tf32 operands
+    # (10-bit mantissa, rounded to nearest) with fp32 accumulation: 1e-3 relative, the north_star bar.
+    tol = 1e-3 if ops.tc_mode(int(np.prod(ks)), cin, cout) else 1e-4
     # (a) hot path: table-driven Function
     f = torch.from_numpy(feat).cuda().requires_grad_()
     wt = torch.from_numpy(w).cuda().requires_grad_()
     out = Fsp.table_conv(f, wt, None, rb, len(o_out))
     out.backward(torch.from_numpy(go).cuda())
-    assert rel_err(out.detach().cpu().numpy(), ref) < 1e-4
-    assert rel_err(f.grad.cpu().numpy(), ref_gi) < 1e-4
-    assert rel_err(wt.grad.cpu().numpy(), ref_gw) < 1e-4
+    assert rel_err(out.detach().cpu().numpy(), ref) < tol
+    assert rel_err(f.grad.cpu().numpy(), ref_gi) < tol
+    assert rel_err(wt.grad.cpu().numpy(), ref_gw) < tol
     # (b) drop-in path: reference-named Functions on the reference-format rulebook
     f2 = torch.from_numpy(feat).cuda().requires_grad_()
     w2 = torch.from_numpy(w).cuda().requires_grad_()
     fn = Fsp.indice_subm_conv if subm else Fsp.indice_conv
     out2 = fn(f2, w2, rb.indice_pairs, rb.indice_pair_num, len(o_out))
     out2.backward(torch.from_numpy(go).cuda())
-    assert rel_err(out2.detach().cpu().numpy(), ref) < 1e-4
-    assert rel_err(f2.grad.cpu().numpy(), ref_gi) < 1e-4
-    assert rel_err(w2.grad.cpu().numpy(), ref_gw) < 1e-4
+    assert rel_err(out2.detach().cpu().numpy(), ref) < 1e-4  # drop-in forward stays fp32 SIMT
+    assert rel_err(f2.grad.cpu().numpy(), ref_gi) < tol
+    assert rel_err(w2.grad.cpu().numpy(), ref_gw) < tol
 
 
 def test_inverse_conv_roundtrip_shapes_and_values():
@@ -99,7 +102,7 @@ def test_inverse_conv_roundtrip_shapes_and_values():
     o_out, o_pairs, o_num, _ = osp.get_indice_pairs(idx, 2, shape, [3] * 3, [2] * 3, [1] * 3, [1] * 3, False, order="gpu")
     ref_y = osp.indice_conv(feat, down.weight.detach().cpu().numpy(), o_pairs, o_num, len(o_out))
     ref_z = osp.indice_conv(ref_y, up.weight.detach().cpu().numpy(), o_pairs, o_num, len(idx), inverse=True)
-    assert rel_err(z.features.detach().cpu().numpy(), ref_z) < 1e-4
+    assert rel_err(z.features.detach().cpu().numpy(), ref_z) < 1e-3
 
 
 def test_dense_matches_oracle_and_backward():
