@@ -1,0 +1,147 @@
+"""3D local self-attention over voxel queries: ``LocalTransformer``
+(<proj>/models/model_utils/pointformer.py:250-380) and its pre-norm encoder layer (:10-44).
+D-FPS picks ``npoint`` centres, a ball query groups ``nsample`` neighbours, a small MLP encodes the
+(absolute) neighbour coordinates, a pre-norm transformer attends inside each group and the result
+is written back to the voxels ("unique"/"replace": the FIRST grouped copy of a voxel in flattened
+(group, slot) order wins — the reference's scatter_ with duplicate indices is nondeterministic on
+CUDA; first occurrence is what it yields on CPU and is the contract here)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops.pointops import Points_Sampler, QueryAndGroup, gather_points
+
+
+class ConvModule(nn.Module):
+    """The subset of mmcv.cnn.ConvModule LocalTransformer uses: Conv2d (+ BN2d) (+ ReLU), with
+    mmcv's sub-module names ``conv`` / ``bn`` and bias only when there is no norm."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, norm_cfg=None, act_cfg=dict(type="ReLU")):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, bias=norm_cfg is None)
+        self.with_norm = norm_cfg is not None
+        if self.with_norm:
+            self.bn = nn.BatchNorm2d(out_channels)
+        self.with_activation = act_cfg is not None
+        if self.with_activation:
+            self.activate = nn.ReLU(inplace=True)
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode="fan_out", nonlinearity="relu")
+        if self.conv.bias is not None:
+            nn.init.constant_(self.conv.bias, 0)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_norm:
+            x = self.bn(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+class TransformerEncoderLayerPreNorm(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu"):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout, inplace=True)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout, inplace=True)
+        self.dropout2 = nn.Dropout(dropout, inplace=True)
+        self.activation = nn.ReLU(inplace=True)
+
+    def forward(self, src, src_mask=None, src_key_padding_mask=None, **kwargs):
+        src = self.norm1(src)
+        src2, _ = self.self_attn(src, src, src, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)
+        src = src + self.dropout1(src2)
+        src = self.norm2(src)
+        src2 = self.linear2(self.dropout(self.activation(self.linear1(src))))
+        return src + self.dropout2(src2)
+
+
+class _EncoderStack(nn.Module):
+    """nn.TransformerEncoder's state-dict layout (``layers.{i}.*``) without its fast-path checks."""
+
+    def __init__(self, layer, num_layers):
+        super().__init__()
+        import copy
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+    def forward(self, src):
+        for layer in self.layers:
+            src = layer(src)
+        return src
+
+
+def first_occurrence_scatter(attn_features, feats, idxs):
+    """attn_features (B, C, N) is updated IN PLACE: for every voxel that appears in ``idxs``
+    (B, np, ns), take the grouped feature of its first occurrence in flattened order."""
+    B, C, N = attn_features.shape
+    for b in range(B):
+        idx_f = idxs[b].reshape(-1).long()
+        feat_f = feats[b].reshape(C, -1)
+        pos = torch.arange(idx_f.numel(), device=idx_f.device)
+        first = torch.full((N,), idx_f.numel(), dtype=torch.long, device=idx_f.device)
+        first.scatter_reduce_(0, idx_f, pos, reduce="amin", include_self=True)
+        hit = first < idx_f.numel()
+        attn_features[b][:, hit] = feat_f[:, first[hit]]
+
+
+class LocalTransformer(nn.Module):
+    def __init__(self, npoint, radius, nsample, dim_feature, dim_out, nhead=4, num_layers=2,
+                 norm_cfg=dict(type="BN2d"), ratio=1, drop=0.0, prenorm=True,
+                 attn_feat_agg_method="unique", feat_agg_method="replace"):
+        super().__init__()
+        assert ratio == 1 and prenorm, "only the configuration 3D-DF uses is implemented"
+        self.npoint = npoint
+        self.nsample = nsample
+        self.radius = radius
+        self.nc_in = dim_feature
+        self.nc_out = dim_out
+        self.sampler = Points_Sampler([self.npoint], ["D-FPS"])
+        self.grouper = QueryAndGroup(self.radius, self.nsample, use_xyz=False, return_grouped_xyz=True,
+                                     return_grouped_idx=True, normalize_xyz=False)
+        self.pe = nn.Sequential(ConvModule(3, self.nc_in // 2, 1, norm_cfg=norm_cfg),
+                                ConvModule(self.nc_in // 2, self.nc_in, 1, act_cfg=None, norm_cfg=None))
+        self.chunk = _EncoderStack(
+            TransformerEncoderLayerPreNorm(d_model=self.nc_in, dim_feedforward=2 * self.nc_in, dropout=drop,
+                                           nhead=nhead), num_layers)
+        self.attn_feat_agg_method = attn_feat_agg_method
+        self.feat_agg_method = feat_agg_method
+
+    def scatter(self, attn_features, feats, idxs):
+        if self.attn_feat_agg_method == "unique":
+            first_occurrence_scatter(attn_features, feats, idxs)
+        elif self.attn_feat_agg_method == "sum":
+            B, C, N = attn_features.shape
+            for b in range(B):
+                idx_f = idxs[b].reshape(-1).long()
+                summed = torch.zeros_like(attn_features[b]).index_add_(1, idx_f, feats[b].reshape(C, -1))
+                cnt = torch.bincount(idx_f, minlength=N)
+                nz = cnt > 0
+                attn_features[b][:, nz] = (attn_features[b][:, nz] + summed[:, nz]) / cnt[nz]
+        else:
+            raise NotImplementedError(self.attn_feat_agg_method)
+
+    def forward(self, xyz, features):
+        """xyz (B, N, 3), features (B, C, N) -> (B, N, C). Mutates ``features`` like the reference."""
+        xyz = xyz.contiguous()
+        fps_idx = self.sampler(xyz, features)
+        new_xyz = gather_points(xyz.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2)
+        group_features, group_xyz, group_idx = self.grouper(xyz, new_xyz.contiguous(), features.contiguous())
+        input_features = group_features + self.pe(group_xyz)
+        B, D, n_p, ns = input_features.shape
+        tokens = input_features.permute(0, 2, 1, 3).reshape(-1, D, ns).permute(2, 0, 1)
+        transformed = self.chunk(tokens).permute(1, 2, 0).reshape(B, n_p, D, ns).transpose(1, 2)
+        if self.feat_agg_method == "replace":
+            features = features.clone() if features.requires_grad else features
+            self.scatter(features, transformed, group_idx)
+        elif self.feat_agg_method == "sum":
+            attn_features = torch.zeros_like(features)
+            self.scatter(attn_features, transformed, group_idx)
+            features = features + attn_features
+        else:
+            raise NotImplementedError(self.feat_agg_method)
+        return features.permute(0, 2, 1)

@@ -205,6 +205,37 @@ int ddf_dense_to_sparse(const float* grad_dense, const int* indices, float* grad
                         int64_t n, int64_t C, int64_t B, int64_t D, int64_t H, int64_t W,
                         void* stream);
 
+/* ---- Point-set ops of the 3D local self-attention (LocalTransformer) ---------------------
+ * Replace furthest_point_sample_ext / ball_query_ext / group_points_ext / gather_points_ext
+ *   reference: <proj>/ops/furthest_point_sample/src/furthest_point_sample.cpp (wrapper),
+ *              furthest_point_sample_cuda.cu:25-141; <proj>/ops/ball_query/src/ball_query.cpp:30-43,
+ *              ball_query_cuda.cu:11-54; <proj>/ops/group_points/src/group_points_cuda.cu:10-79;
+ *              <proj>/ops/gather_points/src/gather_points_cuda.cu:8-70
+ *   Python callers: furthest_point_sample.py:7-40, ball_query.py:7-47, group_points.py:153-208,
+ *              gather_points.py:7-52 (<proj> = TransFusion/mmdet3d, CenterPoint/det3d, ...)
+ * All tensors float32 / int32, contiguous.
+ *   furthest_point_sampling: xyz [B,N,3], temp [B,N] running min distance (in/out; NULL = 1e10
+ *       start, not written), idx [B,m] out. Picks are bit-identical to the reference kernel incl.
+ *       its tie-break (see pointops.cu). N <= 65536.
+ *   ball_query: new_xyz [B,m,3], xyz [B,N,3], idx [B,m,nsample] (ZERO-initialised by the caller as
+ *       in ball_query.py:36): first nsample points in index order with d2 == 0 or
+ *       min_r^2 <= d2 < max_r^2; unfilled slots repeat the first hit.
+ *   group_points: out[b,c,p,s] = features[b,c,idx[b,p,s]]; *_grad scatter-adds (grad zeroed inside).
+ *   gather_points: out[b,c,p] = points[b,c,idx[b,p]]; *_grad likewise.
+ */
+int ddf_furthest_point_sampling(const float* xyz, float* temp, int* idx, int64_t B, int64_t N,
+                                int64_t m, void* stream);
+int ddf_ball_query(const float* new_xyz, const float* xyz, int* idx, int64_t B, int64_t N, int64_t m,
+                   float min_radius, float max_radius, int64_t nsample, void* stream);
+int ddf_group_points(const float* features, const int* idx, float* out, int64_t B, int64_t C,
+                     int64_t N, int64_t npoints, int64_t nsample, void* stream);
+int ddf_group_points_grad(const float* grad_out, const int* idx, float* grad_features, int64_t B,
+                          int64_t C, int64_t N, int64_t npoints, int64_t nsample, void* stream);
+int ddf_gather_points(const float* points, const int* idx, float* out, int64_t B, int64_t C,
+                      int64_t N, int64_t npoints, void* stream);
+int ddf_gather_points_grad(const float* grad_out, const int* idx, float* grad_points, int64_t B,
+                           int64_t C, int64_t N, int64_t npoints, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch.autograd import Function
 
 from . import ref_build
+from . import pointops as opointops
 from . import spconv as ospconv
 from . import voxel as ovoxel
 
@@ -135,6 +136,41 @@ def _cpu_dense(self, channels_first=True):
     return ret.permute(0, 4, 1, 2, 3).contiguous() if channels_first else ret
 
 
+# ---- point ops (numpy restatements of the CUDA kernels; the reference has no CPU version) -------
+class _CpuGroup(Function):
+    @staticmethod
+    def forward(ctx, features, indices):
+        ctx.save_for_backward(indices)
+        ctx.n = features.shape[2]
+        return torch.from_numpy(opointops.grouping_operation(features.detach().numpy(), indices.numpy()))
+
+    @staticmethod
+    def backward(ctx, g):
+        (indices,) = ctx.saved_tensors
+        return torch.from_numpy(opointops.grouping_operation_grad(g.contiguous().numpy(), indices.numpy(), ctx.n)), None
+
+
+class _CpuGather(Function):
+    @staticmethod
+    def forward(ctx, features, indices):
+        ctx.save_for_backward(indices)
+        ctx.n = features.shape[2]
+        return torch.from_numpy(opointops.gather_points(features.detach().numpy(), indices.numpy()))
+
+    @staticmethod
+    def backward(ctx, g):
+        (indices,) = ctx.saved_tensors
+        return torch.from_numpy(opointops.gather_points_grad(g.contiguous().numpy(), indices.numpy(), ctx.n)), None
+
+
+def _cpu_fps(xyz, npoint):
+    return torch.from_numpy(opointops.furthest_point_sample(xyz.detach().numpy(), npoint))
+
+
+def _cpu_ball_query(min_r, max_r, ns, xyz, center):
+    return torch.from_numpy(opointops.ball_query(min_r, max_r, ns, xyz.detach().numpy(), center.detach().numpy()))
+
+
 @contextlib.contextmanager
 def reference_cpu_ops():
     """Patch the product's op entry points with the reference CPU implementations (from outside)."""
@@ -142,6 +178,8 @@ def reference_cpu_ops():
     import ddf_b200.ops.spconv.conv as m_conv
     import ddf_b200.ops.spconv.ops as m_ops
     import ddf_b200.ops.spconv.structure as m_struct
+    import ddf_b200.fusion.pointformer as m_pf
+    import ddf_b200.ops.pointops as m_po
     import ddf_b200.ops.voxel as m_voxel
 
     def build_rb(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, out_padding, subm, transposed):
@@ -153,13 +191,23 @@ def reference_cpu_ops():
              (m_ops, "build_rulebook", m_ops.build_rulebook),
              (m_conv.Fsp, "table_conv", m_conv.Fsp.table_conv),
              (m_struct.SparseConvTensor, "dense", m_struct.SparseConvTensor.dense),
-             (m_voxel, "voxelization", m_voxel.voxelization)]
+             (m_voxel, "voxelization", m_voxel.voxelization),
+             (m_po, "furthest_point_sample", m_po.furthest_point_sample),
+             (m_po, "ball_query", m_po.ball_query),
+             (m_po, "grouping_operation", m_po.grouping_operation),
+             (m_po, "gather_points", m_po.gather_points),
+             (m_pf, "gather_points", m_pf.gather_points)]
     try:
         m_msda.MSDeformAttnFunction = _CpuMSDA
         m_ops.build_rulebook = build_rb
         m_conv.Fsp.table_conv = _cpu_table_conv
         m_struct.SparseConvTensor.dense = _cpu_dense
         m_voxel.voxelization = cpu_voxelization
+        m_po.furthest_point_sample = _cpu_fps
+        m_po.ball_query = _cpu_ball_query
+        m_po.grouping_operation = _CpuGroup.apply
+        m_po.gather_points = _CpuGather.apply
+        m_pf.gather_points = _CpuGather.apply
         yield
     finally:
         for obj, name, val in saved:

@@ -1,0 +1,93 @@
+"""ORACLE (test infrastructure): numpy restatements of the point-set CUDA ops used by the 3D local
+self-attention. The reference has no CPU implementation of these; each function follows the kernel:
+
+  furthest_point_sample  <proj>/ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:25-141
+                         (incl. its tie-break: per-thread strided scan keeps the lowest index, the
+                         pairwise tree keeps the lower thread => lowest (k mod B), then lowest k,
+                         B = largest power of two <= n capped at 1024, :9-13)
+  ball_query             <proj>/ops/ball_query/src/ball_query_cuda.cu:11-54
+  grouping_operation     <proj>/ops/group_points/src/group_points_cuda.cu:10-31,56-79
+  gather_points          <proj>/ops/gather_points/src/gather_points_cuda.cu:8-26,51-70
+
+Pinned by the known-answer vectors of TransFusion/tests/test_models/test_common_modules/
+test_pointnet_ops.py:9-24 (FPS), :26-73 (ball query incl. dilated), :126-196 (grouping),
+:198-238 (gather) through tests/golden/pointops_golden.npz. fp32 arithmetic as written (no FMA).
+"""
+import numpy as np
+
+
+def _sqdist(a, b):
+    d = (b - a).astype(np.float32)
+    return ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32) \
+        + (d[..., 2] * d[..., 2]).astype(np.float32)
+
+
+def furthest_point_sample(xyz, npoint, temp=None):
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    B, N, _ = xyz.shape
+    idx = np.zeros((B, npoint), np.int32)
+    if npoint == 0:
+        return idx
+    block = 1
+    while block * 2 <= N and block < 1024:
+        block *= 2
+    k = np.arange(N)
+    tie = (k % block).astype(np.int64) * (1 << 21) + k // block   # smaller wins
+    for b in range(B):
+        dist = np.full((N,), 1e10, np.float32) if temp is None else temp[b]
+        old = 0
+        for j in range(1, npoint):
+            d = _sqdist(xyz[b, old][None, :], xyz[b]).astype(np.float32)
+            dist = np.minimum(d, dist)
+            best = dist.max()
+            cand = np.nonzero(dist == best)[0]
+            old = int(cand[np.argmin(tie[cand])])
+            idx[b, j] = old
+        if temp is not None:
+            temp[b] = dist
+    return idx
+
+
+def ball_query(min_radius, max_radius, nsample, xyz, new_xyz):
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    new_xyz = np.ascontiguousarray(new_xyz, np.float32)
+    B, N, _ = xyz.shape
+    m = new_xyz.shape[1]
+    idx = np.zeros((B, m, nsample), np.int32)
+    r0 = np.float32(min_radius) * np.float32(min_radius)
+    r1 = np.float32(max_radius) * np.float32(max_radius)
+    for b in range(B):
+        for p in range(m):
+            d2 = _sqdist(xyz[b], new_xyz[b, p][None, :])  # (new - x)^2, same squares
+            hits = np.nonzero((d2 == 0) | ((d2 >= r0) & (d2 < r1)))[0][:nsample]
+            if len(hits):
+                idx[b, p, :] = hits[0]
+                idx[b, p, :len(hits)] = hits
+    return idx
+
+
+def grouping_operation(features, idx):
+    """features (B,C,N), idx (B,np,ns) -> (B,C,np,ns)."""
+    B, C, N = features.shape
+    return np.stack([features[b][:, idx[b]] for b in range(B)])
+
+
+def grouping_operation_grad(grad_out, idx, N):
+    B, C = grad_out.shape[:2]
+    g = np.zeros((B, C, N), grad_out.dtype)
+    for b in range(B):
+        np.add.at(g[b], (slice(None), idx[b].reshape(-1)), grad_out[b].reshape(C, -1))
+    return g
+
+
+def gather_points(points, idx):
+    """points (B,C,N), idx (B,M) -> (B,C,M)."""
+    return np.stack([points[b][:, idx[b]] for b in range(points.shape[0])])
+
+
+def gather_points_grad(grad_out, idx, N):
+    B, C = grad_out.shape[:2]
+    g = np.zeros((B, C, N), grad_out.dtype)
+    for b in range(B):
+        np.add.at(g[b], (slice(None), idx[b]), grad_out[b])
+    return g
