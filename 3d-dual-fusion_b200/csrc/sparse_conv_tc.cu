@@ -149,7 +149,9 @@ spconv_tc_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t mask = *s_mask;
   const uint32_t tmem_base = *s_tmem;
-  const int n_chunks = cin / KCH;
+  const int n_chunks = (cin + KCH - 1) / KCH;
+  const int kc = cin < KCH ? cin : KCH;   // floats per chunk actually present (cin < 32: one partial chunk)
+  const int live_chunks = kc >> 2;         // 16-byte pieces per row to copy
 
   if (warp < 4) {
     // ===================== producers: gather A, stream B =====================
@@ -167,18 +169,22 @@ spconv_tc_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
         for (int i = 0; i < (TM * 8) / kProducers; ++i) {
           const int e = i * kProducers + tid;
           const int r = e >> 3, ch = e & 7;
-          const int j = s_idx[r * kvol + k];
-          const float* src = feat + (j >= 0 ? ((long long)j * cin + c0 + ch * 4) : 0);
-          cp_async16(a_smem + r * 128 + ((ch ^ (r & 7)) << 4), src, j >= 0 ? 16u : 0u);
+          if (ch < live_chunks) {
+            const int j = s_idx[r * kvol + k];
+            const float* src = feat + (j >= 0 ? ((long long)j * cin + c0 + ch * 4) : 0);
+            cp_async16(a_smem + r * 128 + ((ch ^ (r & 7)) << 4), src, j >= 0 ? 16u : 0u);
+          }
         }
 #pragma unroll
         for (int i = 0; i < (CO * 8 + kProducers - 1) / kProducers; ++i) {
           const int e = i * kProducers + tid;
           if (e < CO * 8) {
             const int r = e >> 3, ch = e & 7;
-            const bool ok = r < cout;
-            const float* src = wk + (ok ? ((long long)r * cin + c0 + ch * 4) : 0);
-            cp_async16(b_smem + r * 128 + ((ch ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+            if (ch < live_chunks) {
+              const bool ok = r < cout;
+              const float* src = wk + (ok ? ((long long)r * cin + c0 + ch * 4) : 0);
+              cp_async16(b_smem + r * 128 + ((ch ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+            }
           }
         }
         cp_async_arrive_noinc(full_bar + stage);
@@ -250,9 +256,8 @@ spconv_tc_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
           const uint32_t a_smem = smem_u32(stage_base + stage * Cfg::kStageBytes);
           const uint64_t a_desc = make_desc_sw128(a_smem);
           const uint64_t b_desc = make_desc_sw128(a_smem + Cfg::kABytes);
-#pragma unroll
-          for (int ks = 0; ks < KCH / 8; ++ks) {
-            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+          for (int ks = 0; ks < (kc >> 3); ++ks) {
+            // only the K steps backed by real channels are issued; advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
             umma_tf32(tmem_base, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, accumulate);
             accumulate = 1;
           }
@@ -297,16 +302,20 @@ int launch_tc(const float* feat, const float* wt, const int* table, const float*
 // ------------------------------------------------------------------------------------------------
 // wgrad on tensor cores:  gW[k] (Cin x Cout) = sum over the pairs (i, o) of offset k of
 //   feat[i, :]^T . gout[o, :]
-// = a GEMM with M = Cin (padded to 128 TMEM lanes), N = Cout, K = pairs.  The gathered rows are
-// channel-contiguous, i.e. both operands are MN-major.  For 32-bit MN-major operands the only UMMA
-// smem layout is SWIZZLE_128B_BASE32B: atoms of 4 pairs x 32 channels (4 rows of 128 bytes), the
-// 32-byte chunk index XORed with (pair & 3).  Atoms of one 4-pair group are contiguous (LBO = 512 B
-// between 32-channel blocks, SBO between 4-pair groups); one tf32 MMA (K = 8) spans two groups.
-// Grid (kvol, S): CTA (k, s) reduces slice s of pair list k in stages of 32 pairs (4 MMAs, K = 8)
-// into TMEM and adds its tile to gW[k] with 16-byte red.global.
+// = a GEMM with M = Cin (128 TMEM lanes; lanes >= Cin hold don't-care rows), N = Cout, K = pairs.
+// The gathered rows are channel-contiguous, i.e. both operands are MN-major.  For 32-bit MN-major
+// operands the only UMMA smem layout is SWIZZLE_128B_BASE32B: atoms of 4 pairs x 32 channels
+// (4 rows of 128 bytes), the 32-byte chunk index XORed with (pair & 3).  Atoms of one 4-pair group
+// are contiguous (LBO = 512 B between 32-channel blocks, SBO between 4-pair groups); one tf32 MMA
+// (K = 8) spans two groups.
+//
+// Scheduling: the pair lists of all kernel offsets are cut into stages of WP pairs and the global
+// stage sequence (offset-major) is divided EVENLY over a persistent grid of 2 CTAs per SM, so the
+// load is balanced whatever the per-offset pair counts are.  A CTA accumulates a segment (its
+// stages of one offset) in TMEM, adds the tile to gW[k] with 16-byte red.global, and moves on to
+// the next offset if its range crosses one.  Pair indices of stage g+1 are fetched while stage g
+// is being issued (one index per producer thread, staged through shared memory).
 // ------------------------------------------------------------------------------------------------
-constexpr int WPAIRS = 32;  // pairs per stage
-
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -322,50 +331,46 @@ __device__ __forceinline__ uint32_t mn_chunk_offset(int p, int mb, int ch, int n
   return (uint32_t)((((p >> 2) * nblk + mb) << 9) + (r << 7) + ((((ch >> 1) ^ r)) << 5) + ((ch & 1) << 4));
 }
 
-template <int CO>
-struct WgCfg {
-  static constexpr int kStages = 3;
-  static constexpr int kABytes = WPAIRS * 128 * 4;   // M padded to 128 channels: 16 KB
-  static constexpr int kBBytes = WPAIRS * CO * 4;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
-};
+constexpr int kWgStages = 3;
+constexpr int kWgStageBytes = 32 * 1024;                       // A + B tile budget per stage
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 2048 /*dead-block over-read slack*/ +
+                             2 * 128 * 4 /*pair indices*/ + 512 /*barriers, offsets*/ + 1024;
 
 template <int CO>
 __global__ void __launch_bounds__(kThreadsTC)
 spconv_wgrad_tc_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
                        const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
-                       int cin, int cout, int inverse, float* __restrict__ gw) {
-  using Cfg = WgCfg<CO>;
+                       int kvol, int cin, int cout, int inverse, float* __restrict__ gw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  int* s_pidx = reinterpret_cast<int*>(smem + kWgStages * kWgStageBytes + 2048);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_pidx + 256);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* accum_bar = bars + 2 * Cfg::kStages;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+  uint64_t* empty_bar = bars + kWgStages;
+  uint64_t* accum_bar = bars + 2 * kWgStages;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  int* s_first = reinterpret_cast<int*>(s_tmem + 1);  // [kvol + 1] first global stage of each offset
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k = blockIdx.x;
-  const int nk = num[k];
-  const int S = gridDim.y;
-  // slices are multiples of the stage size so only the last stage of a slice is ragged
-  int per = (nk + S - 1) / S;
-  per = ((per + WPAIRS - 1) / WPAIRS) * WPAIRS;
-  const int s0 = blockIdx.y * per;
-  const int s1 = min(nk, s0 + per);
-  if (s0 >= s1) return;  // uniform for the CTA, before any barrier / TMEM allocation
-  const int n_stage = (s1 - s0 + WPAIRS - 1) / WPAIRS;
-  const int* pin = pairs + ((long long)k * 2 + (inverse ? 1 : 0)) * pair_stride;
-  const int* pout = pairs + ((long long)k * 2 + (inverse ? 0 : 1)) * pair_stride;
   constexpr int kTmemCols = CO < 32 ? 32 : CO;
+  const int a_nb = (cin + 31) >> 5;            // 32-channel blocks per pair row
+  const int b_nb = CO < 32 ? 1 : CO / 32;
+  // pairs per stage: 64 when two tiles of 64 rows fit the stage budget, else 32
+  const int WP = (64 * (a_nb + b_nb) * 128 <= kWgStageBytes) ? 64 : 32;
+  const int a_bytes = WP * a_nb * 128;
 
   if (tid == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kWgStages; ++s) {
       mbar_init(full_bar + s, kProducers);
       mbar_init(empty_bar + s, 1);
     }
     mbar_init(accum_bar, 1);
+    int acc = 0;
+    for (int k = 0; k < kvol; ++k) {
+      s_first[k] = acc;
+      acc += (num[k] + WP - 1) / WP;
+    }
+    s_first[kvol] = acc;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -374,110 +379,128 @@ spconv_wgrad_tc_kernel(const float* __restrict__ feat, const float* __restrict__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // channel blocks of A beyond cin are zero for the whole kernel: clear them once
-  const int a_blocks = cin / 32;  // live 32-channel blocks of the 4
-  if (a_blocks < 4) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      uint8_t* a = smem + s * Cfg::kStageBytes;
-      for (int e = tid; e < Cfg::kABytes / 16; e += kThreadsTC) {
-        const int atom = e >> 5;  // 32 chunks of 16 B per 512-B atom
-        if ((atom & 3) >= a_blocks) reinterpret_cast<float4*>(a)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
-  const int nb = CO / 32;           // 32-channel blocks of B (CO is the padded width)
-  const int b_live = cout / 32;
+  const long long total = s_first[kvol];
+  const int g_begin = (int)(total * blockIdx.x / gridDim.x);
+  const int g_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp < 4) {
-    int stage = 0;
-    uint32_t phase = 0;
-    const int a_chunks = a_blocks * 8;  // 16-B chunks per pair row of A
-    const int b_chunks = b_live * 8;
-    for (int it = 0; it < n_stage; ++it) {
-      mbar_wait(empty_bar + stage, phase ^ 1u);
-      const uint32_t a_smem = smem_u32(smem + stage * Cfg::kStageBytes);
-      const uint32_t b_smem = a_smem + Cfg::kABytes;
-      const int p0 = s0 + it * WPAIRS;
-      for (int e = tid; e < WPAIRS * a_chunks; e += kProducers) {
-        const int p = e / a_chunks, cc = e % a_chunks;
-        const int mb = cc >> 3, ch = cc & 7;
-        const bool ok = p0 + p < s1;
-        const int row = ok ? __ldg(pin + p0 + p) : 0;
-        const uint32_t dst = a_smem + mn_chunk_offset(p, mb, ch, 4);
-        cp_async16(dst, feat + (long long)row * cin + cc * 4, ok ? 16u : 0u);
-      }
-      for (int e = tid; e < WPAIRS * b_chunks; e += kProducers) {
-        const int p = e / b_chunks, cc = e % b_chunks;
-        const int mb = cc >> 3, ch = cc & 7;
-        const bool ok = p0 + p < s1;
-        const int row = ok ? __ldg(pout + p0 + p) : 0;
-        const uint32_t dst = b_smem + mn_chunk_offset(p, mb, ch, nb);
-        cp_async16(dst, gout + (long long)row * cout + cc * 4, ok ? 16u : 0u);
-      }
-      cp_async_arrive_noinc(full_bar + stage);
-      if (++stage == Cfg::kStages) {
-        stage = 0;
-        phase ^= 1u;
-      }
-    }
-    // epilogue: lane = input channel, columns = output channels
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int ci = warp * 32 + lane;
-#pragma unroll
-    for (int cb = 0; cb < CO; cb += 16) {
-      uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-            "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-            "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (ci < cin && cb < cout) {
-        float* dst = gw + ((long long)k * cin + ci) * cout + cb;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else {
-    if (lane == 0) {
-      // M = 128, N = CO, both operands MN-major
-      constexpr uint32_t idesc = make_idesc_tf32(CO) | (1u << 15) | (1u << 16);
+  if (g_begin < g_end) {
+    int k = 0;
+    while (s_first[k + 1] <= g_begin) ++k;  // offset that owns the first stage
+    if (warp < 4) {
+      // ===================== producers (+ epilogue at segment ends) =====================
       int stage = 0;
-      uint32_t phase = 0, accumulate = 0;
-      for (int it = 0; it < n_stage; ++it) {
-        mbar_wait(full_bar + stage, phase);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      uint32_t phase = 0, accum_phase = 0;
+      const int a_chunks = cin >> 2, b_chunks = cout >> 2;
+      // which pair index this thread fetches for a stage: threads 0..63 input rows, 64..127 output rows
+      auto fetch = [&](int g, int kk) -> int {
+        const int p = (g - s_first[kk]) * WP + (tid & 63);
+        if ((tid & 63) >= WP || p >= num[kk]) return -1;
+        const int col = (tid < 64) ? (inverse ? 1 : 0) : (inverse ? 0 : 1);
+        return __ldg(pairs + ((long long)kk * 2 + col) * pair_stride + p);
+      };
+      s_pidx[tid] = fetch(g_begin, k);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      int g = g_begin;
+      while (g < g_end) {
+        const int seg_end = min(g_end, s_first[k + 1]);
+        for (; g < seg_end; ++g) {
+          // prefetch the next stage's pair index (possibly of the next offset)
+          int nk = k;
+          if (g + 1 >= s_first[k + 1]) {
+            nk = k + 1;
+            while (nk < kvol && s_first[nk + 1] <= g + 1) ++nk;
+          }
+          const int nxt = (g + 1 < g_end) ? fetch(g + 1, nk) : -1;
+          const int* idx_a = s_pidx + ((g - g_begin) & 1) * 128;
+          const int* idx_b = idx_a + 64;
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          const uint32_t a_smem = smem_u32(smem + stage * kWgStageBytes);
+          const uint32_t b_smem = a_smem + a_bytes;
+          for (int e = tid; e < WP * a_chunks; e += kProducers) {
+            const int p = e / a_chunks, cc = e % a_chunks;
+            const int row = idx_a[p];
+            cp_async16(a_smem + mn_chunk_offset(p, cc >> 3, cc & 7, a_nb),
+                       feat + (row >= 0 ? ((long long)row * cin + cc * 4) : 0), row >= 0 ? 16u : 0u);
+          }
+          for (int e = tid; e < WP * b_chunks; e += kProducers) {
+            const int p = e / b_chunks, cc = e % b_chunks;
+            const int row = idx_b[p];
+            cp_async16(b_smem + mn_chunk_offset(p, cc >> 3, cc & 7, b_nb),
+                       gout + (row >= 0 ? ((long long)row * cout + cc * 4) : 0), row >= 0 ? 16u : 0u);
+          }
+          cp_async_arrive_noinc(full_bar + stage);
+          if (++stage == kWgStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          s_pidx[((g + 1 - g_begin) & 1) * 128 + tid] = nxt;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // segment done: drain the accumulator of offset k into gW[k]
+        mbar_wait(accum_bar, accum_phase);
+        accum_phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_smem = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t b_smem = a_smem + Cfg::kABytes;
+        const int ci = warp * 32 + lane;
 #pragma unroll
-        for (int ks = 0; ks < WPAIRS / 8; ++ks) {
-          const uint64_t a_desc = make_desc_mn_sw128(a_smem + ks * 2 * 4 * 512, 4 * 512);
-          const uint64_t b_desc = make_desc_mn_sw128(b_smem + ks * 2 * nb * 512, nb * 512);
-          umma_tf32(tmem_base, a_desc, b_desc, idesc, accumulate);
-          accumulate = 1;
+        for (int cb = 0; cb < CO; cb += 16) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ci < cin && cb < cout) {
+            float* dst = gw + ((long long)k * cin + ci) * cout + cb;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          }
         }
-        umma_commit(empty_bar + stage);
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        ++k;
+        while (k < kvol && s_first[k + 1] <= g) ++k;  // skip offsets without pairs
       }
-      umma_commit(accum_bar);
+    } else if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_tf32(CO) | (1u << 15) | (1u << 16);  // A, B MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      int g = g_begin;
+      while (g < g_end) {
+        const int seg_end = min(g_end, s_first[k + 1]);
+        uint32_t accumulate = 0;
+        for (; g < seg_end; ++g) {
+          mbar_wait(full_bar + stage, phase);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_smem = smem_u32(smem + stage * kWgStageBytes);
+          const uint32_t b_smem = a_smem + a_bytes;
+          for (int ks = 0; ks < WP / 8; ++ks) {
+            const uint64_t a_desc = make_desc_mn_sw128(a_smem + ks * 2 * a_nb * 512, a_nb * 512);
+            const uint64_t b_desc = make_desc_mn_sw128(b_smem + ks * 2 * b_nb * 512, b_nb * 512);
+            umma_tf32(tmem_base, a_desc, b_desc, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(empty_bar + stage);
+          if (++stage == kWgStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(accum_bar);
+        ++k;
+        while (k < kvol && s_first[k + 1] <= g) ++k;
+      }
     }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == 4) {
@@ -491,21 +514,19 @@ template <int CO>
 int launch_wgrad_tc(const float* feat, const float* gout, const int* pairs, const int* num,
                     int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
                     cudaStream_t stream) {
-  using Cfg = WgCfg<CO>;
   static bool configured = false;
   if (!configured) {
     DDF_CUDA(cudaFuncSetAttribute(spconv_wgrad_tc_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
+                                  kWgSmemBytes));
     configured = true;
   }
-  // ~4 waves of (offset, slice) CTAs, each slice at least 256 pairs when the list is that long
-  int S = (int)ddf::cdiv(4 * ddf::kNumSM, kvol);
-  const int maxS = (int)ddf::cdiv(pair_stride, 256);
-  if (S > maxS) S = maxS;
-  if (S < 1) S = 1;
-  dim3 grid((unsigned)kvol, (unsigned)S);
-  DDF_LAUNCH(spconv_wgrad_tc_kernel<CO>, grid, kThreadsTC, Cfg::kSmemBytes, stream, feat, gout, pairs,
-             num, (int)pair_stride, cin, cout, inverse, gw);
+  // persistent grid: 2 CTAs per SM (100 KB of smem each), fewer when the lists are short
+  long long grid = 2 * ddf::kNumSM;
+  const long long max_useful = ddf::cdiv((long long)pair_stride * kvol, 256);
+  if (grid > max_useful) grid = max_useful;
+  if (grid < 1) grid = 1;
+  DDF_LAUNCH(spconv_wgrad_tc_kernel<CO>, (unsigned)grid, kThreadsTC, kWgSmemBytes, stream, feat, gout,
+             pairs, num, (int)pair_stride, kvol, cin, cout, inverse, gw);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
@@ -516,7 +537,7 @@ namespace ddf {
 
 // true when the tensor-core kernel can take this launch
 bool spconv_tc_supported(int kvol, int cin, int cout) {
-  return kvol <= kMaxKvol && cin % KCH == 0 && cin >= KCH && cout >= 8 && cout <= 128;
+  return kvol <= kMaxKvol && (cin % KCH == 0 || cin == 8 || cin == 16 || cin == 24) && cout >= 8 && cout <= 128;
 }
 
 // feat [n_in, cin]; wt [K, cout, cin] (K-major B operand); table [n_out, K]
@@ -530,13 +551,14 @@ int spconv_tc_launch(const float* feat, const float* wt, const int* table, const
 
 
 bool spconv_wgrad_tc_supported(int cin, int cout) {
-  return cin % 32 == 0 && cout % 32 == 0 && cin >= 32 && cin <= 128 && cout >= 32 && cout <= 128;
+  return cin % 4 == 0 && cout % 16 == 0 && cin >= 4 && cin <= 128 && cout >= 16 && cout <= 128;  // kvol <= 100
 }
 
 // gw must be zeroed by the caller; tiles are accumulated with red.global
 int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pairs, const int* num,
                            int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
                            cudaStream_t stream) {
+  if (cout <= 16) return launch_wgrad_tc<16>(feat, gout, pairs, num, pair_stride, gw, kvol, cin, cout, inverse, stream);
   if (cout <= 32) return launch_wgrad_tc<32>(feat, gout, pairs, num, pair_stride, gw, kvol, cin, cout, inverse, stream);
   if (cout <= 64) return launch_wgrad_tc<64>(feat, gout, pairs, num, pair_stride, gw, kvol, cin, cout, inverse, stream);
   return launch_wgrad_tc<128>(feat, gout, pairs, num, pair_stride, gw, kvol, cin, cout, inverse, stream);

@@ -1,5 +1,6 @@
 """autograd Functions with the reference's names (TransFusion/mmdet3d/ops/spconv/functional.py:20-98)
 plus the table-driven Function the SparseConvolution module uses on the hot path."""
+import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
@@ -73,6 +74,14 @@ class TableConvFunction(Function):
         features = features.contiguous()
         filters = filters.contiguous()
         cin, cout = filters.shape[-2], filters.shape[-1]
+        ctx.cin = cin
+        pad = ops.padded_cin(rulebook.indice_pairs.shape[0], cin, cout) - cin
+        if pad:
+            # e.g. the 5-channel input layer: zero-pad the contraction to a multiple of 8 so the rows
+            # are 16-byte aligned and the layer runs on the tensor-core kernels like all the others
+            features = torch.nn.functional.pad(features, (0, pad))
+            filters = torch.nn.functional.pad(filters, (0, 0, 0, pad))
+            cin += pad
         ctx.mode = mode = ops.tc_mode(rulebook.indice_pairs.shape[0], cin, cout)
         if mode & 5 and features.shape[0]:
             # tensor-core operands are made exact tf32 once; forward and wgrad share the copy
@@ -96,6 +105,9 @@ class TableConvFunction(Function):
             gin = ops.sparse_conv_dgrad(filters, grad_output, rb.scatter_table, features.shape[0])
         if ctx.needs_input_grad[1]:
             gw = ops.sparse_conv_wgrad(features, filters, grad_output, rb.indice_pairs, rb.indice_pair_num)
+        if ctx.cin != filters.shape[-2]:  # drop the zero-padded input channels again
+            gin = gin[:, :ctx.cin].contiguous() if gin is not None else None
+            gw = gw[..., :ctx.cin, :].contiguous() if gw is not None else None
         return gin, gw, gb, None, None
 
 

@@ -165,6 +165,15 @@ def tc_mode(kvol, cin, cout):
     return int(_lib.get_lib().ddf_sparse_conv_tc_mode(int(kvol), int(cin), int(cout)))
 
 
+def padded_cin(kvol, cin, cout):
+    """Input-channel count the hot-path Function actually runs a layer with: narrow, unaligned
+    contractions (e.g. the 5-channel input layer) are zero-padded to a multiple of 8 when that puts
+    the layer on the tensor-core kernels."""
+    if cin < 32 and cin % 8 and tc_mode(kvol, cin + (-cin) % 8, cout):
+        return cin + (-cin) % 8
+    return cin
+
+
 def round_tf32(x):
     """Copy of ``x`` rounded to the nearest tf32 (operand preparation for the tensor-core kernels)."""
     x = x.contiguous()

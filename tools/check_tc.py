@@ -15,7 +15,7 @@ idx = random_voxels(20000, 2, shape, seed=4)
 for subm, ks, st, pad in [(True, [3]*3, [1]*3, [1]*3), (False, [3]*3, [2]*3, [1]*3)]:
     o_out, o_pairs, o_num, _ = osp.get_indice_pairs(idx, 2, shape, ks, st, pad, [1]*3, subm, order="gpu")
     rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, 1, 0, subm, False)
-    for cin, cout in [(32, 32), (32, 64), (64, 64), (64, 128), (128, 128), (16, 32)]:
+    for cin, cout in [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128), (8, 16), (24, 48)]:
         rng = np.random.default_rng(1)
         feat = rng.standard_normal((len(idx), cin)).astype(np.float32)
         w = (rng.standard_normal((*ks, cin, cout)) / np.sqrt(cin * 9)).astype(np.float32)
