@@ -69,7 +69,10 @@ class ACTR(nn.Module):
         q_i_feat = None
         if self.feature_modal in ["image", "hybrid"]:
             assert v_i_feat is not None
-            q_i_feat = self.i_input_proj(v_i_feat.transpose(1, 2)).transpose(1, 2)
+            # Conv1d(k=1) on (B', C, Lq) == Linear on (B', Lq, C): skip the two transposes around it
+            conv, gn = self.i_input_proj[0], self.i_input_proj[1]
+            q_i_feat = torch.nn.functional.linear(v_i_feat, conv.weight.squeeze(-1), conv.bias)
+            q_i_feat = gn(q_i_feat.transpose(1, 2)).transpose(1, 2)
             if self.feature_modal == "image":
                 q_feat = q_i_feat
         if self.pos_encode_method == "image_coor":

@@ -15,8 +15,9 @@ class _BiGateBase(nn.Module):
 
     @staticmethod
     def _gate(conv, x):
-        # Conv1d(C -> 1, k=1) over (B, L, C) laid out channel-last: a per-row dot product
-        return torch.sigmoid(conv(x.permute(0, 2, 1)).permute(0, 2, 1))
+        # Conv1d(C -> 1, k=1) over (B, L, C) laid out channel-last is a per-row dot product: run it as
+        # a matmul on the rows (same parameters, weight [1, C, 1]) instead of a cuDNN grouped conv
+        return torch.sigmoid(torch.nn.functional.linear(x, conv.weight.squeeze(-1), conv.bias))
 
 
 class BiGate1D(_BiGateBase):

@@ -69,3 +69,35 @@ def nusc_img_meta(n_cam=6, ori_hw=(900, 1600), input_hw=(448, 800)):
 def camera_features(batch, n_cam, hw, channels=256, seed=0):
     rng = np.random.default_rng(seed)
     return rng.standard_normal((batch * n_cam, channels, hw[0], hw[1]), dtype=np.float32)
+
+
+CP_CAMS = ["CAM_FRONT", "CAM_FRONT_LEFT", "CAM_FRONT_RIGHT", "CAM_BACK", "CAM_BACK_LEFT", "CAM_BACK_RIGHT"]
+
+
+def centerpoint_batch(batch, feat_hw=(150, 267), img_hw=(600, 1066), ori_hw=(900, 1600), channels=256, seed=0):
+    """Det3D batch_dict pieces VoxelWithPointProjection reads (SURVEY.md 8(b) metadata contract)."""
+    import torch
+    rig = camera_rig(6, ori_hw)             # K @ [R|t]; split back into extrinsic / intrinsic
+    focal = 1266.0
+    K = np.array([[focal, 0, ori_hw[1] / 2.0], [0, focal, ori_hw[0] / 2.0], [0, 0, 1]], np.float64)
+    rng = np.random.default_rng(seed)
+    calib, image_shape, img_feat = {}, {}, {}
+    for i, cam in enumerate(CP_CAMS):
+        key = cam.lower()[4:]
+        Kinv = np.linalg.inv(K)
+        ext = np.eye(4)
+        ext[:3, :] = Kinv @ rig[i][:3, :]
+        calib["lidar2cam_" + key] = torch.from_numpy(np.repeat(ext[None], batch, 0).astype(np.float32))
+        calib["cam_intrinsic_" + key] = torch.from_numpy(np.repeat(K[None], batch, 0).astype(np.float32))
+        image_shape[cam.lower()] = torch.tensor([list(img_hw)] * batch)
+        img_feat[cam.lower()] = torch.from_numpy(rng.standard_normal((batch, channels, *feat_hw), dtype=np.float32))
+    return dict(calib=calib, image_shape=image_shape, img_feat={"layer1_ori_feat2d": img_feat})
+
+
+def kitti_lidar2img(img_hw=(375, 1242), focal=721.5):
+    """Single forward camera (x forward) for the KITTI-shaped config: (3, 4) LiDAR -> pixel matrix."""
+    H, W = img_hw
+    K = np.array([[focal, 0, W / 2.0], [0, focal, H / 2.0], [0, 0, 1]], np.float64)
+    R = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])  # cam x = -y_l, cam y = -z_l, cam z = x_l
+    t = -R @ np.array([0.27, 0.0, -0.08])
+    return (K @ np.concatenate([R, t[:, None]], 1)).astype(np.float32)

@@ -7,6 +7,7 @@ import configs, synth
 from ddf_b200.fusion.detector import TransFusionPtsBranch
 import ddf_b200.fusion.point_fusion, ddf_b200.fusion.sparse_encoder, ddf_b200.fusion.voxel_encoder
 torch.manual_seed(0)
+torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
 m = TransFusionPtsBranch(**configs.transfusion_f()).cuda().train()
 B = 2
 pts = [torch.from_numpy(synth.lidar_points(260000, seed=b)).cuda() for b in range(B)]
@@ -27,4 +28,4 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     out = m(pts, img_feats, metas); loss = out.square().mean(); opt.zero_grad(); loss.backward(); opt.step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=35, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=60))
