@@ -91,6 +91,21 @@ def cpu_build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, pa
     else:
         o, p, n, _ = ospconv.get_indice_pairs(indices.numpy(), batch_size, spatial_shape, ksize, stride, padding, dilation, subm)
         outids, pairs, num = torch.from_numpy(np.ascontiguousarray(o)), torch.from_numpy(p), torch.from_numpy(n)
+    if not subm and outids.shape[0] > 0:
+        # the reference CPU path numbers output voxels in first-touch order, its GPU path (and the
+        # product) in sorted flat (b,z,y,x) order (spconv_ops.h:129-137); ops that depend on the row
+        # order (FPS start / ball-query order in the LocalTransformer) need the same order on both sides
+        flat = outids[:, 0].long()
+        for d in range(3):
+            flat = flat * out_shape[d] + outids[:, 1 + d].long()
+        perm = torch.argsort(flat, stable=True)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel())
+        outids = outids[perm].contiguous()
+        pairs = pairs.clone()
+        for k in range(pairs.shape[0]):
+            nk = int(num[k])
+            pairs[k, 1, :nk] = inv[pairs[k, 1, :nk].long()].int()
     return _CpuRulebook(outids, pairs, num, out_shape)
 
 
