@@ -30,13 +30,15 @@ int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pair
 
 namespace {
 
-// DDF_DISABLE_TC=1 forces the fp32 SIMT kernels (A/B testing, bit-for-bit fp32 accumulation)
+// DDF_DISABLE_TC=1 (or ddf_set_tensor_cores(0)) forces the fp32 SIMT kernels: full fp32 products,
+// used for A/B timing and for the strict 1e-3 whole-path parity test
+int g_tc_state = -1;  // -1: not read yet
 bool tc_enabled() {
-  static const bool on = [] {
+  if (g_tc_state < 0) {
     const char* e = getenv("DDF_DISABLE_TC");
-    return !(e && e[0] == '1');
-  }();
-  return on;
+    g_tc_state = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_tc_state != 0;
 }
 
 
@@ -357,6 +359,13 @@ extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_ou
         features, grad_out, indice_pairs, indice_num, (int)pair_stride, (int)cin, (int)cout, inverse, grad_filters);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
+}
+
+// Runtime switch of the tensor-core conv kernels; returns the previous setting.
+extern "C" int ddf_set_tensor_cores(int on) {
+  const int prev = tc_enabled() ? 1 : 0;
+  g_tc_state = on ? 1 : 0;
+  return prev;
 }
 
 // Which of the three conv kernels of a (kvol, cin, cout) layer run on the tensor cores:

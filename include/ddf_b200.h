@@ -183,6 +183,9 @@ int ddf_sparse_conv_forward(const float* features, const float* filters, const i
  * tensor to the nearest tf32 first (dst may alias src) so the error is unbiased. Filters are
  * rounded inside the conv calls. */
 int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout);
+/* Switch the tcgen05 conv kernels on (1, default) or off (0 = fp32 SIMT kernels, full fp32 products);
+ * returns the previous setting. Not thread-safe against concurrent conv calls. */
+int ddf_set_tensor_cores(int on);
 int ddf_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 
 int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters, const int* scatter_table,

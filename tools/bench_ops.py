@@ -82,11 +82,142 @@ def bench_msda(args):
                           alg_MB=bwd_bytes / 1e6, GBs=bwd_bytes / med / 1e6, frac=bwd_bytes / med / 1e6 / hbm, peak=how)))
 
 
+def _tf_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), "measured bf16 burst"
+    return 1590.0, "fallback bf16"
+
+
+def _scene(args):
+    """Voxelised synthetic nuScenes sweep(s): int32 [N,4] (b,z,y,x) indices + the points."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    from ddf_b200.ops.voxel import Voxelization
+    vox = Voxelization(synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, (120000, 160000)).cuda().train()
+    idx, pts_all = [], []
+    for b in range(args.batch):
+        pts = torch.from_numpy(synth.lidar_points(args.points, seed=b)).cuda()
+        _, coors, _ = vox(pts)
+        idx.append(torch.nn.functional.pad(coors, (1, 0), value=b))
+        pts_all.append(pts)
+    return torch.cat(idx).contiguous(), pts_all
+
+
+def bench_voxel(args):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    from ddf_b200.ops import voxel
+    pts = torch.from_numpy(synth.lidar_points(args.points, seed=0)).cuda()
+    n, f = pts.shape
+    T, cap = 10, 120000
+    voxels = pts.new_empty((cap, T, f)); coors = pts.new_empty((cap, 3), dtype=torch.int)
+    npv = pts.new_empty((cap,), dtype=torch.int)
+    m = voxel.hard_voxelize(pts, voxels, coors, npv, synth.NUSC_VOXEL, synth.NUSC_RANGE, T, cap)
+    hbm, how = peaks()
+    byts = 4 * n * f + m * (4 * T * f + 16)
+    med, best = time_cuda(lambda: voxel.hard_voxelize_device(pts, voxels, coors, npv, synth.NUSC_VOXEL,
+                                                             synth.NUSC_RANGE, T, cap), args.iters)
+    print(json.dumps(dict(kernel="hard_voxelize (all launches)", points=n, voxels=m, ms_median=med, ms_best=best,
+                          alg_MB=byts / 1e6, GBs=byts / med / 1e6, frac=byts / med / 1e6 / hbm, peak=how)))
+
+
+STAGES = [  # (name, subm, ksize, stride, padding, cin, cout) along the TransFusion sparse encoder
+    ("subm1 16->16", True, [3] * 3, [1] * 3, [1] * 3, 16, 16),
+    ("down1 16->32", False, [3] * 3, [2] * 3, [1] * 3, 16, 32),
+    ("subm2 32->32", True, [3] * 3, [1] * 3, [1] * 3, 32, 32),
+    ("down2 32->64", False, [3] * 3, [2] * 3, [1] * 3, 32, 64),
+    ("subm3 64->64", True, [3] * 3, [1] * 3, [1] * 3, 64, 64),
+    ("down3 64->128", False, [3] * 3, [2] * 3, [0, 1, 1], 64, 128),
+    ("subm4 128->128", True, [3] * 3, [1] * 3, [1] * 3, 128, 128),
+]
+
+
+def bench_spconv(args):
+    """Rulebook build + conv fwd / dgrad / wgrad per stage of the encoder on the real active sets."""
+    from ddf_b200.ops.spconv import ops
+    idx, _ = _scene(args)
+    shape = [41, 1440, 1440]
+    hbm, how = peaks()
+    tfp, tfhow = _tf_peak()
+    for name, subm, ks, st, pad, cin, cout in STAGES:
+        n = idx.shape[0]
+        build = lambda: ops.build_rulebook(idx, args.batch, shape, ks, st, pad, 1, 0, subm, False)
+        rb = build()
+        n_out = rb.outids.shape[0]
+        pairs = int(rb.indice_pair_num.sum())
+        med, best = time_cuda(build, args.iters)
+        rb_bytes = 16 * n + 8 * pairs + 16 * n_out
+        print(json.dumps(dict(kernel="rulebook " + name, n_in=n, n_out=n_out, pairs=pairs, ms_median=med,
+                              alg_MB=rb_bytes / 1e6, GBs=rb_bytes / med / 1e6, frac=rb_bytes / med / 1e6 / hbm,
+                              peak=how)))
+        feat = ops.round_tf32(torch.randn(n, cin, device="cuda"))
+        w = torch.randn(*ks, cin, cout, device="cuda") / (cin * 27) ** 0.5
+        go = ops.round_tf32(torch.randn(n_out, cout, device="cuda"))
+        flops = 2.0 * pairs * cin * cout
+        byts = 4.0 * (n * cin + n_out * cout + 27 * cin * cout) + 8.0 * pairs
+        for kind, fn in (("fwd", lambda: ops.sparse_conv_forward(feat, w, rb.gather_table, None, n_out)),
+                         ("dgrad", lambda: ops.sparse_conv_dgrad(w, go, rb.scatter_table, n)),
+                         ("wgrad", lambda: ops.sparse_conv_wgrad(feat, w, go, rb.indice_pairs, rb.indice_pair_num))):
+            med, best = time_cuda(fn, args.iters)
+            print(json.dumps(dict(kernel="spconv %s %s" % (kind, name), ms_median=med, ms_best=best,
+                                  GFLOP=flops / 1e9, TFLOPs=flops / med / 1e9, tensor_frac_bf16=flops / med / 1e9 / tfp,
+                                  tensor_frac_tf32=flops / med / 1e9 / (tfp / 2), alg_MB=byts / 1e6,
+                                  GBs=byts / med / 1e6, hbm_frac=byts / med / 1e6 / hbm, peak="%s; %s" % (how, tfhow))))
+        if not subm:
+            idx = rb.outids
+            shape = rb.out_spatial_shape
+
+
+def bench_dense(args):
+    from ddf_b200.ops.spconv.structure import SparseConvTensor
+    n, C, B, D, H, W = 60000 * args.batch, 128, args.batch, 2, 180, 180
+    g = torch.Generator(device="cuda").manual_seed(0)
+    flat = torch.randperm(B * D * H * W, device="cuda", generator=g)[:n].sort().values
+    idx = torch.stack([flat // (D * H * W), flat // (H * W) % D, flat // W % H, flat % W], 1).int().contiguous()
+    feat = torch.randn(n, C, device="cuda")
+    t = SparseConvTensor(feat, idx, [D, H, W], B)
+    hbm, how = peaks()
+    byts = 4 * n * C + 16 * n + 4 * B * C * D * H * W
+    med, best = time_cuda(lambda: t.dense(), args.iters)
+    print(json.dumps(dict(kernel="sparse_to_dense (memset + scatter)", n=n, ms_median=med, ms_best=best,
+                          alg_MB=byts / 1e6, GBs=byts / med / 1e6, frac=byts / med / 1e6 / hbm, peak=how)))
+
+
+def bench_pointops(args):
+    from ddf_b200.ops import pointops
+    Bp, N, m, ns, C = 12, 8000, 2048, 32, 128
+    torch.manual_seed(0)
+    xyz = (torch.rand(Bp, N, 3, device="cuda") * torch.tensor([108.0, 108.0, 8.0], device="cuda")).contiguous()
+    feats = torch.randn(Bp, C, N, device="cuda")
+    hbm, how = peaks()
+    med, best = time_cuda(lambda: pointops.furthest_point_sample(xyz, m), args.iters)
+    idx = pointops.furthest_point_sample(xyz, m)
+    byts = 12 * Bp * N
+    print(json.dumps(dict(kernel="furthest_point_sample", rows=Bp, N=N, m=m, ms_median=med, us_per_row=med * 1e3 / Bp,
+                          alg_MB=byts / 1e6, GBs=byts / med / 1e6, frac=byts / med / 1e6 / hbm, note="latency-bound")))
+    centres = pointops.gather_points(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    med, best = time_cuda(lambda: pointops.ball_query(0.0, 2.0, ns, xyz, centres), args.iters)
+    bq = pointops.ball_query(0.0, 2.0, ns, xyz, centres)
+    byts = 12 * Bp * (N + m) + 4 * Bp * m * ns
+    print(json.dumps(dict(kernel="ball_query", ms_median=med, alg_MB=byts / 1e6, GBs=byts / med / 1e6,
+                          frac=byts / med / 1e6 / hbm, peak=how)))
+    med, best = time_cuda(lambda: pointops.grouping_operation(feats, bq), args.iters)
+    byts = 4 * Bp * C * m * ns * 2
+    print(json.dumps(dict(kernel="group_points", ms_median=med, alg_MB=byts / 1e6, GBs=byts / med / 1e6,
+                          frac=byts / med / 1e6 / hbm, peak=how)))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["msda"])
+    ap.add_argument("op", choices=["msda", "voxel", "spconv", "dense", "pointops", "all"])
     ap.add_argument("--shape", default="ctf")
     ap.add_argument("--loc", default="clustered", choices=["uniform", "clustered"])
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--points", type=int, default=260000)
+    ap.add_argument("--batch", type=int, default=2)
     a = ap.parse_args()
-    dict(msda=bench_msda)[a.op](a)
+    table = dict(msda=bench_msda, voxel=bench_voxel, spconv=bench_spconv, dense=bench_dense, pointops=bench_pointops)
+    for name in (table if a.op == "all" else [a.op]):
+        table[name](a)
