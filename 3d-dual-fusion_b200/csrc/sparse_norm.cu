@@ -1,0 +1,312 @@
+// BatchNorm1d over sparse-voxel features [N, C] fused with the residual add and ReLU that follow it
+// in every block of the sparse encoders, forward and backward, for sm_100a.
+//
+// Replaces, per conv layer of the reference (TransFusion/mmdet3d/ops/sparse_block.py:102-120, 153-185:
+// conv -> BN1d(eps 1e-3, momentum 0.01) -> [+ identity] -> ReLU), the chain of separate elementwise
+// kernels over (N, C): batch_norm statistics + transform, add, clamp in forward (4 launches) and
+// threshold_backward, batch_norm backward reduce + elemt, add in backward (4-5 launches) by
+//   forward : bn_stats_kernel (column sums; the last CTA to finish folds the partials, writes
+//             mean / invstd and updates the running statistics) + bn_apply_kernel
+//   backward: bn_bwd_reduce_kernel (ReLU mask applied on the fly; last CTA writes grad_weight /
+//             grad_bias and the two per-channel coefficients) + bn_bwd_apply_kernel
+// HBM-bound streaming kernels: rows are read as 16-byte vectors, a thread owns 4 channels of a row,
+// per-thread accumulation in fp64 (so E[x^2] - mean^2 is safe), deterministic (no float atomics:
+// fixed-order fold of per-CTA partials).
+// Algorithmic bytes: forward 4*N*C*(2 reads + [1 residual read] + 1 write); backward
+// 4*N*C*(3 reads + 3 reads + 1-2 writes).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxGrid = 2 * ddf::kNumSM;
+
+struct Acc8 {
+  double v[8];
+};
+
+// Block-level fold of the per-thread (sum[4], sq[4]) accumulators over the rows of the block, then
+// one partial per CTA: part[blockIdx.x][0..1][C].  Returns true in the last CTA to arrive.
+__device__ __forceinline__ bool fold_and_publish(Acc8& a, int tpr, int cg, int rl, int rpb, int C,
+                                                 double* __restrict__ part, unsigned* counter) {
+  __shared__ double sm[kThreads * 8];
+  __shared__ bool s_last;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[i * kThreads + threadIdx.x] = a.v[i];
+  __syncthreads();
+  for (int off = rpb >> 1; off > 0; off >>= 1) {
+    if (rl < off) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[i * kThreads + threadIdx.x] += sm[i * kThreads + threadIdx.x + off * tpr];
+    }
+    __syncthreads();
+  }
+  if (rl == 0) {
+    double* p = part + (long long)blockIdx.x * 2 * C + cg * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      p[i] = sm[i * kThreads + threadIdx.x];
+      p[C + i] = sm[(4 + i) * kThreads + threadIdx.x];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = ticket == gridDim.x - 1;
+    if (s_last) *counter = 0;  // ready for the next launch on this workspace
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+// Last CTA: totals of the 2*C columns over all CTAs' partials, in a fixed order -> tot[2*C] (shared).
+__device__ __forceinline__ void fold_partials(const double* __restrict__ part, int C, double* tot) {
+  __shared__ double sm[kThreads];
+  const int cols = 2 * C;
+  const int G = gridDim.x;
+  if (cols >= kThreads) {
+    for (int col = threadIdx.x; col < cols; col += kThreads) {
+      double s = 0.0;
+      for (int g = 0; g < G; ++g) s += __ldcg(part + (long long)g * cols + col);
+      tot[col] = s;
+    }
+  } else {
+    const int nsl = kThreads / cols;  // cols is a power of two >= 8
+    const int col = threadIdx.x % cols, sl = threadIdx.x / cols;
+    double s = 0.0;
+    for (int g = sl; g < G; g += nsl) s += __ldcg(part + (long long)g * cols + col);
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (sl == 0) {
+      for (int j = 1; j < nsl; ++j) s += sm[j * cols + col];
+      tot[col] = s;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ part,
+                unsigned* counter, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                float* running_mean, float* running_var, float momentum, float eps) {
+  extern __shared__ double tot[];  // [2*C]
+  const int tpr = C >> 2, rpb = kThreads / tpr;
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  Acc8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = 0.0;
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < n; r += (long long)gridDim.x * rpb) {
+    const float4 v = ldg4(x + r * C + cg * 4);
+    a.v[0] += v.x; a.v[1] += v.y; a.v[2] += v.z; a.v[3] += v.w;
+    a.v[4] += (double)v.x * v.x; a.v[5] += (double)v.y * v.y;
+    a.v[6] += (double)v.z * v.z; a.v[7] += (double)v.w * v.w;
+  }
+  if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
+  fold_partials(part, C, tot);
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    const double mean = tot[c] / n;
+    double var = tot[C + c] / n - mean * mean;  // biased, used for normalisation
+    if (var < 0.0) var = 0.0;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) {
+      const double unbiased = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+// y = relu?((x - mean) * invstd * w + b + res?).  stat_is_var: `invstd` holds a variance (eval mode).
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                const float* __restrict__ mean, const float* __restrict__ invstd,
+                const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y,
+                long long n4, int C, int relu, int stat_is_var, float eps) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % (C >> 2)) * 4;
+  const float4 v = ldg4(x + i * 4);
+  const float4 m = ldg4(mean + c);
+  float4 s = ldg4(invstd + c);
+  if (stat_is_var) {
+    s.x = 1.f / sqrtf(s.x + eps); s.y = 1.f / sqrtf(s.y + eps);
+    s.z = 1.f / sqrtf(s.z + eps); s.w = 1.f / sqrtf(s.w + eps);
+  }
+  if (w) {
+    const float4 g = ldg4(w + c);
+    s.x *= g.x; s.y *= g.y; s.z *= g.z; s.w *= g.w;
+  }
+  float4 o = b ? ldg4(b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  o.x = fmaf(v.x - m.x, s.x, o.x); o.y = fmaf(v.y - m.y, s.y, o.y);
+  o.z = fmaf(v.z - m.z, s.z, o.z); o.w = fmaf(v.w - m.w, s.w, o.w);
+  if (res) {
+    const float4 r = ldg4(res + i * 4);
+    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+  }
+  if (relu) {
+    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+  }
+  *reinterpret_cast<float4*>(y + i * 4) = o;
+}
+
+// sums over rows of g and g * xhat, g = gy masked by (y > 0) when relu.
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                     const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, int n, int C, int relu, int train,
+                     double* __restrict__ part, unsigned* counter, float* __restrict__ gweight,
+                     float* __restrict__ gbias, float* __restrict__ coef) {
+  extern __shared__ double tot[];
+  const int tpr = C >> 2, rpb = kThreads / tpr;
+  const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const float4 m = ldg4(mean + cg * 4), s = ldg4(invstd + cg * 4);
+  Acc8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = 0.0;
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < n; r += (long long)gridDim.x * rpb) {
+    const long long o = r * C + cg * 4;
+    float4 g = ldg4(gy + o);
+    if (relu) {
+      const float4 yy = ldg4(y + o);
+      g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
+      g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+    }
+    const float4 v = ldg4(x + o);
+    a.v[0] += g.x; a.v[1] += g.y; a.v[2] += g.z; a.v[3] += g.w;
+    a.v[4] += (double)g.x * ((v.x - m.x) * s.x); a.v[5] += (double)g.y * ((v.y - m.y) * s.y);
+    a.v[6] += (double)g.z * ((v.z - m.z) * s.z); a.v[7] += (double)g.w * ((v.w - m.w) * s.w);
+  }
+  if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
+  fold_partials(part, C, tot);
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    if (gbias) gbias[c] = (float)tot[c];
+    if (gweight) gweight[c] = (float)tot[C + c];
+    coef[c] = train ? (float)(tot[c] / n) : 0.f;
+    coef[C + c] = train ? (float)(tot[C + c] / n) : 0.f;
+  }
+}
+
+// gx = (g - c1 - xhat * c2) * invstd * w ; gres = g (the gradient of the residual branch).
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                    const float* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ w,
+                    const float* __restrict__ coef, float* __restrict__ gx,
+                    float* __restrict__ gres, long long n4, int C, int relu) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % (C >> 2)) * 4;
+  float4 g = ldg4(gy + i * 4);
+  if (relu) {
+    const float4 yy = ldg4(y + i * 4);
+    g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
+    g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+  }
+  if (gres) *reinterpret_cast<float4*>(gres + i * 4) = g;
+  if (!gx) return;
+  const float4 v = ldg4(x + i * 4);
+  const float4 m = ldg4(mean + c), s = ldg4(invstd + c);
+  const float4 c1 = ldg4(coef + c), c2 = ldg4(coef + C + c);
+  float4 sw = s;
+  if (w) {
+    const float4 ww = ldg4(w + c);
+    sw.x *= ww.x; sw.y *= ww.y; sw.z *= ww.z; sw.w *= ww.w;
+  }
+  float4 o;
+  o.x = (g.x - c1.x - (v.x - m.x) * s.x * c2.x) * sw.x;
+  o.y = (g.y - c1.y - (v.y - m.y) * s.y * c2.y) * sw.y;
+  o.z = (g.z - c1.z - (v.z - m.z) * s.z * c2.z) * sw.z;
+  o.w = (g.w - c1.w - (v.w - m.w) * s.w * c2.w) * sw.w;
+  *reinterpret_cast<float4*>(gx + i * 4) = o;
+}
+
+inline bool pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline unsigned stats_grid(int64_t n, int64_t C) {
+  const int rpb = kThreads / (int)(C >> 2);
+  long long g = ddf::cdiv(n, rpb);
+  if (g > kMaxGrid) g = kMaxGrid;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" int64_t ddf_sparse_bn_workspace_bytes(int64_t C) {
+  if (!pow2(C) || C < 4 || C > 1024) return -1;
+  // per-CTA partials [kMaxGrid][2][C] doubles + coefficient block [2][C] floats + arrival counter
+  return (int64_t)kMaxGrid * 2 * C * 8 + 2 * C * 4 + 256;
+}
+
+static inline float* ws_coef(void* ws, int64_t C) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (int64_t)kMaxGrid * 2 * C * 8);
+}
+static inline unsigned* ws_counter(void* ws, int64_t C) {
+  return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (int64_t)kMaxGrid * 2 * C * 8 + 2 * C * 4 + 128);
+}
+
+extern "C" int ddf_sparse_bn_forward(const float* x, const float* residual, const float* weight,
+                                     const float* bias, float* running_mean, float* running_var,
+                                     float* y, float* save_mean, float* save_invstd, int64_t n,
+                                     int64_t C, int training, float momentum, float eps, int relu,
+                                     void* workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n >= 0 && pow2(C) && C >= 4 && C <= 1024,
+                "sparse_bn_forward: C must be a power of two in [4, 1024], got n=%lld C=%lld",
+                (long long)n, (long long)C);
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(x && y, "sparse_bn_forward: null pointer");
+  DDF_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(residual) && aligned16(weight) && aligned16(bias),
+                "sparse_bn_forward: tensors must be 16-byte aligned");
+  const long long n4 = n * C / 4;
+  if (training) {
+    DDF_CHECK_ARG(workspace && save_mean && save_invstd, "sparse_bn_forward: training needs workspace and save buffers");
+    DDF_LAUNCH(bn_stats_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, x, (int)n,
+               (int)C, (double*)workspace, ws_counter(workspace, C), save_mean, save_invstd,
+               running_mean, running_var, momentum, eps);
+    DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
+               (const float*)save_mean, (const float*)save_invstd, weight, bias, y, n4, (int)C, relu, 0, eps);
+  } else {
+    DDF_CHECK_ARG(running_mean && running_var, "sparse_bn_forward: eval mode needs running statistics");
+    DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
+               (const float*)running_mean, (const float*)running_var, weight, bias, y, n4, (int)C, relu, 1, eps);
+  }
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// mean / invstd: the statistics forward normalised with (batch statistics in training; running mean
+// and 1/sqrt(running_var + eps) in eval).  grad_x and grad_residual may be NULL when not needed.
+extern "C" int ddf_sparse_bn_backward(const float* grad_y, const float* y, const float* x,
+                                      const float* weight, const float* mean, const float* invstd,
+                                      float* grad_x, float* grad_residual, float* grad_weight,
+                                      float* grad_bias, int64_t n, int64_t C, int training, int relu,
+                                      void* workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n >= 0 && pow2(C) && C >= 4 && C <= 1024,
+                "sparse_bn_backward: C must be a power of two in [4, 1024], got n=%lld C=%lld",
+                (long long)n, (long long)C);
+  if (n == 0) {
+    if (grad_weight) DDF_CUDA(cudaMemsetAsync(grad_weight, 0, sizeof(float) * C, stream));
+    if (grad_bias) DDF_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float) * C, stream));
+    return DDF_OK;
+  }
+  DDF_CHECK_ARG(grad_y && x && mean && invstd && workspace && (y || !relu), "sparse_bn_backward: null pointer");
+  DDF_CHECK_ARG(aligned16(grad_y) && aligned16(y) && aligned16(x) && aligned16(grad_x) && aligned16(grad_residual) &&
+                    aligned16(weight) && aligned16(mean) && aligned16(invstd),
+                "sparse_bn_backward: tensors must be 16-byte aligned");
+  float* coef = ws_coef(workspace, C);
+  DDF_LAUNCH(bn_bwd_reduce_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, grad_y, y, x,
+             mean, invstd, (int)n, (int)C, relu, training, (double*)workspace, ws_counter(workspace, C),
+             grad_weight, grad_bias, coef);
+  if (grad_x || grad_residual) {
+    const long long n4 = n * C / 4;
+    DDF_LAUNCH(bn_bwd_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, grad_y, y, x, mean,
+               invstd, weight, (const float*)coef, grad_x, grad_residual, n4, (int)C, relu);
+  }
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}

@@ -21,6 +21,7 @@ from ..ops import spconv
 from ..ops.spconv import SparseConv3d, SubMConv3d
 from ..registry import BACKBONES, FUSION
 from .actr import build as build_actr
+from ..ops import sparse_norm
 from .sparse_block import build_norm_layer
 
 
@@ -53,12 +54,11 @@ class SparseBasicBlock(spconv.SparseModule):
     def forward(self, x):
         identity = x
         out = self.conv1(x)
-        out = replace_feature(out, self.relu(self.bn1(out.features)))
+        out = replace_feature(out, sparse_norm.batch_norm_act(self.bn1, out.features, None, True))
         out = self.conv2(out)
-        out = replace_feature(out, self.bn2(out.features))
         if self.downsample is not None:
             identity = self.downsample(x)
-        return replace_feature(out, self.relu(out.features + identity.features))
+        return replace_feature(out, sparse_norm.batch_norm_act(self.bn2, out.features, identity.features, True))
 
 
 @BACKBONES.register_module

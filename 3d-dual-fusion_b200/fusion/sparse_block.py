@@ -2,7 +2,7 @@
 keeps mmdet BasicBlock's sub-module names (conv1 / bn1 / conv2 / bn2) so state dicts line up."""
 from torch import nn
 
-from ..ops import spconv
+from ..ops import sparse_norm, spconv
 from ..registry import CONV_LAYERS, NORM_LAYERS
 
 NORM_LAYERS.register_module("BN1d", module=nn.BatchNorm1d)
@@ -54,12 +54,12 @@ class SparseBasicBlock(spconv.SparseModule):
         identity = x.features
         assert x.features.dim() == 2, "x.features.dim()=%d" % x.features.dim()
         out = self.conv1(x)
-        out.features = self.relu(self.norm1(out.features))
+        # BN -> ReLU and BN -> + identity -> ReLU run as fused kernels on the same BatchNorm1d modules
+        out.features = sparse_norm.batch_norm_act(self.norm1, out.features, None, True)
         out = self.conv2(out)
-        out.features = self.norm2(out.features)
         if self.downsample is not None:
             identity = self.downsample(x)
-        out.features = self.relu(out.features + identity)
+        out.features = sparse_norm.batch_norm_act(self.norm2, out.features, identity, True)
         return out
 
 

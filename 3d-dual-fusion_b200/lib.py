@@ -44,10 +44,14 @@ _SIGNATURES = {
     "ddf_group_points_grad": [c_ptr] * 3 + [c_i64] * 5 + [c_ptr],
     "ddf_gather_points": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
     "ddf_gather_points_grad": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
+    "ddf_sparse_bn_workspace_bytes": [c_i64],
+    "ddf_sparse_bn_forward": [c_ptr] * 9 + [c_i64, c_i64, c_int, c_f32, c_f32, c_int, c_ptr, c_ptr],
+    "ddf_sparse_bn_backward": [c_ptr] * 10 + [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr],
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_dense_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
 }
-_RESTYPES = {"ddf_launch_count": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64}
+_RESTYPES = {"ddf_launch_count": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64,
+             "ddf_sparse_bn_workspace_bytes": c_i64}
 
 
 def exported_symbols():

@@ -59,7 +59,19 @@ class SparseSequential(SparseModule):
         self.add_module(name, module)
 
     def forward(self, input):
-        for k, module in self._modules.items():
+        from .. import sparse_norm
+        mods = list(self._modules.items())
+        skip = False
+        for i, (k, module) in enumerate(mods):
+            if skip:
+                skip = False
+                continue
+            if (isinstance(module, nn.BatchNorm1d) and isinstance(input, SparseConvTensor)
+                    and input.indices.shape[0] != 0):
+                # BatchNorm1d [-> ReLU] on sparse features: one fused op (same modules, same state dict)
+                skip = i + 1 < len(mods) and isinstance(mods[i + 1][1], nn.ReLU)
+                input.features = sparse_norm.batch_norm_act(module, input.features, None, skip)
+                continue
             if is_spconv_module(module):
                 assert isinstance(input, SparseConvTensor)
                 self._sparity_dict[k] = input.sparity

@@ -239,6 +239,27 @@ int ddf_gather_points(const float* points, const int* idx, float* out, int64_t B
 int ddf_gather_points_grad(const float* grad_out, const int* idx, float* grad_points, int64_t B,
                            int64_t C, int64_t N, int64_t npoints, void* stream);
 
+/* ---- BatchNorm1d over sparse-voxel features [N, C], fused with the residual add and ReLU -----------
+ * Replaces the elementwise chain conv -> BN1d -> [+ identity] -> ReLU of the reference's sparse
+ * blocks (TransFusion/mmdet3d/ops/sparse_block.py:102-120,153-185; torch.nn.BatchNorm1d semantics:
+ * batch statistics with biased variance in training, running statistics updated with the unbiased
+ * variance and `momentum`; running statistics in eval).  C: power of two in [4, 1024]; fp32; all
+ * pointers 16-byte aligned; residual / weight / bias / running_* may be NULL.
+ * workspace: ddf_sparse_bn_workspace_bytes(C) bytes, ZERO-INITIALISED ONCE by the caller and then
+ * reusable by successive calls on the same stream (the kernels leave it ready for the next call). */
+int64_t ddf_sparse_bn_workspace_bytes(int64_t C);
+int ddf_sparse_bn_forward(const float* x, const float* residual, const float* weight, const float* bias,
+                          float* running_mean, float* running_var, float* y, float* save_mean,
+                          float* save_invstd, int64_t n, int64_t C, int training, float momentum,
+                          float eps, int relu, void* workspace, void* stream);
+/* mean / invstd: what forward normalised with (saved batch statistics in training; running_mean and
+ * 1/sqrt(running_var + eps) in eval).  y is read only for the ReLU mask.  grad_x / grad_residual /
+ * grad_weight / grad_bias may be NULL. */
+int ddf_sparse_bn_backward(const float* grad_y, const float* y, const float* x, const float* weight,
+                           const float* mean, const float* invstd, float* grad_x, float* grad_residual,
+                           float* grad_weight, float* grad_bias, int64_t n, int64_t C, int training,
+                           int relu, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -186,6 +186,14 @@ def _cpu_ball_query(min_r, max_r, ns, xyz, center):
     return torch.from_numpy(opointops.ball_query(min_r, max_r, ns, xyz.detach().numpy(), center.detach().numpy()))
 
 
+def _cpu_batch_norm_act(bn, x, residual=None, relu=False):
+    """The reference's module chain: nn.BatchNorm1d -> (+ identity) -> ReLU (sparse_block.py:102-120)."""
+    y = bn(x)
+    if residual is not None:
+        y = y + residual
+    return torch.relu(y) if relu else y
+
+
 @contextlib.contextmanager
 def reference_cpu_ops():
     """Patch the product's op entry points with the reference CPU implementations (from outside)."""
@@ -196,6 +204,7 @@ def reference_cpu_ops():
     import ddf_b200.fusion.pointformer as m_pf
     import ddf_b200.ops.pointops as m_po
     import ddf_b200.ops.voxel as m_voxel
+    import ddf_b200.ops.sparse_norm as m_norm
 
     def build_rb(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, out_padding, subm, transposed):
         rb = cpu_build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, out_padding, subm)
@@ -207,6 +216,7 @@ def reference_cpu_ops():
              (m_conv.Fsp, "table_conv", m_conv.Fsp.table_conv),
              (m_struct.SparseConvTensor, "dense", m_struct.SparseConvTensor.dense),
              (m_voxel, "voxelization", m_voxel.voxelization),
+             (m_norm, "batch_norm_act", m_norm.batch_norm_act),
              (m_po, "furthest_point_sample", m_po.furthest_point_sample),
              (m_po, "ball_query", m_po.ball_query),
              (m_po, "grouping_operation", m_po.grouping_operation),
@@ -218,6 +228,7 @@ def reference_cpu_ops():
         m_conv.Fsp.table_conv = _cpu_table_conv
         m_struct.SparseConvTensor.dense = _cpu_dense
         m_voxel.voxelization = cpu_voxelization
+        m_norm.batch_norm_act = _cpu_batch_norm_act
         m_po.furthest_point_sample = _cpu_fps
         m_po.ball_query = _cpu_ball_query
         m_po.grouping_operation = _CpuGroup.apply

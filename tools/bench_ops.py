@@ -24,9 +24,12 @@ def peaks():
     return 6650.0, "fallback"
 
 
+WARM = 3
+
+
 def time_cuda(fn, iters, flush=True):
     fbuf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush else None
-    for _ in range(3):
+    for _ in range(WARM):
         fn()
     torch.cuda.synchronize()
     ts = []
@@ -142,6 +145,8 @@ def bench_spconv(args):
     hbm, how = peaks()
     tfp, tfhow = _tf_peak()
     for name, subm, ks, st, pad, cin, cout in STAGES:
+        if args.stages and subm and not any(t in name for t in args.stages.split(",")):
+            continue
         n = idx.shape[0]
         build = lambda: ops.build_rulebook(idx, args.batch, shape, ks, st, pad, 1, 0, subm, False)
         rb = build()
@@ -217,7 +222,10 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--points", type=int, default=260000)
     ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--stages", default="", help="spconv: comma list of SubM stage names to run (strided convs always run)")
+    ap.add_argument("--warm", type=int, default=3, help="untimed warm-up launches (0 for ncu captures)")
     a = ap.parse_args()
+    WARM = a.warm
     table = dict(msda=bench_msda, voxel=bench_voxel, spconv=bench_spconv, dense=bench_dense, pointops=bench_pointops)
     for name in (table if a.op == "all" else [a.op]):
         table[name](a)
