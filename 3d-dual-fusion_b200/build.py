@@ -39,7 +39,7 @@ def _compile(src, force):
     if (not force and os.path.exists(obj)
             and os.path.getmtime(obj) > max(os.path.getmtime(spath), _headers_mtime())):
         return obj, ""
-    cmd = [NVCC, *NVCC_FLAGS, "-c", spath, "-o", obj]
+    cmd = [NVCC, *NVCC_FLAGS, *os.environ.get("DDF_NVCC_EXTRA", "").split(), "-c", spath, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -22,7 +22,7 @@ void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); 
 
 extern "C" {
 const char* ddf_last_error(void) { return ddf::get_error(); }
-int ddf_abi_version(void) { return 2; }
+int ddf_abi_version(void) { return 3; }
 int ddf_compiled_arch(void) { return 100; }
 int64_t ddf_launch_count(int reset) {
   long long v = ddf::g_launches.load();

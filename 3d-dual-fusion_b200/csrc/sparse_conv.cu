@@ -22,6 +22,11 @@ namespace ddf {
 bool spconv_tc_supported(int kvol, int cin, int cout);
 int spconv_tc_launch(const float* feat, const float* wt, const int* table, const float* bias,
                      float* out, int64_t n_out, int kvol, int cin, int cout, cudaStream_t stream);
+// TMA-staged tcgen05 path (sparse_conv_tma.cu)
+bool spconv_tma_supported(int kvol, int cin, int cout);
+int spconv_tma_launch(const float* feat, const float* wt, const int* table, const float* bias, float* out,
+                      int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4,
+                      cudaStream_t stream);
 bool spconv_wgrad_tc_supported(int cin, int cout);
 int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pairs, const int* num,
                            int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
@@ -30,16 +35,22 @@ int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pair
 
 namespace {
 
-// DDF_DISABLE_TC=1 (or ddf_set_tensor_cores(0)) forces the fp32 SIMT kernels: full fp32 products,
-// used for A/B timing and for the strict 1e-3 whole-path parity test
+// Conv kernel selection. 0 (DDF_DISABLE_TC=1 or ddf_set_tensor_cores(0)): fp32 SIMT kernels, full
+// fp32 products - A/B timing and the strict 1e-3 whole-path parity test. 1 (default): tcgen05 tf32,
+// multi-tile kernel (filter slices by tiled TMA and shared by up to 4 row tiles, rows gathered by
+// cp.async from 16 warps) where the layer shape allows, else the single-tile cp.async kernel.
+// 2: tcgen05 tf32, single-tile cp.async kernel only. 3: as 1 with the rows gathered by TMA gather4.
 int g_tc_state = -1;  // -1: not read yet
-bool tc_enabled() {
+int tc_mode_state() {
   if (g_tc_state < 0) {
     const char* e = getenv("DDF_DISABLE_TC");
     g_tc_state = (e && e[0] == '1') ? 0 : 1;
   }
-  return g_tc_state != 0;
+  return g_tc_state;
 }
+bool tc_enabled() { return tc_mode_state() != 0; }
+bool tma_enabled() { return tc_mode_state() == 1 || tc_mode_state() == 3; }
+bool gather4_enabled() { return tc_mode_state() == 3; }
 
 
 constexpr int kThreads = 256;
@@ -287,10 +298,10 @@ int launch_gather_gemm(const float* feat, const float* filt, const int* table, c
 // [n_out, K]; bias optional ([cout] or NULL).  Fully overwrites out.
 extern "C" int ddf_sparse_conv_forward(const float* features, const float* filters,
                                        const int* gather_table, const float* bias, float* out,
-                                       float* filters_t_ws, int64_t n_out, int64_t kvol,
+                                       float* filters_t_ws, int64_t n_out, int64_t n_in, int64_t kvol,
                                        int64_t cin, int64_t cout, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DDF_CHECK_ARG(n_out >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_forward: bad sizes");
+  DDF_CHECK_ARG(n_out >= 0 && n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_forward: bad sizes");
   if (n_out == 0) return DDF_OK;
   DDF_CHECK_ARG(features && filters && gather_table && out, "sparse_conv_forward: null pointer");
   if (filters_t_ws && tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) {
@@ -298,6 +309,9 @@ extern "C" int ddf_sparse_conv_forward(const float* features, const float* filte
     const long long nw = kvol * cin * cout;
     DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
                filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, true);
+    if (tma_enabled() && ddf::spconv_tma_supported((int)kvol, (int)cin, (int)cout))
+      return ddf::spconv_tma_launch(features, filters_t_ws, gather_table, bias, out, n_out, n_in, (int)kvol,
+                                    (int)cin, (int)cout, gather4_enabled(), stream);
     return ddf::spconv_tc_launch(features, filters_t_ws, gather_table, bias, out, n_out, (int)kvol,
                                  (int)cin, (int)cout, stream);
   }
@@ -309,10 +323,10 @@ extern "C" int ddf_sparse_conv_forward(const float* features, const float* filte
 // of K*cin*cout floats (receives the transposed filters).
 extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters,
                                      const int* scatter_table, float* grad_in, float* filters_t_ws,
-                                     int64_t n_in, int64_t kvol, int64_t cin, int64_t cout,
+                                     int64_t n_in, int64_t n_out, int64_t kvol, int64_t cin, int64_t cout,
                                      void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DDF_CHECK_ARG(n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_dgrad: bad sizes");
+  DDF_CHECK_ARG(n_in >= 0 && n_out >= -1 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_dgrad: bad sizes");
   if (n_in == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_out && filters && scatter_table && grad_in && filters_t_ws,
                 "sparse_conv_dgrad: null pointer");
@@ -321,6 +335,9 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
   if (tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cout, (int)cin)) {
     DDF_LAUNCH(round_tf32_kernel, (unsigned)ddf::cdiv(nw / 4 + 1, kThreads), kThreads, 0, stream, filters,
                filters_t_ws, nw / 4, nw);
+    if (n_out >= 0 && tma_enabled() && ddf::spconv_tma_supported((int)kvol, (int)cout, (int)cin))
+      return ddf::spconv_tma_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, n_out,
+                                    (int)kvol, (int)cout, (int)cin, gather4_enabled(), stream);
     return ddf::spconv_tc_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, (int)kvol,
                                  (int)cout, (int)cin, stream);
   }
@@ -363,8 +380,8 @@ extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_ou
 
 // Runtime switch of the tensor-core conv kernels; returns the previous setting.
 extern "C" int ddf_set_tensor_cores(int on) {
-  const int prev = tc_enabled() ? 1 : 0;
-  g_tc_state = on ? 1 : 0;
+  const int prev = tc_mode_state();
+  g_tc_state = on < 0 ? 0 : (on > 3 ? 3 : on);
   return prev;
 }
 
@@ -432,7 +449,8 @@ extern "C" int ddf_indice_conv_backward(const float* features, const float* filt
   if (np > 0)
     DDF_LAUNCH(pairs_to_table_kernel, (unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream, 
         indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 1 : 0, table_ws);
-  return ddf_sparse_conv_dgrad(grad_out, filters, table_ws, grad_in, filters_t_ws, n_in, kvol, cin,
+  // this signature does not carry the row count of grad_out: n_out = -1 keeps dgrad off the TMA kernel
+  return ddf_sparse_conv_dgrad(grad_out, filters, table_ws, grad_in, filters_t_ws, n_in, -1, kvol, cin,
                                cout, stream_);
 }
 

@@ -1,0 +1,543 @@
+// Sparse 3-D convolution forward / dgrad as an implicit GEMM whose operands are staged by TMA:
+//   A (gathered feature rows)  : cp.async.bulk.tensor.2d ... tile::gather4  (UTMALDG.2D.GATHER4) —
+//                                one instruction fetches the 32-channel slice of FOUR rulebook rows
+//                                into four 128-byte rows of the SWIZZLE_128B operand tile; a missing
+//                                neighbour is an out-of-bounds row index, which TMA zero-fills
+//                                without touching memory
+//   B (filter slice Wt[k])     : one tiled TMA box [cout rows x 32 channels] per (offset, chunk)
+//   D                          : tcgen05.mma kind::tf32, fp32 accumulators in TMEM
+//
+// Why: the cp.async build (sparse_conv_tc.cu) issues 1024 16-byte LDGSTS per 16 KB stage from 128
+// producer threads; ncu shows it neither L2- nor tensor-bound but limited by that instruction stream
+// (profiles/r1_ncu_spconv_msda_cpasync.md).  Here a stage is 32 gather4 instructions from one warp.
+//
+// A CTA owns T (1..4) consecutive 128-row output tiles, one TMEM accumulator each, and walks
+// (kernel offset k, 32-channel chunk c) in the OUTER loop: the filter slice B(k, c) is fetched once
+// and reused by the T tiles, which divides the filter traffic (as large as the gather traffic for
+// 64/128-channel layers at 128 rows per CTA) by T.  Offsets no row of a tile uses are skipped.
+//
+// A-stage ring: the 8 slots are divided into one ring per tile (8 / T slots each).  The issuer of a
+// tile is the only consumer of its ring and walks it in order, so the usual "at most one phase
+// apart" parity argument holds per ring.  (One ring shared by all tiles does not work: an issuer
+// whose tile skips several offsets runs two ring phases ahead of the producers and a parity wait
+// cannot tell phase n from phase n + 2.)
+//
+// Warp roles (416 threads).  UTMALDG takes its operands from uniform registers, so per-lane gather4s
+// are serialised inside a warp (about 60 cycles each); the measured issue rate only reaches the L2
+// limit (about 14 cycles per 512-byte gather4 per SM, tools/probes/tma_gather4_bench.cu) with 16
+// warps issuing concurrently.  Hence:
+//   warps 0..7  : rulebook-table loader, then A producers (cp.async: 4 x 16 bytes per thread and
+//                 stage; gather4: 2 groups of 4 warps, 8 lanes x 1 gather4 per warp), then epilogue
+//                 (tcgen05.ld -> +bias -> global; TMEM lane quadrant = warp & 3, the (tile, 16-column)
+//                 items of a quadrant are split over its 2 warps)
+//   warps 8..11 : MMA issuers, one per tile of the CTA (own accumulator; one elected lane each).  A
+//                 single issuing thread needs about 1200 cycles per stage (tcgen05.mma operands go
+//                 through uniform registers: ELECT + R2UR per instruction), which capped the first
+//                 build; four issuers run in parallel.  Warp 8 also owns the TMEM allocation.
+//   warp 12     : B producer (one tiled TMA per filter slice)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+constexpr int TM = 128;            // rows per tile = UMMA M
+constexpr int KCH = 32;            // floats per K chunk (one 128-byte swizzle row)
+constexpr int kMaxT = 4;           // tiles per CTA
+constexpr int kMaxKvol = 27;
+constexpr int kProducerWarps = 8;
+constexpr int kGroups = 2;         // gather4 producer groups; group g fills A stages n with n % 2 == g
+constexpr int kThreads = (kProducerWarps + kMaxT + 1) * 32;   // + one MMA issuer warp per tile + B producer
+constexpr int kStagesA = 8;         // split into per-tile rings of 8 / T slots (see below)
+constexpr int kABytes = TM * KCH * 4;  // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// Bounded wait: a transaction that never completes (a broken tensor map, say) becomes a trap the
+// host sees as a launch error instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) {
+      printf("spconv mbarrier timeout: block %d thread %d smem 0x%x parity %u\n", blockIdx.x, threadIdx.x, addr, parity);
+      __trap();
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col,
+                                            int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col,
+                                            int row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(row)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-convergent variants: every lane executes the statement, one elected lane issues.  With
+// operands the compiler can prove warp-uniform they stay in uniform registers, which avoids the
+// ELECT / R2UR / branch sequence it otherwise wraps around every UTCHMMA / UTCBAR of a
+// single-thread issuer (about 25 SASS instructions per MMA).
+__device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+template <int CO>
+struct Cfg {
+  // deep enough that a filter slice is requested several TMA latencies (about 2.5 us) ahead of its use
+  static constexpr int kStagesB = CO >= 128 ? 2 : 4;
+  static constexpr int kBBytes = CO * KCH * 4;
+  static constexpr int kCols = CO < 32 ? 32 : CO;     // TMEM columns per tile
+  static constexpr int kIdxBytes = kMaxT * TM * kMaxKvol * 4;
+  static constexpr int kSmemBytes = kStagesA * kABytes + kStagesB * kBBytes + kIdxBytes + 512 + 1024;
+};
+
+// GATHER4 = false: the A tile is gathered by cp.async (LDGSTS, 16 bytes per thread, zero-fill for
+// missing neighbours) from all 16 producer warps; true: by TMA gather4 (kept selectable: measured
+// 1.7x slower than cp.async here because UTMALDG issue, not bandwidth, limits it).
+template <int CO, bool GATHER4>
+__global__ void __launch_bounds__(kThreads)
+spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_constant__ CUtensorMap map_w,
+                  const float* __restrict__ feat, const int* __restrict__ table, const float* __restrict__ bias, float* __restrict__ out,
+                  int n_out, int n_in, int kvol, int cin, int cout, int T) {
+  using C = Cfg<CO>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + kStagesA * kABytes;
+  int* s_idx = reinterpret_cast<int*>(b_base + C::kStagesB * C::kBBytes);   // [kvol][T*TM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_idx) + C::kIdxBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kStagesA;
+  uint64_t* b_full = a_empty + kStagesA;
+  uint64_t* b_empty = b_full + C::kStagesB;
+  uint64_t* accum_bar = b_empty + C::kStagesB;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint32_t* s_mask = s_tmem + 1;   // [kMaxT]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef DDF_TRACE
+  __shared__ long long s_tr[6][64];
+#define TR(ev, i) do { if (blockIdx.x == 3 && (i) < 64) s_tr[ev][i] = clock64(); } while (0)
+#else
+#define TR(ev, i) do {} while (0)
+#endif
+  const int tile0 = blockIdx.x * T;
+  const int rows = T * TM;         // rows of this CTA (padded)
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(T * C::kCols)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesA; ++s) {
+      // gather4: one arrive.expect_tx per warp of the owning group; cp.async: one arrival per thread
+      // of the owning 2-warp group
+      mbar_init(a_full + s, GATHER4 ? kProducerWarps / kGroups : 64);
+      mbar_init(a_empty + s, 1);
+    }
+    for (int s = 0; s < C::kStagesB; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, T);   // every issuer releases every filter slice
+    }
+    mbar_init(accum_bar, T);
+    for (int t = 0; t < kMaxT; ++t) s_mask[t] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp < kProducerWarps) {
+    // rulebook rows of the T tiles -> smem, transposed to [k][row]; per-tile mask of the offsets in use
+    for (int r = tid; r < rows; r += kProducerWarps * 32) {
+      const long long o = (long long)tile0 * TM + r;
+      uint32_t m = 0;
+      for (int k = 0; k < kvol; ++k) {
+        const int j = o < n_out ? __ldg(table + o * kvol + k) : -1;
+        s_idx[k * rows + r] = j >= 0 ? j : n_in;   // n_in = out of bounds = zero row
+        if (j >= 0) m |= 1u << k;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+      if (lane == 0 && m) atomicOr(s_mask + (r >> 7), m);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  uint32_t tmask[kMaxT];
+  uint32_t any = 0;
+#pragma unroll
+  for (int t = 0; t < kMaxT; ++t) {
+    tmask[t] = t < T ? s_mask[t] : 0u;
+    any |= tmask[t];
+  }
+  const int n_chunks = cin / KCH;
+  const int ring_shift = T == 1 ? 3 : T == 2 ? 2 : 1;   // A slots per tile ring: 8, 4, 2 (T = 3: 2)
+  const int ring = 1 << ring_shift;
+
+  if (warp < kProducerWarps) {
+    // ===================== A producers =====================
+    int n = 0;                                   // running A-stage number
+    int cnt[kMaxT] = {0, 0, 0, 0};               // stages issued so far per tile ring
+    if constexpr (GATHER4) {
+      const int grp = warp >> 2, wq = warp & 3;  // group, 32-row quarter of the tile
+      for (int k = 0; k < kvol; ++k) {
+        if (!((any >> k) & 1u)) continue;
+        for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+          for (int t = 0; t < kMaxT; ++t) {
+            if (!((tmask[t] >> k) & 1u)) continue;
+            const int slot = t * ring + (cnt[t] & (ring - 1));
+            const uint32_t par = (uint32_t)(cnt[t] >> ring_shift) & 1u;
+            ++cnt[t];
+            if ((n & (kGroups - 1)) == grp) {
+              int4 idx = make_int4(0, 0, 0, 0);
+              if (lane < 8) idx = *reinterpret_cast<const int4*>(s_idx + k * rows + t * TM + wq * 32 + lane * 4);
+              if (lane == 0) {
+                mbar_wait(a_empty + slot, par ^ 1u);
+                mbar_expect_tx(a_full + slot, kABytes / 4);
+              }
+              __syncwarp();
+              if (lane < 8)
+                tma_gather4(smem_u32(a_base + slot * kABytes) + (wq * 32 + lane * 4) * 128, &map_feat,
+                            a_full + slot, c * KCH, idx.x, idx.y, idx.z, idx.w);
+            }
+            ++n;
+          }
+        }
+      }
+    } else {
+      // Producer groups of 2 warps; group g owns the A slots s with s % 4 == g, so four stages are
+      // being issued at any time (a thread spends about 500 cycles per stage between the barrier
+      // poll and 16 dependent address computations; with every thread on every stage that latency
+      // was the stage period).  Thread -> 16-byte chunk ch of 16 consecutive rows.
+      constexpr int kCpGroups = kProducerWarps / 2;
+      const int grp = warp >> 1, gt = tid & 63;
+      const int rb = (gt >> 3) * 16, ch = gt & 7;      // first row, chunk
+      const uint32_t a0 = smem_u32(a_base) + (uint32_t)(rb * 128);
+      const float* col0 = feat + ch * 4;
+      for (int k = 0; k < kvol; ++k) {
+        if (!((any >> k) & 1u)) continue;
+        const int* ik = s_idx + k * rows + rb;
+        for (int c = 0; c < n_chunks; ++c) {
+          const float* col = col0 + c * KCH;
+#pragma unroll
+          for (int t = 0; t < kMaxT; ++t) {
+            if (!((tmask[t] >> k) & 1u)) continue;
+            const int slot = t * ring + (cnt[t] & (ring - 1));
+            const uint32_t par = (uint32_t)(cnt[t] >> ring_shift) & 1u;
+            ++cnt[t];
+            // a slot always belongs to the same group: one producer and one consumer per slot, both
+            // in order, so a parity wait can never be two phases off
+            if ((slot & (kCpGroups - 1)) != grp) continue;
+            int4 j4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) j4[i] = *reinterpret_cast<const int4*>(ik + t * TM + 4 * i);
+            const int* j = reinterpret_cast<const int*>(j4);
+            const uint32_t dst = a0 + (uint32_t)(slot * kABytes);
+            mbar_wait(a_empty + slot, par ^ 1u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool v = (unsigned)j[i] < (unsigned)n_in;
+              // rows rb + i: rb is a multiple of 16, so (row & 7) == (i & 7)
+              cp_async16(dst + (uint32_t)(i * 128 + ((ch ^ (i & 7)) << 4)),
+                         col + (v ? (size_t)(unsigned)j[i] * (unsigned)cin : 0), v ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(a_full + slot);
+          }
+        }
+      }
+    }
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;     // TMEM lane quadrant this warp may read
+    const int part = warp >> 2; // the quadrant's (tile, 16-column) items are split over its 2 warps
+    if (any) {
+      mbar_wait(accum_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    constexpr int kBlocks = CO / 16;
+    for (int item = part; item < T * kBlocks; item += kProducerWarps / 4) {
+      const int t = item / kBlocks, cb = (item % kBlocks) * 16;
+      const long long o = (long long)(tile0 + t) * TM + q * 32 + lane;
+      const bool live = ((t == 0 ? tmask[0] : t == 1 ? tmask[1] : t == 2 ? tmask[2] : tmask[3])) != 0;
+      uint32_t v[16];
+      if (live) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * C::kCols + cb);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+              "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+              "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+      if (o < n_out && cb < cout) {
+        float* dst = out + o * cout + cb;
+        if (cb + 16 <= cout) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float4 r4 = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                    __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            if (bias) {
+              const float4 b4 = ldg4(bias + cb + 4 * g);
+              r4.x += b4.x; r4.y += b4.y; r4.z += b4.z; r4.w += b4.w;
+            }
+            *reinterpret_cast<float4*>(dst + 4 * g) = r4;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (cb + i < cout) dst[i] = __uint_as_float(v[i]) + (bias ? __ldg(bias + cb + i) : 0.f);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp < kProducerWarps + kMaxT) {
+    // ===================== MMA issuers: warp 8 + t drives tile t =====================
+    const int t = warp - kProducerWarps;
+    if (t < T) {
+      // all 32 lanes walk the loop; values that come from shared memory are passed through a warp
+      // reduction, whose result the compiler knows to be uniform
+      constexpr uint32_t idesc = make_idesc_tf32(CO);
+      const uint32_t mt = __reduce_or_sync(0xffffffffu, t == 0 ? tmask[0] : t == 1 ? tmask[1] : t == 2 ? tmask[2] : tmask[3]);
+      const uint32_t any_u = __reduce_or_sync(0xffffffffu, any);
+      const uint32_t d_tmem = __reduce_or_sync(0xffffffffu, tmem_base) + (uint32_t)(t * C::kCols);
+      const uint32_t a_ring = smem_u32(a_base) + (uint32_t)(t * ring * kABytes);
+      int cnt = 0, sb = 0;    // stages of this tile consumed so far; filter-slice ring position
+      uint32_t pb = 0, accumulate = 0;
+      for (int k = 0; k < kvol; ++k) {
+        if (!((any_u >> k) & 1u)) continue;
+        const bool mine = (mt >> k) & 1u;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(b_full + sb, pb);
+          if (mine) {
+            const int slot = cnt & (ring - 1);
+            if (t == 0 && lane == 0) TR(3, cnt);
+            mbar_wait(a_full + t * ring + slot, (uint32_t)(cnt >> ring_shift) & 1u);
+            if (t == 0 && lane == 0) TR(4, cnt);
+            ++cnt;
+            if constexpr (!GATHER4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t a_desc = make_desc_sw128(a_ring + (uint32_t)(slot * kABytes));
+            const uint64_t b_desc = make_desc_sw128(smem_u32(b_base) + (uint32_t)(sb * C::kBBytes));
+#pragma unroll
+            for (int ks = 0; ks < KCH / 8; ++ks) {
+              // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+              umma_tf32_elect(d_tmem, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit_elect(a_empty + t * ring + slot);
+            umma_commit_elect(b_empty + sb);
+            if (t == 0 && lane == 0) TR(5, cnt - 1);
+          } else {
+            // tile without this offset: release the filter slice (after it landed, so the arrival
+            // is counted in the right phase)
+            mbar_arrive_elect(b_empty + sb);
+          }
+          if (++sb == C::kStagesB) { sb = 0; pb ^= 1u; }
+        }
+      }
+      umma_commit_elect(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===================== B producer (tiled TMA) =====================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int k = 0; k < kvol; ++k) {
+        if (!((any >> k) & 1u)) continue;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(b_empty + sb, pb ^ 1u);
+          mbar_expect_tx(b_full + sb, (uint32_t)(cout * KCH * 4));
+          tma_tile_2d(smem_u32(b_base + sb * C::kBBytes), &map_w, b_full + sb, c * KCH, k * cout);
+          if (++sb == C::kStagesB) { sb = 0; pb ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+#ifdef DDF_TRACE
+  if (blockIdx.x == 3 && tid == 0) {
+    const long long t0 = s_tr[0][0];
+    for (int i = 0; i < 40; ++i)
+      printf("stage %2d: prod wait_start %6lld got_slot %6lld issued %6lld | issuer wait_start %6lld full %6lld committed %6lld\n", i,
+             s_tr[0][i] - t0, s_tr[1][i] - t0, s_tr[2][i] - t0, s_tr[3][i] - t0, s_tr[4][i] - t0, s_tr[5][i] - t0);
+  }
+#endif
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box [box_rows x 32 floats], 128-byte swizzle, zero OOB fill
+bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KCH, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CO, bool GATHER4>
+int launch_tma(const float* feat, const float* wt, const int* table, const float* bias, float* out,
+               int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
+  using C = Cfg<CO>;
+  static bool configured = false;
+  if (!configured) {
+    DDF_CUDA(cudaFuncSetAttribute(spconv_tma_kernel<CO, GATHER4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kSmemBytes));
+    configured = true;
+  }
+  CUtensorMap map_feat, map_w;
+  if (!make_map(&map_feat, feat, n_in, cin, 1) || !make_map(&map_w, wt, (int64_t)kvol * cout, cin, cout)) {
+    ddf::set_error("sparse conv: cuTensorMapEncodeTiled failed (n_in=%lld cin=%d cout=%d)", (long long)n_in, cin, cout);
+    return DDF_ERR_CUDA;
+  }
+  const long long ntiles = ddf::cdiv(n_out, TM);
+  // tiles per CTA: enough CTAs to fill the SMs first, then share filter slices between tiles
+  int T = (int)ddf::cdiv(ntiles, ddf::kNumSM);
+  const int tmax = 512 / C::kCols < kMaxT ? 512 / C::kCols : kMaxT;
+  if (T > tmax) T = tmax;
+  if (T < 1) T = 1;
+  const unsigned grid = (unsigned)ddf::cdiv(ntiles, T);
+  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4>), grid, kThreads, C::kSmemBytes, stream, map_feat, map_w, feat, table,
+             bias, out, (int)n_out, (int)n_in, kvol, cin, cout, T);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+}  // namespace
+
+namespace ddf {
+
+// the TMA kernel takes full 32-channel chunks (narrower layers stay on the cp.async kernel) and
+// output widths that are a multiple of 16
+bool spconv_tma_supported(int kvol, int cin, int cout) {
+  return encode_fn() != nullptr && kvol <= kMaxKvol && cin % KCH == 0 && cout % 16 == 0 && cout >= 16 && cout <= 128;
+}
+
+// feat [n_in, cin]; wt [K, cout, cin] (K-major B operand); table [n_out, K]
+int spconv_tma_launch(const float* feat, const float* wt, const int* table, const float* bias, float* out,
+                      int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4,
+                      cudaStream_t stream) {
+#define DDF_TMA_CASE(CO)                                                                                   \
+  return gather4 ? launch_tma<CO, true>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream) \
+                 : launch_tma<CO, false>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream)
+  if (cout <= 16) { DDF_TMA_CASE(16); }
+  if (cout <= 32) { DDF_TMA_CASE(32); }
+  if (cout <= 64) { DDF_TMA_CASE(64); }
+  DDF_TMA_CASE(128);
+#undef DDF_TMA_CASE
+}
+
+}  // namespace ddf

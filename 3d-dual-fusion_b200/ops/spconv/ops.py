@@ -193,7 +193,7 @@ def sparse_conv_forward(features, filters, gather_table, bias, n_out):
     with torch.cuda.device(features.device):
         rc = _lib.get_lib().ddf_sparse_conv_forward(
             _lib.ptr(features), _lib.ptr(filters), _lib.ptr(gather_table), _lib.ptr(bias), _lib.ptr(out),
-            _lib.ptr(wt_ws), n_out, kvol, cin, cout, _lib.current_stream())
+            _lib.ptr(wt_ws), n_out, features.shape[0], kvol, cin, cout, _lib.current_stream())
     _lib.check(rc, "sparse_conv_forward")
     return out
 
@@ -206,7 +206,8 @@ def sparse_conv_dgrad(filters, grad_out, scatter_table, n_in):
     with torch.cuda.device(grad_out.device):
         rc = _lib.get_lib().ddf_sparse_conv_dgrad(_lib.ptr(grad_out), _lib.ptr(filters),
                                                   _lib.ptr(scatter_table), _lib.ptr(gin), _lib.ptr(wt_ws),
-                                                  n_in, kvol, cin, cout, _lib.current_stream())
+                                                  n_in, grad_out.shape[0], kvol, cin, cout,
+                                                  _lib.current_stream())
     _lib.check(rc, "sparse_conv_dgrad")
     return gin
 

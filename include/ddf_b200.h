@@ -175,7 +175,7 @@ int ddf_indice_conv_backward(const float* features, const float* filters, const 
  * K <= 27) the tcgen05 tf32 implicit-GEMM kernel runs, otherwise the fp32 SIMT kernel. */
 int ddf_sparse_conv_forward(const float* features, const float* filters, const int* gather_table,
                             const float* bias, float* out, float* filters_t_ws, int64_t n_out,
-                            int64_t kvol, int64_t cin, int64_t cout, void* stream);
+                            int64_t n_in, int64_t kvol, int64_t cin, int64_t cout, void* stream);
 
 /* Tensor-core bookkeeping: ddf_sparse_conv_tc_mode returns a bit mask of the kernels of a layer
  * that run as tcgen05 tf32 implicit GEMMs (1 forward, 2 dgrad, 4 wgrad; 0 with DDF_DISABLE_TC=1).
@@ -183,13 +183,18 @@ int ddf_sparse_conv_forward(const float* features, const float* filters, const i
  * tensor to the nearest tf32 first (dst may alias src) so the error is unbiased. Filters are
  * rounded inside the conv calls. */
 int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout);
-/* Switch the tcgen05 conv kernels on (1, default) or off (0 = fp32 SIMT kernels, full fp32 products);
- * returns the previous setting. Not thread-safe against concurrent conv calls. */
+/* Conv kernel selection: 1 (default) tcgen05 tf32, multi-tile kernel (filter slices by tiled TMA,
+ * shared by up to 4 row tiles; rows gathered by cp.async) where the layer shape allows, else the
+ * single-tile cp.async kernel; 2 single-tile cp.async kernel only; 3 as 1 with rows gathered by TMA
+ * gather4; 0 fp32 SIMT kernels (full fp32 products). Returns the previous setting. Not thread-safe
+ * against concurrent conv calls. */
 int ddf_set_tensor_cores(int on);
 int ddf_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 
+/* n_out = rows of grad_out (-1 when unknown: the TMA-staged kernel, whose tensor map needs the
+ * height of the gathered tensor, is then not used). */
 int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters, const int* scatter_table,
-                          float* grad_in, float* filters_t_ws, int64_t n_in, int64_t kvol,
+                          float* grad_in, float* filters_t_ws, int64_t n_in, int64_t n_out, int64_t kvol,
                           int64_t cin, int64_t cout, void* stream);
 
 int ddf_sparse_conv_wgrad(const float* features, const float* grad_out, const int* indice_pairs,

@@ -224,8 +224,11 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--stages", default="", help="spconv: comma list of SubM stage names to run (strided convs always run)")
     ap.add_argument("--warm", type=int, default=3, help="untimed warm-up launches (0 for ncu captures)")
+    ap.add_argument("--tc-mode", type=int, default=1, help="conv kernels: 1 TMA+tcgen05 (default), 2 cp.async+tcgen05, 0 fp32 SIMT")
     a = ap.parse_args()
     WARM = a.warm
+    from ddf_b200 import lib as _l
+    _l.get_lib().ddf_set_tensor_cores(a.tc_mode)
     table = dict(msda=bench_msda, voxel=bench_voxel, spconv=bench_spconv, dense=bench_dense, pointops=bench_pointops)
     for name in (table if a.op == "all" else [a.op]):
         table[name](a)
