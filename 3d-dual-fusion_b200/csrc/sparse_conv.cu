@@ -27,6 +27,9 @@ bool spconv_tma_supported(int kvol, int cin, int cout);
 int spconv_tma_launch(const float* feat, const float* wt, const int* table, const float* bias, float* out,
                       int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4,
                       cudaStream_t stream);
+bool spconv_wgrad_table_supported(int kvol, int cin, int cout);
+int spconv_wgrad_table_launch(const float* feat, const float* gout, const int* table, float* gw,
+                              int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream);
 bool spconv_wgrad_tc_supported(int cin, int cout);
 int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pairs, const int* num,
                            int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
@@ -385,6 +388,26 @@ extern "C" int ddf_set_tensor_cores(int on) {
   return prev;
 }
 
+// grad_filters [K, cin, cout] (zeroed inside) through the gather table [n_out, K] of the forward conv:
+// the output rows are walked once, gout rows are read densely, only feature rows are gathered.
+// Returns DDF_ERR_ARG when the layer shape is not supported (callers fall back to the pair lists).
+extern "C" int ddf_sparse_conv_wgrad_table(const float* features, const float* grad_out,
+                                           const int* gather_table, float* grad_filters, int64_t n_out,
+                                           int64_t n_in, int64_t kvol, int64_t cin, int64_t cout,
+                                           void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n_out >= 0 && n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_wgrad_table: bad sizes");
+  DDF_CHECK_ARG(grad_filters != nullptr, "sparse_conv_wgrad_table: null grad_filters");
+  DDF_CHECK_ARG(tc_enabled() && ddf::spconv_wgrad_table_supported((int)kvol, (int)cin, (int)cout),
+                "sparse_conv_wgrad_table: unsupported layer shape K=%lld Cin=%lld Cout=%lld", (long long)kvol,
+                (long long)cin, (long long)cout);
+  DDF_CUDA(cudaMemsetAsync(grad_filters, 0, sizeof(float) * (size_t)(kvol * cin * cout), stream));
+  if (n_out == 0) return DDF_OK;
+  DDF_CHECK_ARG(features && grad_out && gather_table, "sparse_conv_wgrad_table: null pointer");
+  return ddf::spconv_wgrad_table_launch(features, grad_out, gather_table, grad_filters, n_out, n_in, (int)kvol,
+                                        (int)cin, (int)cout, stream);
+}
+
 // Which of the three conv kernels of a (kvol, cin, cout) layer run on the tensor cores:
 // bit 0 forward, bit 1 dgrad, bit 2 wgrad.  Callers use it to decide which operands to pre-round.
 extern "C" int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout) {
@@ -393,6 +416,7 @@ extern "C" int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout) 
   if (ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) m |= 1;
   if (ddf::spconv_tc_supported((int)kvol, (int)cout, (int)cin)) m |= 2;
   if (ddf::spconv_wgrad_tc_supported((int)cin, (int)cout)) m |= 4;
+  if (tc_mode_state() != 2 && ddf::spconv_wgrad_table_supported((int)kvol, (int)cin, (int)cout)) m |= 8;
   return m;
 }
 

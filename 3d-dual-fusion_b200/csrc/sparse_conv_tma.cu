@@ -317,7 +317,9 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
             for (int i = 0; i < 4; ++i) j4[i] = *reinterpret_cast<const int4*>(ik + t * TM + 4 * i);
             const int* j = reinterpret_cast<const int*>(j4);
             const uint32_t dst = a0 + (uint32_t)(slot * kABytes);
+            if (t == 0 && tid == 0) TR(0, cnt[0] - 1);
             mbar_wait(a_empty + slot, par ^ 1u);
+            if (t == 0 && tid == 0) TR(1, cnt[0] - 1);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const bool v = (unsigned)j[i] < (unsigned)n_in;
@@ -326,6 +328,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
                          col + (v ? (size_t)(unsigned)j[i] * (unsigned)cin : 0), v ? 16u : 0u);
             }
             cp_async_arrive_noinc(a_full + slot);
+            if (t == 0 && tid == 0) TR(2, cnt[0] - 1);
           }
         }
       }
@@ -459,6 +462,261 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad, table driven:   gW[k] (Cin x Cout) = sum over output rows o of  feat[G[o, k], :]^T . gout[o, :]
+//
+// The pair-list kernel (sparse_conv_tc.cu) gathers BOTH operands and walks one offset at a time, i.e.
+// 27 streaming passes over feat and gout (2.3 GB of DRAM reads for the 64-channel stage of the bench
+// workload, ncu).  Here the output rows are walked ONCE: a CTA owns a group of KG = 512 / Cout kernel
+// offsets (one TMEM accumulator each) and a range of 32-row sub-tiles; per sub-tile the gout rows
+// (dense, contiguous) and the 32 x K slice of the gather table are staged once and reused by the KG
+// offsets, only the feat rows are gathered (neighbours of consecutive output rows: L2 hits).
+// GEMM per stage: M = Cin (128 TMEM lanes, lanes >= Cin unused), N = Cout, K = 32 rows; both
+// operands are MN-major, SWIZZLE_128B_BASE32B: atoms of 4 rows x 32 channels (512 bytes), the
+// 32-byte chunk index XORed with (row & 3).
+// Warp roles as in the forward kernel: warps 0..7 gather A in 4 groups (group = slot & 3) and drain
+// the accumulators at the end (red.global.add.v4), warps 8..11 issue the MMAs of the offsets
+// kk = j (mod 4), warp 12 stages gout + table.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgSlotsA = 8;        // 2 per issuer
+constexpr int kWgSlotsB = 3;
+// rows per sub-tile (= K extent of a stage) are chosen so that a stage is 16 KB: 4096 / Cin; the
+// per-stage fixed costs (barrier polls, address set-up, MMA issue) are the same for any stage size
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(512 >> 4) << 16;           // LBO: next 32-channel block
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;     // SBO: next 4-row group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
+  return d;
+}
+// byte offset of 16-byte chunk `ch` (0..7) of row `p` in channel block `mb` (nblk blocks per 4-row group)
+__device__ __forceinline__ uint32_t mn_chunk_offset(int p, int mb, int ch, int nblk) {
+  const int r = p & 3;
+  return (uint32_t)((((p >> 2) * nblk + mb) << 9) + (r << 7) + ((((ch >> 1) ^ r)) << 5) + ((ch & 1) << 4));
+}
+
+template <int CO, int SR>
+__global__ void __launch_bounds__(kThreads)
+spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
+                          const int* __restrict__ table, float* __restrict__ gw, int n_out, int n_in,
+                          int kvol, int cin, int cout, int KG, int G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
+  const int a_nb = cin >> 5, b_nb = CO >> 5;           // 32-channel blocks per row
+  const int a_bytes = SR * cin * 4, b_bytes = SR * CO * 4;
+  uint8_t* a_base = smem;
+  uint8_t* b_base = a_base + kWgSlotsA * a_bytes;
+  uint8_t* t_base = b_base + kWgSlotsB * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(t_base + kWgSlotsB * kTblBytes + 2048);  // + over-read slack
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kWgSlotsA;
+  uint64_t* b_full = a_empty + kWgSlotsA;
+  uint64_t* b_empty = b_full + kWgSlotsB;
+  uint64_t* accum_bar = b_empty + kWgSlotsB;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.x % G, split = blockIdx.x / G, S = gridDim.x / G;
+  const int k0 = g * KG;
+  const int nk = min(KG, kvol - k0);
+  const int NS = (n_out + SR - 1) / SR;
+  const int st_begin = (int)((long long)NS * split / S), st_end = (int)((long long)NS * (split + 1) / S);
+  constexpr uint32_t kCols = CO;     // CO >= 32 here
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)nk * kCols) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWgSlotsA; ++s) {
+      mbar_init(a_full + s, 64);
+      mbar_init(a_empty + s, 1);
+    }
+    for (int s = 0; s < kWgSlotsB; ++s) {
+      mbar_init(b_full + s, 32);
+      mbar_init(b_empty + s, kMaxT);
+    }
+    mbar_init(accum_bar, kMaxT);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const bool work = st_begin < st_end;
+
+  if (warp < kProducerWarps) {
+    // ===================== A producers =====================
+    if (work) {
+      const int grp = warp >> 1, gt = tid & 63;
+      const int a_chunks = cin >> 2;                 // 16-byte chunks per row (8, 16 or 32)
+      const int a_shift = 31 - __clz(a_chunks);
+      const int iters = (SR * a_chunks) >> 6;        // chunks per thread and stage
+      int cnt[kMaxT] = {0, 0, 0, 0};
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        bool have_tbl = false;
+        const int* tbl = reinterpret_cast<const int*>(t_base + sb * kTblBytes);
+#pragma unroll 1
+        for (int kk = 0; kk < nk; ++kk) {
+          const int j = kk & (kMaxT - 1);
+          int c;
+          if (j == 0) c = cnt[0]++; else if (j == 1) c = cnt[1]++; else if (j == 2) c = cnt[2]++; else c = cnt[3]++;
+          const int sl = j * 2 + (c & 1);
+          if ((sl & 3) != grp) continue;
+          if (!have_tbl) {
+            mbar_wait(b_full + sb, pb);     // table slice (and gout rows) of this sub-tile landed
+            have_tbl = true;
+          }
+          mbar_wait(a_empty + sl, (uint32_t)((c >> 1) & 1) ^ 1u);
+          const uint32_t dst = smem_u32(a_base + sl * a_bytes);
+          const int k = k0 + kk;
+          for (int i = 0; i < iters; ++i) {
+            const int e = gt + (i << 6);
+            const int p = e >> a_shift, cc = e & (a_chunks - 1);
+            const int row = tbl[p * kvol + k];
+            const bool v = row >= 0 && st * SR + p < n_out;
+            cp_async16(dst + mn_chunk_offset(p, cc >> 3, cc & 7, a_nb),
+                       feat + (v ? (size_t)(unsigned)row * (unsigned)cin + cc * 4 : 0), v ? 16u : 0u);
+          }
+          cp_async_arrive_noinc(a_full + sl);
+        }
+        if (++sb == kWgSlotsB) { sb = 0; pb ^= 1u; }
+      }
+    }
+    // ===================== epilogue: accumulators -> gW (red.global.add) =====================
+    if (work) {
+      mbar_wait(accum_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3, half = warp >> 2;
+      const int ci = q * 32 + lane;
+      for (int kk = half; kk < nk; kk += kProducerWarps / 4) {
+        for (int cb = 0; cb < cout; cb += 16) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kk * kCols + cb);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ci < cin) {
+            float* dst = gw + ((long long)(k0 + kk) * cin + ci) * cout + cb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              red_add_v4(dst + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  } else if (warp < kProducerWarps + kMaxT) {
+    // ===================== MMA issuers: offsets kk = j (mod 4) =====================
+    const int j = warp - kProducerWarps;
+    if (work) {
+      constexpr uint32_t idesc = make_idesc_tf32(CO) | (1u << 15) | (1u << 16);   // A, B MN-major
+      const uint32_t tm = __reduce_or_sync(0xffffffffu, tmem_base);
+      const uint32_t a_ring = smem_u32(a_base) + (uint32_t)(j * 2 * a_bytes);
+      int cnt = 0, sb = 0;
+      uint32_t pb = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        mbar_wait(b_full + sb, pb);
+        const uint32_t b_smem = smem_u32(b_base) + (uint32_t)(sb * b_bytes);
+        bool issued = false;
+        for (int kk = j; kk < nk; kk += kMaxT) {
+          const int sl = cnt & 1;
+          mbar_wait(a_full + j * 2 + sl, (uint32_t)(cnt >> 1) & 1u);
+          ++cnt;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_smem = a_ring + (uint32_t)(sl * a_bytes);
+#pragma unroll
+          for (int ks = 0; ks < SR / 8; ++ks) {
+            // one MMA (K = 8 rows) spans two 4-row groups
+            const uint64_t a_desc = make_desc_mn_sw128(a_smem + ks * 2 * a_nb * 512, a_nb * 512);
+            const uint64_t b_desc = make_desc_mn_sw128(b_smem + ks * 2 * b_nb * 512, b_nb * 512);
+            umma_tf32_elect(tm + (uint32_t)kk * kCols, a_desc, b_desc, idesc, (st != st_begin || ks != 0) ? 1u : 0u);
+          }
+          umma_commit_elect(a_empty + j * 2 + sl);
+          issued = true;
+        }
+        if (issued) umma_commit_elect(b_empty + sb); else mbar_arrive_elect(b_empty + sb);
+        if (++sb == kWgSlotsB) { sb = 0; pb ^= 1u; }
+      }
+      umma_commit_elect(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===================== gout rows + table slice of each sub-tile (cp.async, 32 threads) =====================
+    if (work) {
+      const int b_chunks = cout >> 2;
+      const int b_shift = 31 - __clz(b_chunks);
+      int sb = 0;
+      uint32_t pb = 0;
+      const long long tbl_bytes_total = (long long)n_out * kvol * 4;
+      for (int st = st_begin; st < st_end; ++st) {
+        mbar_wait(b_empty + sb, pb ^ 1u);
+        const uint32_t tdst = smem_u32(t_base + sb * kTblBytes);
+        const long long tsrc = (long long)st * SR * kvol * 4;
+        for (int e = lane; e < (SR * kvol * 4 + 15) / 16; e += 32) {
+          const long long off = tsrc + e * 16;
+          const long long left = tbl_bytes_total - off;
+          const uint32_t nb = left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u);
+          cp_async16(tdst + e * 16, reinterpret_cast<const uint8_t*>(table) + (nb ? off : 0), nb);
+        }
+        const uint32_t bdst = smem_u32(b_base + sb * b_bytes);
+        for (int e = lane; e < SR * b_chunks; e += 32) {
+          const int p = e >> b_shift, cc = e & (b_chunks - 1);
+          const long long row = (long long)st * SR + p;
+          const bool v = row < n_out;
+          cp_async16(bdst + mn_chunk_offset(p, cc >> 3, cc & 7, b_nb), gout + (v ? row * cout + cc * 4 : 0), v ? 16u : 0u);
+        }
+        cp_async_arrive_noinc(b_full + sb);
+        if (++sb == kWgSlotsB) { sb = 0; pb ^= 1u; }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+template <int CO>
+int launch_wgrad_table(const float* feat, const float* gout, const int* table, float* gw, int64_t n_out,
+                       int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
+  constexpr int SR = 4096 / CO;   // cin == cout == CO
+  constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
+  const int smem = kWgSlotsA * SR * cin * 4 + kWgSlotsB * SR * CO * 4 + kWgSlotsB * kTblBytes + 2048 + 512 + 1024;
+  DDF_CUDA(cudaFuncSetAttribute((spconv_wgrad_table_kernel<CO, SR>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int per_sm = 1;
+  int KG = (512 / per_sm) / CO;
+  if (KG > kvol) KG = kvol;
+  const int G = (kvol + KG - 1) / KG;
+  const long long NS = ddf::cdiv(n_out, SR);
+  long long S = (ddf::kNumSM * per_sm) / G;
+  if (S > NS) S = NS;
+  if (S < 1) S = 1;
+  DDF_LAUNCH((spconv_wgrad_table_kernel<CO, SR>), (unsigned)(G * S), kThreads, smem, stream, feat, gout, table, gw,
+             (int)n_out, (int)n_in, kvol, cin, cout, KG, G);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
 // ---- host side: tensor maps ---------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -538,6 +796,20 @@ int spconv_tma_launch(const float* feat, const float* wt, const int* table, cons
   if (cout <= 64) { DDF_TMA_CASE(64); }
   DDF_TMA_CASE(128);
 #undef DDF_TMA_CASE
+}
+
+// table-driven wgrad: SubM layers with Cin == Cout in {32, 64, 128} (the sub-tile of the gather table
+// must fit its smem slot: kvol <= 27)
+bool spconv_wgrad_table_supported(int kvol, int cin, int cout) {
+  return kvol <= kMaxKvol && cin == cout && (cin == 32 || cin == 64 || cin == 128);
+}
+
+// gw [K, cin, cout] must be zeroed by the caller; table [n_out, K]
+int spconv_wgrad_table_launch(const float* feat, const float* gout, const int* table, float* gw,
+                              int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
+  if (cout <= 32) return launch_wgrad_table<32>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
+  if (cout <= 64) return launch_wgrad_table<64>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
+  return launch_wgrad_table<128>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
 }
 
 }  // namespace ddf

@@ -13,6 +13,8 @@ What is different from the reference:
     masks with host syncs; the padded layout (B*n_cam, max_pts_per_cam, .) is bit-identical, which
     matters because GroupNorm statistics include the padded rows.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -126,6 +128,9 @@ class ACTR(nn.Module):
         starts = torch.cumsum(counts, 0) - counts
         col_sorted = torch.arange(group.numel(), device=group.device) - starts[g_sorted]
         max_points = int(counts.max().item())
+        if os.environ.get("DDF_PRINT_QUERY_STATS"):
+            print("query stats: n=%d groups=%d max=%d padded=%d counts=%s" % (
+                group.numel(), n_groups, max_points, n_groups * max_points, counts.tolist()), flush=True)
         row = torch.empty_like(group)
         col = torch.empty_like(group)
         row[order] = g_sorted

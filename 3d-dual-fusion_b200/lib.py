@@ -37,6 +37,7 @@ _SIGNATURES = {
     "ddf_set_tensor_cores": [c_int],
     "ddf_round_tf32": [c_ptr, c_ptr, c_i64, c_ptr],
     "ddf_sparse_conv_dgrad": [c_ptr] * 5 + [c_i64] * 5 + [c_ptr],
+    "ddf_sparse_conv_wgrad_table": [c_ptr] * 4 + [c_i64] * 5 + [c_ptr],
     "ddf_sparse_conv_wgrad": [c_ptr] * 4 + [c_i64, c_ptr] + [c_i64] * 3 + [c_int, c_ptr],
     "ddf_furthest_point_sampling": [c_ptr] * 3 + [c_i64] * 3 + [c_ptr],
     "ddf_ball_query": [c_ptr] * 3 + [c_i64] * 3 + [c_f32, c_f32, c_i64, c_ptr],

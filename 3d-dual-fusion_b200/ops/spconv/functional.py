@@ -104,7 +104,11 @@ class TableConvFunction(Function):
         if ctx.needs_input_grad[0]:
             gin = ops.sparse_conv_dgrad(filters, grad_output, rb.scatter_table, features.shape[0])
         if ctx.needs_input_grad[1]:
-            gw = ops.sparse_conv_wgrad(features, filters, grad_output, rb.indice_pairs, rb.indice_pair_num)
+            if ctx.mode & 8 and getattr(rb, "subm", False) and grad_output.shape[0]:
+                # dense SubM layers: walk the output rows once through the gather table
+                gw = ops.sparse_conv_wgrad_table(features, filters, grad_output, rb.gather_table)
+            else:
+                gw = ops.sparse_conv_wgrad(features, filters, grad_output, rb.indice_pairs, rb.indice_pair_num)
         if ctx.cin != filters.shape[-2]:  # drop the zero-padded input channels again
             gin = gin[:, :ctx.cin].contiguous() if gin is not None else None
             gw = gw[..., :ctx.cin, :].contiguous() if gw is not None else None

@@ -41,7 +41,7 @@ def _listify(v, ndim):
 class Rulebook(object):
     """Reference-format rulebook + the row-major tables of the fused kernels."""
     __slots__ = ("outids", "indice_pairs", "indice_pair_num", "gather_table", "scatter_table",
-                 "out_spatial_shape")
+                 "out_spatial_shape", "subm")
 
     def __init__(self, outids, indice_pairs, indice_pair_num, gather_table, scatter_table,
                  out_spatial_shape):
@@ -51,6 +51,7 @@ class Rulebook(object):
         self.gather_table = gather_table
         self.scatter_table = scatter_table
         self.out_spatial_shape = out_spatial_shape
+        self.subm = False
 
 
 def build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
@@ -91,7 +92,9 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, paddin
                                          _lib.ptr(pairs), _lib.ptr(num), _lib.ptr(gather_t),
                                          _lib.ptr(scatter_t), _lib.ptr(ws), int(ws_bytes), stream)
             _lib.check(rc, "subm_indice_pairs")
-            return Rulebook(indices, pairs, num, gather_t, scatter_t, out_shape)
+            rb = Rulebook(indices, pairs, num, gather_t, scatter_t, out_shape)
+            rb.subm = True
+            return rb
         cnt = torch.empty(1, dtype=torch.int32, device=dev)
         rc = L.ddf_conv_count_outputs(_lib.ptr(indices), n, batch_size, *geo, _lib.ptr(cnt),
                                       _lib.ptr(ws), int(ws_bytes), stream)
@@ -222,4 +225,17 @@ def sparse_conv_wgrad(features, filters, grad_out, indice_pairs, indice_pair_num
                                                   indice_pairs.shape[2], _lib.ptr(gw), kvol, cin, cout, 0,
                                                   _lib.current_stream())
     _lib.check(rc, "sparse_conv_wgrad")
+    return gw
+
+
+def sparse_conv_wgrad_table(features, filters, grad_out, gather_table):
+    """wgrad through the forward gather table (dense SubM layers; see ddf_sparse_conv_wgrad_table)."""
+    cin, cout = filters.shape[-2], filters.shape[-1]
+    kvol = gather_table.shape[1]
+    gw = torch.empty_like(filters)
+    with torch.cuda.device(features.device):
+        rc = _lib.get_lib().ddf_sparse_conv_wgrad_table(_lib.ptr(features), _lib.ptr(grad_out), _lib.ptr(gather_table),
+                                                        _lib.ptr(gw), grad_out.shape[0], features.shape[0], kvol, cin,
+                                                        cout, _lib.current_stream())
+    _lib.check(rc, "sparse_conv_wgrad_table")
     return gw

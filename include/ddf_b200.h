@@ -178,7 +178,8 @@ int ddf_sparse_conv_forward(const float* features, const float* filters, const i
                             int64_t n_in, int64_t kvol, int64_t cin, int64_t cout, void* stream);
 
 /* Tensor-core bookkeeping: ddf_sparse_conv_tc_mode returns a bit mask of the kernels of a layer
- * that run as tcgen05 tf32 implicit GEMMs (1 forward, 2 dgrad, 4 wgrad; 0 with DDF_DISABLE_TC=1).
+ * that run as tcgen05 tf32 implicit GEMMs (1 forward, 2 dgrad, 4 wgrad, 8 table-driven wgrad
+ * available; 0 with DDF_DISABLE_TC=1).
  * tf32 keeps 10 mantissa bits and the hardware TRUNCATES fp32 operands; ddf_round_tf32 rounds a
  * tensor to the nearest tf32 first (dst may alias src) so the error is unbiased. Filters are
  * rounded inside the conv calls. */
@@ -193,6 +194,13 @@ int ddf_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 
 /* n_out = rows of grad_out (-1 when unknown: the TMA-staged kernel, whose tensor map needs the
  * height of the gathered tensor, is then not used). */
+/* wgrad through the forward gather table [n_out, K] instead of the pair lists (tcgen05; Cin, Cout in
+ * {32, 64, 128}, K <= 27): output rows walked once, grad_out read densely. grad_filters is zeroed
+ * inside. ddf_sparse_conv_tc_mode bit 3 (8) says whether a layer shape is supported. */
+int ddf_sparse_conv_wgrad_table(const float* features, const float* grad_out, const int* gather_table,
+                                float* grad_filters, int64_t n_out, int64_t n_in, int64_t kvol,
+                                int64_t cin, int64_t cout, void* stream);
+
 int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters, const int* scatter_table,
                           float* grad_in, float* filters_t_ws, int64_t n_in, int64_t n_out, int64_t kvol,
                           int64_t cin, int64_t cout, void* stream);

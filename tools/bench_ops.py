@@ -164,7 +164,11 @@ def bench_spconv(args):
         byts = 4.0 * (n * cin + n_out * cout + 27 * cin * cout) + 8.0 * pairs
         for kind, fn in (("fwd", lambda: ops.sparse_conv_forward(feat, w, rb.gather_table, None, n_out)),
                          ("dgrad", lambda: ops.sparse_conv_dgrad(w, go, rb.scatter_table, n)),
-                         ("wgrad", lambda: ops.sparse_conv_wgrad(feat, w, go, rb.indice_pairs, rb.indice_pair_num))):
+                         ("wgrad", lambda: ops.sparse_conv_wgrad(feat, w, go, rb.indice_pairs, rb.indice_pair_num)),
+                         ("wgrad_table", (lambda: ops.sparse_conv_wgrad_table(feat, w, go, rb.gather_table))
+                          if (subm and ops.tc_mode(27, cin, cout) & 8) else None)):
+            if fn is None:
+                continue
             med, best = time_cuda(fn, args.iters)
             print(json.dumps(dict(kernel="spconv %s %s" % (kind, name), ms_median=med, ms_best=best,
                                   GFLOP=flops / 1e9, TFLOPs=flops / med / 1e9, tensor_frac_bf16=flops / med / 1e9 / tfp,

@@ -1,10 +1,9 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, headline bench, ncu launch list, torch-profiler table.
+# One gpurun call: GPU parity tests, headline bench, torch-profiler table, ncu launch list.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.json
-timeout 300 python tools/run_tf_profile.py > gpurun_out/tf_profile.log 2>&1; echo "profile rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu rc=$?"
+DDF_PRINT_QUERY_STATS=1 timeout 300 python tools/run_tf_profile.py > gpurun_out/tf_profile.log 2>&1; echo "profile rc=$?"
+grep "query stats" gpurun_out/tf_profile.log | head -3
