@@ -480,8 +480,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgSlotsA = 8;        // 2 per issuer
 constexpr int kWgSlotsB = 3;
-// rows per sub-tile (= K extent of a stage) are chosen so that a stage is 16 KB: 4096 / Cin; the
-// per-stage fixed costs (barrier polls, address set-up, MMA issue) are the same for any stage size
+// rows per sub-tile (= K extent of a stage) is a template parameter; 32 is what ships
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -699,11 +698,12 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 template <int CO>
 int launch_wgrad_table(const float* feat, const float* gout, const int* table, float* gw, int64_t n_out,
                        int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
-  constexpr int SR = 4096 / CO;   // cin == cout == CO
+  constexpr int SR = 32;          // measured: 32-row stages with 2 CTAs per SM beat 64-row stages at 64 channels
   constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
   const int smem = kWgSlotsA * SR * cin * 4 + kWgSlotsB * SR * CO * 4 + kWgSlotsB * kTblBytes + 2048 + 512 + 1024;
   DDF_CUDA(cudaFuncSetAttribute((spconv_wgrad_table_kernel<CO, SR>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int per_sm = 1;
+  // two CTAs per SM when the rings are small; they then share the 512 TMEM columns
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   int KG = (512 / per_sm) / CO;
   if (KG > kvol) KG = kvol;
   const int G = (kvol + KG - 1) / KG;
@@ -798,16 +798,15 @@ int spconv_tma_launch(const float* feat, const float* wt, const int* table, cons
 #undef DDF_TMA_CASE
 }
 
-// table-driven wgrad: SubM layers with Cin == Cout in {32, 64, 128} (the sub-tile of the gather table
+// table-driven wgrad: SubM layers with Cin == Cout in {64, 128} (32 channels: the pair-list kernel is as fast) (the sub-tile of the gather table
 // must fit its smem slot: kvol <= 27)
 bool spconv_wgrad_table_supported(int kvol, int cin, int cout) {
-  return kvol <= kMaxKvol && cin == cout && (cin == 32 || cin == 64 || cin == 128);
+  return kvol <= kMaxKvol && cin == cout && (cin == 64 || cin == 128);
 }
 
 // gw [K, cin, cout] must be zeroed by the caller; table [n_out, K]
 int spconv_wgrad_table_launch(const float* feat, const float* gout, const int* table, float* gw,
                               int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
-  if (cout <= 32) return launch_wgrad_table<32>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
   if (cout <= 64) return launch_wgrad_table<64>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
   return launch_wgrad_table<128>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
 }

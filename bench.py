@@ -180,50 +180,77 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-class ConvTimer(object):
-    """Per-launch CUDA-event timing of the dominant kernel family (fused gather-GEMM sparse conv,
-    forward and dgrad launches) on the launching stream, plus its algorithmic FLOPs / bytes."""
+class KernelTimer(object):
+    """Per-launch CUDA-event timing of this library's kernel families on the launching stream (one
+    extra step after the timed region), with their algorithmic FLOPs / bytes."""
 
     def __init__(self):
-        self.records = []
+        self.records = {"conv": [], "wgrad": [], "msda_fwd": [], "msda_bwd": []}
+        self.saved = []
 
-    def install(self):
-        from ddf_b200.ops.spconv import ops
-        self._ops, self._fwd, self._dgrad = ops, ops.sparse_conv_forward, ops.sparse_conv_dgrad
+    def _wrap(self, mod, name, kind, meta):
+        orig = getattr(mod, name)
         timer = self
 
-        def fwd(features, filters, gather_table, bias, n_out):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = timer._fwd(features, filters, gather_table, bias, n_out)
-            b.record()
-            timer.records.append((a, b, gather_table, features.shape[0], n_out, filters.shape[-2], filters.shape[-1]))
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(*a, **k)
+            e1.record()
+            timer.records[kind].append((e0, e1, meta(*a, **k)))
             return out
 
-        def dgrad(filters, grad_out, scatter_table, n_in):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = timer._dgrad(filters, grad_out, scatter_table, n_in)
-            b.record()
-            # includes the small filter transpose launch that precedes the conv kernel
-            timer.records.append((a, b, scatter_table, grad_out.shape[0], n_in, filters.shape[-1], filters.shape[-2]))
-            return out
+        self.saved.append((mod, name, orig))
+        setattr(mod, name, wrapped)
 
-        ops.sparse_conv_forward, ops.sparse_conv_dgrad = fwd, dgrad
+    def install(self):
+        from ddf_b200.ops import msda
+        from ddf_b200.ops.spconv import ops
+
+        def conv_meta(table, n_src, n_dst, cin, cout):
+            return ("table", table, n_src, n_dst, cin, cout)
+
+        self._wrap(ops, "sparse_conv_forward", "conv",
+                   lambda f, w, t, b, n_out: conv_meta(t, f.shape[0], n_out, w.shape[-2], w.shape[-1]))
+        # dgrad timing includes the small filter-rounding launch that precedes the conv kernel
+        self._wrap(ops, "sparse_conv_dgrad", "conv",
+                   lambda w, g, t, n_in: conv_meta(t, g.shape[0], n_in, w.shape[-1], w.shape[-2]))
+        self._wrap(ops, "sparse_conv_wgrad", "wgrad",
+                   lambda f, w, g, pairs, num: ("pairs", num, f.shape[0], g.shape[0], w.shape[-2], w.shape[-1]))
+        self._wrap(ops, "sparse_conv_wgrad_table", "wgrad",
+                   lambda f, w, g, t: conv_meta(t, f.shape[0], g.shape[0], w.shape[-2], w.shape[-1]))
+
+        def msda_meta(value, shapes, lsi, loc, *rest):
+            N, S, M, D = value.shape
+            Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+            return (N, S, M, D, Lq, L, P)
+
+        self._wrap(msda, "ms_deform_attn_forward", "msda_fwd", msda_meta)
+        self._wrap(msda, "ms_deform_attn_backward", "msda_bwd", msda_meta)
 
     def remove(self):
-        self._ops.sparse_conv_forward, self._ops.sparse_conv_dgrad = self._fwd, self._dgrad
+        for mod, name, orig in self.saved:
+            setattr(mod, name, orig)
 
-    def summary(self):
-        torch.cuda.synchronize()
+    def conv_summary(self, kind):
         ms = flops = byts = 0.0
-        for a, b, table, n_src, n_dst, cin, cout in self.records:
-            pairs = int((table >= 0).sum().item())
-            kvol = table.shape[1]
+        for a, b, (how, t, n_src, n_dst, cin, cout) in self.records[kind]:
+            pairs = int((t >= 0).sum().item()) if how == "table" else int(t.sum().item())
+            kvol = t.shape[1] if how == "table" else t.shape[0]
             ms += a.elapsed_time(b)
             flops += 2.0 * pairs * cin * cout
             byts += 4.0 * (n_src * cin + n_dst * cout + kvol * cin * cout) + 8.0 * pairs
-        return len(self.records), ms, flops, byts
+        return len(self.records[kind]), ms, flops, byts
+
+    def msda_summary(self, kind):
+        ms = byts = 0.0
+        for a, b, (N, S, M, D, Lq, L, P) in self.records[kind]:
+            ms += a.elapsed_time(b)
+            if kind == "msda_fwd":
+                byts += 4.0 * (N * S * M * D + 3 * N * Lq * M * L * P + N * Lq * M * D)
+            else:
+                byts += 4.0 * (2 * N * S * M * D + 2 * N * Lq * M * D + 6 * N * Lq * M * L * P)
+        return len(self.records[kind]), ms, byts
 
 
 def run_ours(args):
@@ -292,25 +319,47 @@ def run_ours(args):
     ms_dev = timed(lambda: step(d_pts, d_feats), args.steps)
     launches = int(L.ddf_launch_count(1))
 
-    # (2) end to end through the public module call: pinned host inputs -> device, loss -> host
+    # (2) end to end through the public module call: every step copies ITS inputs from pinned host
+    # memory and reads the loss back. Like a data loader with pinned memory, the copy of step i+1 is
+    # enqueued on a side stream while step i computes; each step waits for its own copy.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def stage_inputs():
+        with torch.cuda.stream(copy_stream):
+            pts = [p.to(dev, non_blocking=True) for p in h_pts]
+            feats = h_feats.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged["next"] = (pts, feats, ev)
+
     def e2e_step():
-        pts = [p.to(dev, non_blocking=True) for p in h_pts]
-        feats = h_feats.to(dev, non_blocking=True)
+        pts, feats, ev = staged.pop("next")
+        torch.cuda.current_stream().wait_event(ev)
+        for t in pts + [feats]:
+            t.record_stream(torch.cuda.current_stream())
+        stage_inputs()                      # next step's host->device copy overlaps this step
         loss = step(pts, feats)
         h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    stage_inputs()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    staged.clear()
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
 
-    # (3) dominant-kernel roofline, timed live with CUDA events on the launching stream
-    ct = ConvTimer()
+    # (3) kernel-family rooflines, timed live with CUDA events on the launching stream
+    ct = KernelTimer()
     ct.install()
     step(d_pts, d_feats)
-    n_launch, conv_ms, conv_flops, conv_bytes = ct.summary()
+    torch.cuda.synchronize()
+    n_launch, conv_ms, conv_flops, conv_bytes = ct.conv_summary("conv")
+    n_wg, wg_ms, wg_flops, _ = ct.conv_summary("wgrad")
+    n_mf, mf_ms, mf_bytes = ct.msda_summary("msda_fwd")
+    n_mb, mb_ms, mb_bytes = ct.msda_summary("msda_bwd")
     ct.remove()
     if world > 1:
         dist.barrier()
@@ -333,13 +382,27 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {
-                "kernel": "sparse-conv fused gather-GEMM (forward + dgrad launches of one step)",
+                "kernel": "sparse-conv implicit GEMM, tcgen05 (forward + dgrad launches of one step)",
                 "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": tf / peak_tf if peak_tf else None, "traffic": None,
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); kernel computes in tf32/fp32" % how,
                 "launches_per_step": n_launch, "avg_launch_ms": conv_ms / max(n_launch, 1),
                 "share_of_step": conv_ms / (ms_dev / args.steps),
                 "algorithmic_GFLOP_per_step": conv_flops / 1e9, "algorithmic_MB_per_step": conv_bytes / 1e6,
+            },
+            # the other kernel families of the step, same method (achieved = algorithmic work / event time)
+            "kernels": {
+                "sparse_conv_wgrad": {"bound": "tensor", "launches_per_step": n_wg, "ms_per_step": wg_ms,
+                                      "achieved_TFLOPs": wg_flops / (wg_ms / 1e3) / 1e12 if wg_ms else None,
+                                      "frac": wg_flops / (wg_ms / 1e3) / 1e12 / peak_tf if wg_ms else None},
+                "deform_attn_fwd": {"bound": "hbm", "launches_per_step": n_mf, "ms_per_step": mf_ms,
+                                    "achieved_GBs": mf_bytes / (mf_ms / 1e3) / 1e9 if mf_ms else None,
+                                    "peak_GBs": peaks.get("hbm_gbs"),
+                                    "frac": mf_bytes / (mf_ms / 1e3) / 1e9 / peaks["hbm_gbs"] if mf_ms else None},
+                "deform_attn_bwd": {"bound": "hbm", "launches_per_step": n_mb, "ms_per_step": mb_ms,
+                                    "achieved_GBs": mb_bytes / (mb_ms / 1e3) / 1e9 if mb_ms else None,
+                                    "peak_GBs": peaks.get("hbm_gbs"),
+                                    "frac": mb_bytes / (mb_ms / 1e3) / 1e9 / peaks["hbm_gbs"] if mb_ms else None},
             },
         }
         if world == 1 and not args.no_cpu_baseline:
