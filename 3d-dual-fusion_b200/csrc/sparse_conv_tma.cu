@@ -497,8 +497,10 @@ __device__ __forceinline__ uint32_t mn_chunk_offset(int p, int mb, int ch, int n
   return (uint32_t)((((p >> 2) * nblk + mb) << 9) + (r << 7) + ((((ch >> 1) ^ r)) << 5) + ((ch & 1) << 4));
 }
 
+constexpr int kWgThreads = kThreads + 32;   // two staging warps instead of one
+
 template <int CO, int SR>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kWgThreads)
 spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
                           const int* __restrict__ table, float* __restrict__ gw, int n_out, int n_in,
                           int kvol, int cin, int cout, int KG, int G) {
@@ -519,6 +521,13 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef DDF_TRACE
+  __shared__ long long w_tr[8][64];
+  int tr_p = 0, tr_i = 0, tr_b = 0;
+#define WTR(ev, i) do { if (blockIdx.x == 5 && (i) < 64) w_tr[ev][i] = clock64(); } while (0)
+#else
+#define WTR(ev, i) do {} while (0)
+#endif
   const int g = blockIdx.x % G, split = blockIdx.x / G, S = gridDim.x / G;
   const int k0 = g * KG;
   const int nk = min(KG, kvol - k0);
@@ -534,7 +543,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
       mbar_init(a_empty + s, 1);
     }
     for (int s = 0; s < kWgSlotsB; ++s) {
-      mbar_init(b_full + s, 32);
+      mbar_init(b_full + s, 64);
       mbar_init(b_empty + s, kMaxT);
     }
     mbar_init(accum_bar, kMaxT);
@@ -556,15 +565,17 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
     // ===================== A producers =====================
     if (work) {
       const int grp = warp >> 1, gt = tid & 63;
-      const int a_chunks = cin >> 2;                 // 16-byte chunks per row (8, 16 or 32)
-      const int a_shift = 31 - __clz(a_chunks);
-      const int iters = (SR * a_chunks) >> 6;        // chunks per thread and stage
+      constexpr int kChunks = CO / 4;                    // 16-byte chunks per row (Cin == Cout == CO)
+      constexpr int kRowsPerPass = 64 / kChunks;         // rows covered by the 64 threads of a group
+      constexpr int kIters = SR / kRowsPerPass;          // chunks per thread and stage
+      const int cc = gt % kChunks, pr = gt / kChunks;    // this thread's chunk and first row
       int cnt[kMaxT] = {0, 0, 0, 0};
       int sb = 0;
       uint32_t pb = 0;
       for (int st = st_begin; st < st_end; ++st) {
         bool have_tbl = false;
         const int* tbl = reinterpret_cast<const int*>(t_base + sb * kTblBytes);
+        const int rows_left = n_out - st * SR;
 #pragma unroll 1
         for (int kk = 0; kk < nk; ++kk) {
           const int j = kk & (kMaxT - 1);
@@ -576,18 +587,30 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
             mbar_wait(b_full + sb, pb);     // table slice (and gout rows) of this sub-tile landed
             have_tbl = true;
           }
-          mbar_wait(a_empty + sl, (uint32_t)((c >> 1) & 1) ^ 1u);
-          const uint32_t dst = smem_u32(a_base + sl * a_bytes);
           const int k = k0 + kk;
-          for (int i = 0; i < iters; ++i) {
-            const int e = gt + (i << 6);
-            const int p = e >> a_shift, cc = e & (a_chunks - 1);
-            const int row = tbl[p * kvol + k];
-            const bool v = row >= 0 && st * SR + p < n_out;
+          int rowidx[kIters];
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) rowidx[i] = tbl[(pr + i * kRowsPerPass) * kvol + k];
+#ifdef DDF_TRACE
+          if (tid == 0) WTR(0, tr_p);
+#endif
+          mbar_wait(a_empty + sl, (uint32_t)((c >> 1) & 1) ^ 1u);
+#ifdef DDF_TRACE
+          if (tid == 0) WTR(1, tr_p);
+#endif
+          const uint32_t dst = smem_u32(a_base + sl * a_bytes);
+          const float* src0 = feat + cc * 4;
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            const int p = pr + i * kRowsPerPass;
+            const bool v = rowidx[i] >= 0 && p < rows_left;
             cp_async16(dst + mn_chunk_offset(p, cc >> 3, cc & 7, a_nb),
-                       feat + (v ? (size_t)(unsigned)row * (unsigned)cin + cc * 4 : 0), v ? 16u : 0u);
+                       src0 + (v ? (size_t)(unsigned)rowidx[i] * (unsigned)CO : 0), v ? 16u : 0u);
           }
           cp_async_arrive_noinc(a_full + sl);
+#ifdef DDF_TRACE
+          if (tid == 0) { WTR(2, tr_p); ++tr_p; }
+#endif
         }
         if (++sb == kWgSlotsB) { sb = 0; pb ^= 1u; }
       }
@@ -636,7 +659,13 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
         bool issued = false;
         for (int kk = j; kk < nk; kk += kMaxT) {
           const int sl = cnt & 1;
+#ifdef DDF_TRACE
+          if (j == 0 && lane == 0) WTR(3, tr_i);
+#endif
           mbar_wait(a_full + j * 2 + sl, (uint32_t)(cnt >> 1) & 1u);
+#ifdef DDF_TRACE
+          if (j == 0 && lane == 0) WTR(4, tr_i);
+#endif
           ++cnt;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -649,6 +678,9 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
             umma_tf32_elect(tm + (uint32_t)kk * kCols, a_desc, b_desc, idesc, (st != st_begin || ks != 0) ? 1u : 0u);
           }
           umma_commit_elect(a_empty + j * 2 + sl);
+#ifdef DDF_TRACE
+          if (j == 0 && lane == 0) { WTR(5, tr_i); ++tr_i; }
+#endif
           issued = true;
         }
         if (issued) umma_commit_elect(b_empty + sb); else mbar_arrive_elect(b_empty + sb);
@@ -658,36 +690,54 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
     }
     __syncwarp();
   } else {
-    // ===================== gout rows + table slice of each sub-tile (cp.async, 32 threads) =====================
+    // ===================== gout rows + table slice of each sub-tile (cp.async, 2 warps) =====================
     if (work) {
-      const int b_chunks = cout >> 2;
-      const int b_shift = 31 - __clz(b_chunks);
+      constexpr int kChunks = CO / 4;
+      const int bt = tid - (kProducerWarps + kMaxT) * 32;     // 0..63
       int sb = 0;
       uint32_t pb = 0;
       const long long tbl_bytes_total = (long long)n_out * kvol * 4;
+      const int tbl_chunks = (SR * kvol * 4 + 15) / 16;
       for (int st = st_begin; st < st_end; ++st) {
+#ifdef DDF_TRACE
+        if (bt == 0) WTR(6, tr_b);
+#endif
         mbar_wait(b_empty + sb, pb ^ 1u);
         const uint32_t tdst = smem_u32(t_base + sb * kTblBytes);
         const long long tsrc = (long long)st * SR * kvol * 4;
-        for (int e = lane; e < (SR * kvol * 4 + 15) / 16; e += 32) {
+#pragma unroll 4
+        for (int e = bt; e < tbl_chunks; e += 64) {
           const long long off = tsrc + e * 16;
           const long long left = tbl_bytes_total - off;
           const uint32_t nb = left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u);
           cp_async16(tdst + e * 16, reinterpret_cast<const uint8_t*>(table) + (nb ? off : 0), nb);
         }
         const uint32_t bdst = smem_u32(b_base + sb * b_bytes);
-        for (int e = lane; e < SR * b_chunks; e += 32) {
-          const int p = e >> b_shift, cc = e & (b_chunks - 1);
-          const long long row = (long long)st * SR + p;
-          const bool v = row < n_out;
-          cp_async16(bdst + mn_chunk_offset(p, cc >> 3, cc & 7, b_nb), gout + (v ? row * cout + cc * 4 : 0), v ? 16u : 0u);
+        const long long row0 = (long long)st * SR;
+#pragma unroll
+        for (int i = 0; i < SR * kChunks / 64; ++i) {
+          const int e = bt + i * 64;
+          const int p = e / kChunks, cc = e % kChunks;
+          const bool v = row0 + p < n_out;
+          cp_async16(bdst + mn_chunk_offset(p, cc >> 3, cc & 7, b_nb), gout + (v ? (row0 + p) * CO + cc * 4 : 0), v ? 16u : 0u);
         }
         cp_async_arrive_noinc(b_full + sb);
+#ifdef DDF_TRACE
+        if (bt == 0) { WTR(7, tr_b); ++tr_b; }
+#endif
         if (++sb == kWgSlotsB) { sb = 0; pb ^= 1u; }
       }
     }
   }
   __syncthreads();
+#ifdef DDF_TRACE
+  if (blockIdx.x == 5 && tid == 0) {
+    const long long t0 = w_tr[6][0];
+    for (int i = 0; i < 24; ++i)
+      printf("wgrad %2d: prod wait %6lld slot %6lld issued %6lld | issuer wait %6lld full %6lld commit %6lld | B wait %6lld loaded %6lld\n", i,
+             w_tr[0][i] - t0, w_tr[1][i] - t0, w_tr[2][i] - t0, w_tr[3][i] - t0, w_tr[4][i] - t0, w_tr[5][i] - t0, w_tr[6][i] - t0, w_tr[7][i] - t0);
+  }
+#endif
   if (warp == kProducerWarps) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
@@ -698,7 +748,9 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 template <int CO>
 int launch_wgrad_table(const float* feat, const float* gout, const int* table, float* gw, int64_t n_out,
                        int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
-  constexpr int SR = 32;          // measured: 32-row stages with 2 CTAs per SM beat 64-row stages at 64 channels
+  // rows per stage: 32 (64 and 128 channels; measured better than 64-row stages), 128 at 32 channels so
+  // that a stage is 16 KB and the per-stage fixed costs are amortised
+  constexpr int SR = CO == 32 ? 128 : 32;
   constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
   const int smem = kWgSlotsA * SR * cin * 4 + kWgSlotsB * SR * CO * 4 + kWgSlotsB * kTblBytes + 2048 + 512 + 1024;
   DDF_CUDA(cudaFuncSetAttribute((spconv_wgrad_table_kernel<CO, SR>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -711,7 +763,7 @@ int launch_wgrad_table(const float* feat, const float* gout, const int* table, f
   long long S = (ddf::kNumSM * per_sm) / G;
   if (S > NS) S = NS;
   if (S < 1) S = 1;
-  DDF_LAUNCH((spconv_wgrad_table_kernel<CO, SR>), (unsigned)(G * S), kThreads, smem, stream, feat, gout, table, gw,
+  DDF_LAUNCH((spconv_wgrad_table_kernel<CO, SR>), (unsigned)(G * S), kWgThreads, smem, stream, feat, gout, table, gw,
              (int)n_out, (int)n_in, kvol, cin, cout, KG, G);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -798,15 +850,16 @@ int spconv_tma_launch(const float* feat, const float* wt, const int* table, cons
 #undef DDF_TMA_CASE
 }
 
-// table-driven wgrad: SubM layers with Cin == Cout in {64, 128} (32 channels: the pair-list kernel is as fast) (the sub-tile of the gather table
+// table-driven wgrad: SubM layers with Cin == Cout in {32, 64, 128} (the sub-tile of the gather table
 // must fit its smem slot: kvol <= 27)
 bool spconv_wgrad_table_supported(int kvol, int cin, int cout) {
-  return kvol <= kMaxKvol && cin == cout && (cin == 64 || cin == 128);
+  return kvol <= kMaxKvol && cin == cout && (cin == 32 || cin == 64 || cin == 128);
 }
 
 // gw [K, cin, cout] must be zeroed by the caller; table [n_out, K]
 int spconv_wgrad_table_launch(const float* feat, const float* gout, const int* table, float* gw,
                               int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
+  if (cout <= 32) return launch_wgrad_table<32>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
   if (cout <= 64) return launch_wgrad_table<64>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
   return launch_wgrad_table<128>(feat, gout, table, gw, n_out, n_in, kvol, cin, cout, stream);
 }
