@@ -83,12 +83,16 @@ class TableConvFunction(Function):
             filters = torch.nn.functional.pad(filters, (0, 0, 0, pad))
             cin += pad
         ctx.mode = mode = ops.tc_mode(rulebook.indice_pairs.shape[0], cin, cout)
+        saved = features
         if mode & 5 and features.shape[0]:
-            # tensor-core operands are made exact tf32 once; forward and wgrad share the copy
-            features = ops.round_tf32(features)
+            # tensor-core operands are made exact tf32 once; forward and wgrad share the copy. A forward
+            # that runs in fp32 (narrow layers) keeps the unrounded features.
+            saved = ops.round_tf32(features)
+            if mode & 1:
+                features = saved
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(features, filters)
+        ctx.save_for_backward(saved, filters)
         return ops.sparse_conv_forward(features, filters, rulebook.gather_table, bias, num_activate_out)
 
     @staticmethod
@@ -98,11 +102,13 @@ class TableConvFunction(Function):
         rb = ctx.rulebook
         grad_output = grad_output.contiguous()
         gb = grad_output.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        grad_exact = grad_output
         if ctx.mode & 6 and grad_output.shape[0]:
             grad_output = ops.round_tf32(grad_output)  # shared by dgrad and wgrad
         gin = gw = None
         if ctx.needs_input_grad[0]:
-            gin = ops.sparse_conv_dgrad(filters, grad_output, rb.scatter_table, features.shape[0])
+            gin = ops.sparse_conv_dgrad(filters, grad_output if ctx.mode & 2 else grad_exact, rb.scatter_table,
+                                        features.shape[0])
         if ctx.needs_input_grad[1]:
             if ctx.mode & 8 and getattr(rb, "subm", False) and grad_output.shape[0]:
                 # dense SubM layers: walk the output rows once through the gather table
