@@ -1,0 +1,281 @@
+// Fused elementwise kernels of the 3D-DF encoder layers (fp32, sm_100a), replacing chains of separate
+// PyTorch kernels in <proj>/models/model_utils/actr_transformer.py:
+//
+//   forward_ffn (:383-397):  linear2(dropout(relu(linear1(x))))
+//       -> ddf_bias_relu_dropout_forward / _backward on the [tokens, d_ffn] hidden activation (598 MB per
+//          FFN at the TransFusion config): bias add + ReLU + dropout in ONE in-place pass instead of three
+//          read+write passes; backward needs no mask tensor: out != 0  <=>  kept and positive.
+//   norm(src + dropout(src2)) (:385, :391, :406):
+//       -> ddf_add_dropout_layer_norm_forward / _backward: residual add + dropout + LayerNorm, a warp per
+//          token row (torch's LayerNorm kernel takes 224 us for 146k x 128 rows; this is one 4-pass stream).
+//
+// Dropout uses a counter-based hash of (seed, element index): nothing is stored, backward recomputes
+// the keep decision.  All kernels are HBM-bound streaming kernels with 16-byte accesses.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// 64-bit mix (splitmix64 finaliser) of (seed, index of a group of 4 elements) -> four 16-bit uniforms
+__device__ __forceinline__ unsigned long long mix(unsigned long long seed, unsigned long long i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// keep flags of the 4 elements of vector i (bit j = element j kept); thr = p * 65536
+__device__ __forceinline__ unsigned keep4(unsigned long long seed, unsigned long long i, unsigned thr) {
+  const unsigned long long r = mix(seed, i);
+  return ((unsigned)(r & 0xffff) >= thr ? 1u : 0u) | ((unsigned)((r >> 16) & 0xffff) >= thr ? 2u : 0u) |
+         ((unsigned)((r >> 32) & 0xffff) >= thr ? 4u : 0u) | ((unsigned)(r >> 48) >= thr ? 8u : 0u);
+}
+
+__global__ void __launch_bounds__(kThreads)
+bias_relu_dropout_kernel(const float* __restrict__ h, const float* __restrict__ bias, float* __restrict__ out,
+                         long long n4, int c4, unsigned long long seed, unsigned thr, float scale) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = ldg4(h + i * 4);
+  if (bias) {
+    const float4 b = ldg4(bias + (i % c4) * 4);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  const unsigned k = thr ? keep4(seed, (unsigned long long)i, thr) : 15u;
+  v.x = (k & 1u) && v.x > 0.f ? v.x * scale : 0.f;
+  v.y = (k & 2u) && v.y > 0.f ? v.y * scale : 0.f;
+  v.z = (k & 4u) && v.z > 0.f ? v.z * scale : 0.f;
+  v.w = (k & 8u) && v.w > 0.f ? v.w * scale : 0.f;
+  *reinterpret_cast<float4*>(out + i * 4) = v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+relu_dropout_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ out, float* __restrict__ gx,
+                        long long n4, float scale) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n4) return;
+  const float4 g = ldg4(gy + i * 4), o = ldg4(out + i * 4);
+  float4 r;
+  r.x = o.x != 0.f ? g.x * scale : 0.f;
+  r.y = o.y != 0.f ? g.y * scale : 0.f;
+  r.z = o.z != 0.f ? g.z * scale : 0.f;
+  r.w = o.w != 0.f ? g.w * scale : 0.f;
+  *reinterpret_cast<float4*>(gx + i * 4) = r;
+}
+
+// ---- s = a + dropout(b);  y = LayerNorm(s) * gamma + beta.  One warp per row, C = 32 * VPL * 4 ---------
+template <int VPL>   // float4 vectors per lane: C = 128 * VPL
+__global__ void __launch_bounds__(kThreads)
+add_dropout_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* __restrict__ s_out, float* __restrict__ y, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out, long long rows, unsigned long long seed, unsigned thr,
+                          float scale, float eps) {
+  constexpr int C = 128 * VPL;
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  float4 v[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const long long e4 = row * (C / 4) + j * 32 + lane;
+    v[j] = ldg4(a + e4 * 4);
+    if (b) {
+      float4 d = ldg4(b + e4 * 4);
+      const unsigned k = thr ? keep4(seed, (unsigned long long)e4, thr) : 15u;
+      v[j].x += (k & 1u) ? d.x * scale : 0.f;
+      v[j].y += (k & 2u) ? d.y * scale : 0.f;
+      v[j].z += (k & 4u) ? d.z * scale : 0.f;
+      v[j].w += (k & 8u) ? d.w * scale : 0.f;
+    }
+    sum += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / C);
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const float dx = v[j].x - mean, dy = v[j].y - mean, dz = v[j].z - mean, dw = v[j].w - mean;
+    var += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var * (1.f / C) + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const long long e4 = row * (C / 4) + j * 32 + lane;
+    const int c = (j * 32 + lane) * 4;
+    if (s_out) *reinterpret_cast<float4*>(s_out + e4 * 4) = v[j];
+    const float4 g = ldg4(gamma + c), be = ldg4(beta + c);
+    float4 o;
+    o.x = (v[j].x - mean) * rstd * g.x + be.x;
+    o.y = (v[j].y - mean) * rstd * g.y + be.y;
+    o.z = (v[j].z - mean) * rstd * g.z + be.z;
+    o.w = (v[j].w - mean) * rstd * g.w + be.w;
+    *reinterpret_cast<float4*>(y + e4 * 4) = o;
+  }
+}
+
+// gs = rstd * (gy*gamma - mean_c(gy*gamma) - xhat * mean_c(gy*gamma*xhat));  ga = gs;  gb = gs * keep * scale
+// ggamma += sum_rows gy * xhat, gbeta += sum_rows gy  (per-CTA partials in shared memory, then atomics)
+template <int VPL>
+__global__ void __launch_bounds__(kThreads)
+add_dropout_ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ s,
+                          const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, float* __restrict__ ga, float* __restrict__ gb,
+                          float* __restrict__ ggamma, float* __restrict__ gbeta, long long rows,
+                          unsigned long long seed, unsigned thr, float scale) {
+  constexpr int C = 128 * VPL;
+  __shared__ float sh_g[C], sh_b[C];
+  for (int i = threadIdx.x; i < C; i += kThreads) sh_g[i] = sh_b[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * kThreads) >> 5;
+  float4 acc_g[VPL], acc_b[VPL];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) acc_g[j] = acc_b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5; row < rows; row += warps) {
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    float4 g[VPL], xh[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const long long e4 = row * (C / 4) + j * 32 + lane;
+      const float4 gyv = ldg4(gy + e4 * 4), sv = ldg4(s + e4 * 4), gm = ldg4(gamma + (j * 32 + lane) * 4);
+      xh[j] = make_float4((sv.x - mean) * rstd, (sv.y - mean) * rstd, (sv.z - mean) * rstd, (sv.w - mean) * rstd);
+      acc_b[j].x += gyv.x; acc_b[j].y += gyv.y; acc_b[j].z += gyv.z; acc_b[j].w += gyv.w;
+      acc_g[j].x += gyv.x * xh[j].x; acc_g[j].y += gyv.y * xh[j].y;
+      acc_g[j].z += gyv.z * xh[j].z; acc_g[j].w += gyv.w * xh[j].w;
+      g[j] = make_float4(gyv.x * gm.x, gyv.y * gm.y, gyv.z * gm.z, gyv.w * gm.w);
+      s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+      s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 * (1.f / C), m2 = s2 * (1.f / C);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const long long e4 = row * (C / 4) + j * 32 + lane;
+      float4 r;
+      r.x = rstd * (g[j].x - m1 - xh[j].x * m2);
+      r.y = rstd * (g[j].y - m1 - xh[j].y * m2);
+      r.z = rstd * (g[j].z - m1 - xh[j].z * m2);
+      r.w = rstd * (g[j].w - m1 - xh[j].w * m2);
+      if (ga) *reinterpret_cast<float4*>(ga + e4 * 4) = r;
+      if (gb) {
+        const unsigned k = thr ? keep4(seed, (unsigned long long)e4, thr) : 15u;
+        float4 d;
+        d.x = (k & 1u) ? r.x * scale : 0.f;
+        d.y = (k & 2u) ? r.y * scale : 0.f;
+        d.z = (k & 4u) ? r.z * scale : 0.f;
+        d.w = (k & 8u) ? r.w * scale : 0.f;
+        *reinterpret_cast<float4*>(gb + e4 * 4) = d;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = (j * 32 + lane) * 4;
+    atomicAdd(&sh_g[c], acc_g[j].x); atomicAdd(&sh_g[c + 1], acc_g[j].y);
+    atomicAdd(&sh_g[c + 2], acc_g[j].z); atomicAdd(&sh_g[c + 3], acc_g[j].w);
+    atomicAdd(&sh_b[c], acc_b[j].x); atomicAdd(&sh_b[c + 1], acc_b[j].y);
+    atomicAdd(&sh_b[c + 2], acc_b[j].z); atomicAdd(&sh_b[c + 3], acc_b[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += kThreads) {
+    if (ggamma) atomicAdd(ggamma + i, sh_g[i]);
+    if (gbeta) atomicAdd(gbeta + i, sh_b[i]);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline unsigned threshold(float p) {
+  if (p <= 0.f) return 0u;
+  const float t = p * 65536.f + 0.5f;
+  return t >= 65535.f ? 65535u : (unsigned)t;
+}
+
+}  // namespace
+
+// out[n, C] = dropout(relu(h + bias)); out may alias h. p = drop probability (0 in eval), the kept
+// values are scaled by 1/(1-p). C % 4 == 0, 16-byte aligned pointers. bias may be NULL.
+extern "C" int ddf_bias_relu_dropout_forward(const float* h, const float* bias, float* out, int64_t n,
+                                             int64_t C, float p, uint64_t seed, void* stream_) {
+  DDF_CHECK_ARG(n >= 0 && C > 0 && C % 4 == 0 && p >= 0.f && p < 1.f, "bias_relu_dropout: bad arguments");
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(h && out && aligned16(h) && aligned16(out) && aligned16(bias), "bias_relu_dropout: null or misaligned pointer");
+  const long long n4 = n * C / 4;
+  DDF_LAUNCH(bias_relu_dropout_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, (cudaStream_t)stream_, h, bias,
+             out, n4, (int)(C / 4), (unsigned long long)seed, threshold(p), 1.f / (1.f - p));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// grad_h = grad_out * (out != 0) / (1 - p): `out` is the forward result (no mask tensor is kept).
+extern "C" int ddf_bias_relu_dropout_backward(const float* grad_out, const float* out, float* grad_h,
+                                              int64_t numel, float p, void* stream_) {
+  DDF_CHECK_ARG(numel >= 0 && numel % 4 == 0 && p >= 0.f && p < 1.f, "bias_relu_dropout_backward: bad arguments");
+  if (numel == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_out && out && grad_h && aligned16(grad_out) && aligned16(out) && aligned16(grad_h),
+                "bias_relu_dropout_backward: null or misaligned pointer");
+  DDF_LAUNCH(relu_dropout_bwd_kernel, (unsigned)ddf::cdiv(numel / 4, kThreads), kThreads, 0, (cudaStream_t)stream_,
+             grad_out, out, grad_h, (long long)(numel / 4), 1.f / (1.f - p));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+#define DDF_LN_DISPATCH(C, CALL)                     \
+  switch (C) {                                       \
+    case 128: { constexpr int VPL = 1; CALL; } break; \
+    case 256: { constexpr int VPL = 2; CALL; } break; \
+    case 512: { constexpr int VPL = 4; CALL; } break; \
+    default:                                         \
+      ddf::set_error("add_dropout_layer_norm: C must be 128, 256 or 512, got %lld", (long long)(C)); \
+      return DDF_ERR_ARG;                            \
+  }
+
+// s = a + dropout(b) (b may be NULL: s = a);  y = LayerNorm(s) * gamma + beta over the last dim C.
+// s_out (optional) receives s, mean / rstd [rows] are saved for backward.
+extern "C" int ddf_add_dropout_layer_norm_forward(const float* a, const float* b, const float* gamma,
+                                                  const float* beta, float* s_out, float* y, float* mean,
+                                                  float* rstd, int64_t rows, int64_t C, float p,
+                                                  uint64_t seed, float eps, void* stream_) {
+  DDF_CHECK_ARG(rows >= 0 && p >= 0.f && p < 1.f, "add_dropout_layer_norm: bad arguments");
+  if (rows == 0) return DDF_OK;
+  DDF_CHECK_ARG(a && gamma && beta && y && mean && rstd, "add_dropout_layer_norm: null pointer");
+  DDF_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(beta) && aligned16(s_out) && aligned16(y),
+                "add_dropout_layer_norm: misaligned pointer");
+  const unsigned grid = (unsigned)ddf::cdiv(rows * 32, kThreads);
+  DDF_LN_DISPATCH(C, DDF_LAUNCH(add_dropout_ln_fwd_kernel<VPL>, grid, kThreads, 0, (cudaStream_t)stream_, a, b, gamma,
+                                beta, s_out, y, mean, rstd, (long long)rows, (unsigned long long)seed, threshold(p),
+                                1.f / (1.f - p), eps));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// grad_gamma / grad_beta [C] are ACCUMULATED into (caller zeroes them); grad_a / grad_b may be NULL.
+extern "C" int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, const float* gamma,
+                                                   const float* mean, const float* rstd, float* grad_a,
+                                                   float* grad_b, float* grad_gamma, float* grad_beta,
+                                                   int64_t rows, int64_t C, float p, uint64_t seed,
+                                                   void* stream_) {
+  DDF_CHECK_ARG(rows >= 0 && p >= 0.f && p < 1.f, "add_dropout_layer_norm_backward: bad arguments");
+  if (rows == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_y && s && gamma && mean && rstd, "add_dropout_layer_norm_backward: null pointer");
+  long long grid = ddf::cdiv(rows * 32, kThreads);
+  if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;   // grid-stride: bounded number of atomics on grad_gamma / beta
+  DDF_LN_DISPATCH(C, DDF_LAUNCH(add_dropout_ln_bwd_kernel<VPL>, (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_y,
+                                s, gamma, mean, rstd, grad_a, grad_b, grad_gamma, grad_beta, (long long)rows,
+                                (unsigned long long)seed, threshold(p), 1.f / (1.f - p)));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}

@@ -328,12 +328,16 @@ extern "C" int ddf_subm_indice_pairs(const int* indices, int64_t num_in, int64_t
   int rc = make_geom(&g, batch_size, spatial_shape, spatial_shape, ksize, ones, ones, dilation, 1);
   if (rc) return rc;
   DDF_CHECK_ARG(num_in >= 0 && num_in * g.kvol < INT_MAX, "subm_indice_pairs: too many pairs");
-  DDF_CHECK_ARG(indice_num != nullptr, "subm_indice_pairs: null indice_num");
+  // indice_pairs == NULL: tables only (the pair lists cost a scan + compaction over N*K entries and are
+  // not needed when forward, dgrad and wgrad all walk the tables)
+  DDF_CHECK_ARG(indice_num != nullptr || indice_pairs == nullptr, "subm_indice_pairs: null indice_num");
   if (num_in == 0) {
-    DDF_CUDA(cudaMemsetAsync(indice_num, 0, sizeof(int) * g.kvol, stream));
+    if (indice_num) DDF_CUDA(cudaMemsetAsync(indice_num, 0, sizeof(int) * g.kvol, stream));
     return DDF_OK;
   }
-  DDF_CHECK_ARG(indices && indice_pairs, "subm_indice_pairs: null pointer");
+  DDF_CHECK_ARG(indice_pairs != nullptr || gather_table != nullptr || scatter_table != nullptr,
+                "subm_indice_pairs: nothing to build");
+  DDF_CHECK_ARG(indices != nullptr, "subm_indice_pairs: null pointer");
   RbWs w = carve(workspace, num_in, g, 1);
   DDF_CHECK_ARG(workspace && (size_t)workspace_bytes >= w.bytes,
                 "subm_indice_pairs: workspace too small");
@@ -348,6 +352,7 @@ extern "C" int ddf_subm_indice_pairs(const int* indices, int64_t num_in, int64_t
   DDF_LAUNCH(subm_tables_kernel, (unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream, 
       indices, n, g, w.keys, w.vals, slots - 1, st, gather_table, w.flags);
   DDF_LAUNCH_CHECK();
+  if (!indice_pairs) return DDF_OK;
   return emit_pairs(w, st, n, g.kvol, indice_pairs, indice_num, stream);
 }
 

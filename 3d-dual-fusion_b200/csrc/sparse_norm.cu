@@ -97,12 +97,20 @@ bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ 
   Acc8 a;
 #pragma unroll
   for (int i = 0; i < 8; ++i) a.v[i] = 0.0;
-  for (long long r = (long long)blockIdx.x * rpb + rl; r < n; r += (long long)gridDim.x * rpb) {
-    const float4 v = ldg4(x + r * C + cg * 4);
+  auto add = [&](const float4 v) {
     a.v[0] += v.x; a.v[1] += v.y; a.v[2] += v.z; a.v[3] += v.w;
     a.v[4] += (double)v.x * v.x; a.v[5] += (double)v.y * v.y;
     a.v[6] += (double)v.z * v.z; a.v[7] += (double)v.w * v.w;
+  };
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + rl;
+  const float* px = x + cg * 4;
+  for (; r + 3 * step < n; r += 4 * step) {   // four independent 16-byte loads in flight per thread
+    const float4 v0 = ldg4(px + r * C), v1 = ldg4(px + (r + step) * C), v2 = ldg4(px + (r + 2 * step) * C),
+                 v3 = ldg4(px + (r + 3 * step) * C);
+    add(v0); add(v1); add(v2); add(v3);
   }
+  for (; r < n; r += step) add(ldg4(px + r * C));
   if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
   fold_partials(part, C, tot);
   for (int c = threadIdx.x; c < C; c += kThreads) {
@@ -166,18 +174,29 @@ bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
   Acc8 a;
 #pragma unroll
   for (int i = 0; i < 8; ++i) a.v[i] = 0.0;
-  for (long long r = (long long)blockIdx.x * rpb + rl; r < n; r += (long long)gridDim.x * rpb) {
-    const long long o = r * C + cg * 4;
-    float4 g = ldg4(gy + o);
+  auto add = [&](float4 g, const float4 yy, const float4 v) {
     if (relu) {
-      const float4 yy = ldg4(y + o);
       g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f;
       g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
     }
-    const float4 v = ldg4(x + o);
     a.v[0] += g.x; a.v[1] += g.y; a.v[2] += g.z; a.v[3] += g.w;
     a.v[4] += (double)g.x * ((v.x - m.x) * s.x); a.v[5] += (double)g.y * ((v.y - m.y) * s.y);
     a.v[6] += (double)g.z * ((v.z - m.z) * s.z); a.v[7] += (double)g.w * ((v.w - m.w) * s.w);
+  };
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + rl;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (; r + step < n; r += 2 * step) {       // two rows (six 16-byte loads) in flight per thread
+    const long long o0 = r * C + cg * 4, o1 = (r + step) * C + cg * 4;
+    const float4 g0 = ldg4(gy + o0), g1 = ldg4(gy + o1);
+    const float4 y0 = relu ? ldg4(y + o0) : one, y1 = relu ? ldg4(y + o1) : one;
+    const float4 v0 = ldg4(x + o0), v1 = ldg4(x + o1);
+    add(g0, y0, v0);
+    add(g1, y1, v1);
+  }
+  for (; r < n; r += step) {
+    const long long o = r * C + cg * 4;
+    add(ldg4(gy + o), relu ? ldg4(y + o) : one, ldg4(x + o));
   }
   if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
   fold_partials(part, C, tot);

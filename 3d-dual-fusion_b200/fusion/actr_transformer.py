@@ -10,6 +10,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import normal_
 
+from ..ops import fused
 from .attentions import attn_dict
 from .ms_deform_attn import MSDeformAttn
 
@@ -52,14 +53,17 @@ class DeformableTransformerEncoderLayer(nn.Module):
     with_pos_embed = staticmethod(_with_pos)
 
     def forward_ffn(self, src):
-        src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
-        return self.norm2(src + self.dropout3(src2))
+        if self.activation is F.relu:
+            hidden = fused.ffn_hidden(self.linear1, self.dropout2, src)
+        else:
+            hidden = self.dropout2(self.activation(self.linear1(src)))
+        return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, self.linear2(hidden))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
                 padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None):
         src2 = self.self_attn(_with_pos(q_feat, q_pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask)
-        q_feat = self.norm1(q_feat + self.dropout1(src2))
+        q_feat = fused.add_dropout_layer_norm(self.norm1, self.dropout1, q_feat, src2)
         return self.forward_ffn(q_feat), q_i_feat
 
 
@@ -96,19 +100,25 @@ class DeformableTransformerFusionEncoderLayer(nn.Module):
 
     with_pos_embed = staticmethod(_with_pos)
 
+    def _hidden(self, linear, dropout, src):
+        # bias + ReLU + dropout of the [tokens, d_ffn] hidden activation as one in-place pass
+        if self.activation is F.relu:
+            return fused.ffn_hidden(linear, dropout, src)
+        return dropout(self.activation(linear(src)))
+
     def forward_i_ffn(self, src):
-        src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
-        return self.norm2(src + self.dropout3(src2))
+        src2 = self.linear2(self._hidden(self.linear1, self.dropout2, src))
+        return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, src2)
 
     def forward_p_ffn(self, src):
-        src2 = self.linear4(self.dropout4(self.activation(self.linear3(src))))
-        return self.norm3(src + self.dropout5(src2))
+        src2 = self.linear4(self._hidden(self.linear3, self.dropout4, src))
+        return fused.add_dropout_layer_norm(self.norm3, self.dropout5, src, src2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
                 padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None):
         src2 = self.self_attn(_with_pos(q_feat, q_pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask, i_query=_with_pos(q_i_feat, q_pos))
-        q_i_feat = self.norm1(q_i_feat + self.dropout1(src2))
+        q_i_feat = fused.add_dropout_layer_norm(self.norm1, self.dropout1, q_i_feat, src2)
         if self.gate_first:
             q_feat, q_i_feat = self.fusion_layer(q_feat, q_i_feat)
             return self.forward_p_ffn(q_feat), self.forward_i_ffn(q_i_feat)

@@ -1,0 +1,116 @@
+"""Fused elementwise ops of the 3D-DF encoder layers (``ddf_bias_relu_dropout_*``,
+``ddf_add_dropout_layer_norm_*``, include/ddf_b200.h) behind helpers that take the reference's own
+modules (``nn.Linear``, ``nn.Dropout``, ``nn.LayerNorm``: parameters and state-dict keys untouched):
+
+    ffn_hidden(linear1, dropout, x)            == dropout(relu(linear1(x)))
+    add_dropout_layer_norm(norm, dropout, a, b) == norm(a + dropout(b))
+
+(<proj>/models/model_utils/actr_transformer.py:383-397).
+"""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import lib as _lib
+
+
+def _seed():
+    # drawn from the CPU generator, so torch.manual_seed makes the dropout pattern reproducible
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class _BiasReluDropout(Function):
+    @staticmethod
+    def forward(ctx, h, bias, p):
+        _lib.require_cuda(h, bias)
+        C = h.shape[-1]
+        n = h.numel() // C
+        seed = _seed() if p > 0 else 0
+        with torch.cuda.device(h.device):
+            rc = _lib.get_lib().ddf_bias_relu_dropout_forward(_lib.ptr(h), _lib.ptr(bias), _lib.ptr(h), n, C,
+                                                              float(p), seed, _lib.current_stream())
+        _lib.check(rc, "bias_relu_dropout_forward")
+        ctx.p = float(p)
+        ctx.has_bias = bias is not None
+        ctx.mark_dirty(h)
+        ctx.save_for_backward(h)
+        return h
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (out,) = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gh = torch.empty_like(out)
+        with torch.cuda.device(out.device):
+            rc = _lib.get_lib().ddf_bias_relu_dropout_backward(_lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(gh),
+                                                               out.numel(), ctx.p, _lib.current_stream())
+        _lib.check(rc, "bias_relu_dropout_backward")
+        gb = gh.reshape(-1, gh.shape[-1]).sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        return gh, gb, None
+
+
+def ffn_hidden(linear, dropout, x):
+    """``dropout(relu(linear(x)))``: the GEMM without bias, then bias + ReLU + dropout in one in-place pass."""
+    C = linear.out_features
+    if x.dtype != torch.float32 or C % 4:
+        _lib.require_cuda(x)
+        return dropout(F.relu(linear(x)))
+    h = F.linear(x, linear.weight)           # fresh tensor: safe to overwrite in place
+    p = dropout.p if dropout.training else 0.0
+    return _BiasReluDropout.apply(h, linear.bias, p)
+
+
+class _AddDropoutLayerNorm(Function):
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, p, eps):
+        _lib.require_cuda(a, b, gamma, beta)
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        C = a.shape[-1]
+        rows = a.numel() // C
+        s = torch.empty_like(a)
+        y = torch.empty_like(a)
+        mean = torch.empty(rows, dtype=torch.float32, device=a.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=a.device)
+        seed = _seed() if (p > 0 and b is not None) else 0
+        with torch.cuda.device(a.device):
+            rc = _lib.get_lib().ddf_add_dropout_layer_norm_forward(
+                _lib.ptr(a), _lib.ptr(b), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(s), _lib.ptr(y), _lib.ptr(mean),
+                _lib.ptr(rstd), rows, C, float(p), seed, float(eps), _lib.current_stream())
+        _lib.check(rc, "add_dropout_layer_norm_forward")
+        ctx.p, ctx.seed, ctx.has_b = float(p), seed, b is not None
+        ctx.save_for_backward(s, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        s, gamma, mean, rstd = ctx.saved_tensors
+        grad_y = grad_y.contiguous()
+        C = s.shape[-1]
+        rows = s.numel() // C
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_b
+        ga = torch.empty_like(s) if (need_a or (need_b and ctx.p == 0)) else None
+        share = need_b and ctx.p == 0          # without dropout both branches get the same gradient
+        gb = torch.empty_like(s) if (need_b and not share) else None
+        gg = torch.zeros(C, dtype=torch.float32, device=s.device)
+        gbeta = torch.zeros(C, dtype=torch.float32, device=s.device)
+        with torch.cuda.device(s.device):
+            rc = _lib.get_lib().ddf_add_dropout_layer_norm_backward(
+                _lib.ptr(grad_y), _lib.ptr(s), _lib.ptr(gamma), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(ga),
+                _lib.ptr(gb), _lib.ptr(gg), _lib.ptr(gbeta), rows, C, ctx.p, ctx.seed, _lib.current_stream())
+        _lib.check(rc, "add_dropout_layer_norm_backward")
+        return (ga if need_a else None), (ga if share else gb), gg, gbeta, None, None
+
+
+def add_dropout_layer_norm(norm, dropout, a, b):
+    """``norm(a + dropout(b))`` with ``norm`` an ``nn.LayerNorm`` over the last dim."""
+    C = a.shape[-1]
+    if (a.dtype != torch.float32 or C not in (128, 256, 512) or not norm.elementwise_affine
+            or norm.bias is None or tuple(norm.normalized_shape) != (C,)):
+        _lib.require_cuda(a)
+        return norm(a + dropout(b))
+    p = dropout.p if (dropout is not None and dropout.training) else 0.0
+    return _AddDropoutLayerNorm.apply(a, b, norm.weight, norm.bias, p, norm.eps)

@@ -21,6 +21,26 @@ def _fan_in_hwio(tensor):
     return tensor.size(-2) * rf
 
 
+class _IndiceTuple(object):
+    """The reference's ``indice_dict[key]`` 5-tuple (outids, indices, indice_pairs, indice_pair_num,
+    spatial_shape; conv.py:181-186) over a rulebook whose pair lists may be built on first access."""
+
+    def __init__(self, rb, indices, spatial_shape):
+        self._rb, self._indices, self._shape = rb, indices, spatial_shape
+
+    def _items(self):
+        return (self._rb.outids, self._indices, self._rb.indice_pairs, self._rb.indice_pair_num, self._shape)
+
+    def __iter__(self):
+        return iter(self._items())
+
+    def __getitem__(self, i):
+        return self._items()[i]
+
+    def __len__(self):
+        return 5
+
+
 class SparseConvolution(SparseModule):
     def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1,
                  groups=1, bias=True, subm=False, output_padding=0, transposed=False, inverse=False,
@@ -71,13 +91,15 @@ class SparseConvolution(SparseModule):
                    tuple(self.padding), tuple(self.dilation), self.subm)
         rb = input.indice_dict.get(("__rulebook__", key))
         if rb is None:
+            kvol = int(np.prod(self.kernel_size))
+            # SubM layers whose wgrad walks the gather table never read the pair lists
+            need_pairs = not (self.subm and ops.tc_mode(kvol, self.in_channels, self.out_channels) & 8)
             rb = ops.build_rulebook(input.indices, input.batch_size, input.spatial_shape,
                                     self.kernel_size, self.stride, self.padding, self.dilation,
-                                    self.output_padding, self.subm, self.transposed)
+                                    self.output_padding, self.subm, self.transposed, with_pairs=need_pairs)
             input.indice_dict[("__rulebook__", key)] = rb
             if self.indice_key is not None:  # the reference's 5-tuple, for code that reads it
-                input.indice_dict[self.indice_key] = (rb.outids, input.indices, rb.indice_pairs,
-                                                      rb.indice_pair_num, input.spatial_shape)
+                input.indice_dict[self.indice_key] = _IndiceTuple(rb, input.indices, input.spatial_shape)
         return rb
 
     def forward(self, input):

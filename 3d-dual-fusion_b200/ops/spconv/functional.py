@@ -75,14 +75,15 @@ class TableConvFunction(Function):
         filters = filters.contiguous()
         cin, cout = filters.shape[-2], filters.shape[-1]
         ctx.cin = cin
-        pad = ops.padded_cin(rulebook.indice_pairs.shape[0], cin, cout) - cin
+        kvol = rulebook.gather_table.shape[1] if rulebook.gather_table is not None else rulebook.indice_pairs.shape[0]
+        pad = ops.padded_cin(kvol, cin, cout) - cin
         if pad:
             # e.g. the 5-channel input layer: zero-pad the contraction to a multiple of 8 so the rows
             # are 16-byte aligned and the layer runs on the tensor-core kernels like all the others
             features = torch.nn.functional.pad(features, (0, pad))
             filters = torch.nn.functional.pad(filters, (0, 0, 0, pad))
             cin += pad
-        ctx.mode = mode = ops.tc_mode(rulebook.indice_pairs.shape[0], cin, cout)
+        ctx.mode = mode = ops.tc_mode(kvol, cin, cout)
         saved = features
         if mode & 5 and features.shape[0]:
             # tensor-core operands are made exact tf32 once; forward and wgrad share the copy. A forward

@@ -39,24 +39,43 @@ def _listify(v, ndim):
 
 
 class Rulebook(object):
-    """Reference-format rulebook + the row-major tables of the fused kernels."""
-    __slots__ = ("outids", "indice_pairs", "indice_pair_num", "gather_table", "scatter_table",
-                 "out_spatial_shape", "subm")
+    """Reference-format rulebook + the row-major tables of the fused kernels. For SubM layers whose
+    three conv kernels all walk the tables the pair lists are built only when somebody reads them."""
+    __slots__ = ("outids", "_pairs", "_num", "gather_table", "scatter_table", "out_spatial_shape", "subm",
+                 "kvol", "_build_pairs")
 
     def __init__(self, outids, indice_pairs, indice_pair_num, gather_table, scatter_table,
-                 out_spatial_shape):
+                 out_spatial_shape, kvol=None, build_pairs=None):
         self.outids = outids
-        self.indice_pairs = indice_pairs
-        self.indice_pair_num = indice_pair_num
+        self._pairs = indice_pairs
+        self._num = indice_pair_num
         self.gather_table = gather_table
         self.scatter_table = scatter_table
         self.out_spatial_shape = out_spatial_shape
         self.subm = False
+        self.kvol = kvol if kvol is not None else indice_pairs.shape[0]
+        self._build_pairs = build_pairs
+
+    def _ensure_pairs(self):
+        if self._pairs is None:
+            self._pairs, self._num = self._build_pairs()
+            self._build_pairs = None
+
+    @property
+    def indice_pairs(self):
+        self._ensure_pairs()
+        return self._pairs
+
+    @property
+    def indice_pair_num(self):
+        self._ensure_pairs()
+        return self._num
 
 
 def build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
-                   out_padding=0, subm=False, transpose=False, with_tables=True):
-    """Build a rulebook on the device. One host read (num_act_out) for regular convs, none for SubM."""
+                   out_padding=0, subm=False, transpose=False, with_tables=True, with_pairs=True):
+    """Build a rulebook on the device. One host read (num_act_out) for regular convs, none for SubM.
+    ``with_pairs=False`` (SubM with tables): the reference-format pair lists are built lazily."""
     _lib.require_cuda(indices)
     if indices.dtype != torch.int32 or not indices.is_contiguous():
         raise RuntimeError("indices must be a contiguous int32 [N, 4] tensor")
@@ -81,8 +100,9 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, paddin
     if ws_bytes < 0:
         raise RuntimeError("get_indice_pairs: bad geometry")
     ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
-    pairs = torch.empty((kvol, 2, n), dtype=torch.int32, device=dev)
-    num = torch.empty((kvol,), dtype=torch.int32, device=dev)
+    lazy = subm and with_tables and not with_pairs and n > 0
+    pairs = None if lazy else torch.empty((kvol, 2, n), dtype=torch.int32, device=dev)
+    num = None if lazy else torch.empty((kvol,), dtype=torch.int32, device=dev)
     scatter_t = torch.empty((n, kvol), dtype=torch.int32, device=dev) if with_tables else None
     stream = _lib.current_stream()
     with torch.cuda.device(dev):
@@ -92,7 +112,13 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, paddin
                                          _lib.ptr(pairs), _lib.ptr(num), _lib.ptr(gather_t),
                                          _lib.ptr(scatter_t), _lib.ptr(ws), int(ws_bytes), stream)
             _lib.check(rc, "subm_indice_pairs")
-            rb = Rulebook(indices, pairs, num, gather_t, scatter_t, out_shape)
+
+            def build_pairs():
+                full = build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation,
+                                      out_padding, True, False, with_tables=False)
+                return full.indice_pairs, full.indice_pair_num
+
+            rb = Rulebook(indices, pairs, num, gather_t, scatter_t, out_shape, kvol, build_pairs if lazy else None)
             rb.subm = True
             return rb
         cnt = torch.empty(1, dtype=torch.int32, device=dev)

@@ -123,6 +123,7 @@ int ddf_dynamic_voxelize(const float* points, int* coors, const float* voxel_siz
  * cells -> bitmap -> count, written to a DEVICE int), then — after the caller sized its outputs —
  * ddf_conv_indice_pairs.  Transposed (deconv) rulebooks are not generated (no 3D-DF backbone uses
  * them); SparseInverseConv reuses a saved rulebook with inverse=1 below.
+ * ddf_subm_indice_pairs: indice_pairs (and indice_num) may be NULL to build the tables only.
  */
 int64_t ddf_indice_pairs_workspace_bytes(int64_t num_in, int64_t batch_size,
                                          const int64_t* out_spatial_shape,
@@ -272,6 +273,29 @@ int ddf_sparse_bn_backward(const float* grad_y, const float* y, const float* x, 
                            const float* mean, const float* invstd, float* grad_x, float* grad_residual,
                            float* grad_weight, float* grad_bias, int64_t n, int64_t C, int training,
                            int relu, void* workspace, void* stream);
+
+/* ---- Fused elementwise kernels of the 3D-DF encoder layers ---------------------------------------
+ * Replace chains of PyTorch kernels in <proj>/models/model_utils/actr_transformer.py:383-397 (FFN:
+ * linear2(dropout(relu(linear1(x))))) and :385,391,406 (norm(src + dropout(src2))).  fp32, 16-byte
+ * aligned pointers.  Dropout is a counter-based hash of (seed, element index): p = drop probability
+ * (0 in eval mode), kept values are scaled by 1/(1-p), nothing is stored for backward.
+ *   ddf_bias_relu_dropout_forward : out[n, C] = dropout(relu(h + bias)); out may alias h; C % 4 == 0
+ *   ddf_bias_relu_dropout_backward: grad_h = grad_out * (out != 0) / (1 - p)
+ *   ddf_add_dropout_layer_norm_forward : s = a + dropout(b) (b may be NULL), y = LayerNorm(s) * gamma
+ *       + beta over the last dim C in {128, 256, 512}; s_out (optional), mean / rstd [rows] saved
+ *   ddf_add_dropout_layer_norm_backward: grad_a, grad_b (either may be NULL); grad_gamma / grad_beta [C]
+ *       are ACCUMULATED into (the caller zeroes them) */
+int ddf_bias_relu_dropout_forward(const float* h, const float* bias, float* out, int64_t n, int64_t C,
+                                  float p, uint64_t seed, void* stream);
+int ddf_bias_relu_dropout_backward(const float* grad_out, const float* out, float* grad_h, int64_t numel,
+                                   float p, void* stream);
+int ddf_add_dropout_layer_norm_forward(const float* a, const float* b, const float* gamma, const float* beta,
+                                       float* s_out, float* y, float* mean, float* rstd, int64_t rows,
+                                       int64_t C, float p, uint64_t seed, float eps, void* stream);
+int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, const float* gamma,
+                                        const float* mean, const float* rstd, float* grad_a, float* grad_b,
+                                        float* grad_gamma, float* grad_beta, int64_t rows, int64_t C,
+                                        float p, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -194,6 +194,16 @@ def _cpu_batch_norm_act(bn, x, residual=None, relu=False):
     return torch.relu(y) if relu else y
 
 
+def _cpu_ffn_hidden(linear, dropout, x):
+    """The reference's module chain (actr_transformer.py:383-384)."""
+    return dropout(F.relu(linear(x)))
+
+
+def _cpu_add_dropout_layer_norm(norm, dropout, a, b):
+    """norm(a + dropout(b)) (actr_transformer.py:385)."""
+    return norm(a + dropout(b))
+
+
 @contextlib.contextmanager
 def reference_cpu_ops():
     """Patch the product's op entry points with the reference CPU implementations (from outside)."""
@@ -205,8 +215,10 @@ def reference_cpu_ops():
     import ddf_b200.ops.pointops as m_po
     import ddf_b200.ops.voxel as m_voxel
     import ddf_b200.ops.sparse_norm as m_norm
+    import ddf_b200.ops.fused as m_fused
 
-    def build_rb(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, out_padding, subm, transposed):
+    def build_rb(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, out_padding, subm, transposed,
+                 **_unused):
         rb = cpu_build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, out_padding, subm)
         rb.subm = bool(subm)
         return rb
@@ -217,6 +229,8 @@ def reference_cpu_ops():
              (m_struct.SparseConvTensor, "dense", m_struct.SparseConvTensor.dense),
              (m_voxel, "voxelization", m_voxel.voxelization),
              (m_norm, "batch_norm_act", m_norm.batch_norm_act),
+             (m_fused, "ffn_hidden", m_fused.ffn_hidden),
+             (m_fused, "add_dropout_layer_norm", m_fused.add_dropout_layer_norm),
              (m_po, "furthest_point_sample", m_po.furthest_point_sample),
              (m_po, "ball_query", m_po.ball_query),
              (m_po, "grouping_operation", m_po.grouping_operation),
@@ -229,6 +243,8 @@ def reference_cpu_ops():
         m_struct.SparseConvTensor.dense = _cpu_dense
         m_voxel.voxelization = cpu_voxelization
         m_norm.batch_norm_act = _cpu_batch_norm_act
+        m_fused.ffn_hidden = _cpu_ffn_hidden
+        m_fused.add_dropout_layer_norm = _cpu_add_dropout_layer_norm
         m_po.furthest_point_sample = _cpu_fps
         m_po.ball_query = _cpu_ball_query
         m_po.grouping_operation = _CpuGroup.apply

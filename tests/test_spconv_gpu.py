@@ -166,8 +166,15 @@ def test_full_size_properties_nuscenes_grid():
         conv.weight.zero_()
         conv.weight[1, 1, 1] = torch.eye(16)
     y = conv(x)
-    # the C=16 layers run tf32 tensor-core inputs: identity weights return the tf32-rounded input
-    assert torch.equal(y.features, ops.round_tf32(x.features))
+    # the 16-channel layers run the fp32 warp-per-row kernel: identity weights return the input bit for bit
+    assert torch.equal(y.features, x.features)
+    x64 = sp.SparseConvTensor(torch.randn(n, 64, device="cuda"), idx, shape, 2)
+    conv64 = sp.SubMConv3d(64, 64, 3, bias=False).cuda()
+    with torch.no_grad():
+        conv64.weight.zero_()
+        conv64.weight[1, 1, 1] = torch.eye(64)
+    # tensor-core layers (tf32 inputs): identity weights return the tf32-rounded input
+    assert torch.equal(conv64(x64).features, ops.round_tf32(x64.features))
     ones = sp.SparseConvTensor(torch.ones(n, 1, device="cuda"), idx, shape, 2)
     c1 = sp.SubMConv3d(1, 1, 3, bias=False).cuda()
     with torch.no_grad():
