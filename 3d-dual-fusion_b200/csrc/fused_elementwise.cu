@@ -63,6 +63,40 @@ relu_dropout_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
   *reinterpret_cast<float4*>(gx + i * 4) = r;
 }
 
+// Same as relu_dropout_bwd_kernel plus the bias gradient (column sums of grad_h): a thread keeps its 4
+// columns and walks the rows grid-stride, so the [tokens, d_ffn] gradient is not read a second time by
+// a separate reduction.  Requires C / 4 <= 256 and 256 % (C / 4) == 0.
+__global__ void __launch_bounds__(kThreads)
+relu_dropout_bwd_bias_kernel(const float* __restrict__ gy, const float* __restrict__ out, float* __restrict__ gx,
+                             float* __restrict__ gbias, long long rows, int c4, float scale) {
+  const int col = threadIdx.x % c4, rl = threadIdx.x / c4, rpb = kThreads / c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+    const long long i = r * c4 + col;
+    const float4 g = ldg4(gy + i * 4), o = ldg4(out + i * 4);
+    float4 v;
+    v.x = o.x != 0.f ? g.x * scale : 0.f;
+    v.y = o.y != 0.f ? g.y * scale : 0.f;
+    v.z = o.z != 0.f ? g.z * scale : 0.f;
+    v.w = o.w != 0.f ? g.w * scale : 0.f;
+    *reinterpret_cast<float4*>(gx + i * 4) = v;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __shared__ float4 sh[kThreads];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < rpb; ++j) {
+      const float4 t = sh[j * c4 + col];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomicAdd(gbias + col * 4, acc.x);
+    atomicAdd(gbias + col * 4 + 1, acc.y);
+    atomicAdd(gbias + col * 4 + 2, acc.z);
+    atomicAdd(gbias + col * 4 + 3, acc.w);
+  }
+}
+
 // ---- s = a + dropout(b);  y = LayerNorm(s) * gamma + beta.  One warp per row, C = 32 * VPL * 4 ---------
 template <int VPL>   // float4 vectors per lane: C = 128 * VPL
 __global__ void __launch_bounds__(kThreads)
@@ -221,14 +255,25 @@ extern "C" int ddf_bias_relu_dropout_forward(const float* h, const float* bias, 
 }
 
 // grad_h = grad_out * (out != 0) / (1 - p): `out` is the forward result (no mask tensor is kept).
+// grad_bias [C] (optional) is ACCUMULATED into (the caller zeroes it): column sums of grad_h.
 extern "C" int ddf_bias_relu_dropout_backward(const float* grad_out, const float* out, float* grad_h,
-                                              int64_t numel, float p, void* stream_) {
-  DDF_CHECK_ARG(numel >= 0 && numel % 4 == 0 && p >= 0.f && p < 1.f, "bias_relu_dropout_backward: bad arguments");
-  if (numel == 0) return DDF_OK;
+                                              float* grad_bias, int64_t n, int64_t C, float p, void* stream_) {
+  DDF_CHECK_ARG(n >= 0 && C > 0 && C % 4 == 0 && p >= 0.f && p < 1.f, "bias_relu_dropout_backward: bad arguments");
+  if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_out && out && grad_h && aligned16(grad_out) && aligned16(out) && aligned16(grad_h),
                 "bias_relu_dropout_backward: null or misaligned pointer");
-  DDF_LAUNCH(relu_dropout_bwd_kernel, (unsigned)ddf::cdiv(numel / 4, kThreads), kThreads, 0, (cudaStream_t)stream_,
-             grad_out, out, grad_h, (long long)(numel / 4), 1.f / (1.f - p));
+  const int c4 = (int)(C / 4);
+  if (grad_bias && c4 <= kThreads && kThreads % c4 == 0) {
+    const int rpb = kThreads / c4;
+    long long grid = ddf::cdiv(n, rpb);
+    if (grid > 8 * ddf::kNumSM) grid = 8 * ddf::kNumSM;
+    DDF_LAUNCH(relu_dropout_bwd_bias_kernel, (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_out, out, grad_h,
+               grad_bias, (long long)n, c4, 1.f / (1.f - p));
+  } else {
+    DDF_CHECK_ARG(grad_bias == nullptr, "bias_relu_dropout_backward: grad_bias needs C/4 to divide 256");
+    DDF_LAUNCH(relu_dropout_bwd_kernel, (unsigned)ddf::cdiv(n * c4, kThreads), kThreads, 0, (cudaStream_t)stream_,
+               grad_out, out, grad_h, (long long)(n * c4), 1.f / (1.f - p));
+  }
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }

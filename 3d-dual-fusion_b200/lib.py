@@ -49,7 +49,7 @@ _SIGNATURES = {
     "ddf_sparse_bn_forward": [c_ptr] * 9 + [c_i64, c_i64, c_int, c_f32, c_f32, c_int, c_ptr, c_ptr],
     "ddf_sparse_bn_backward": [c_ptr] * 10 + [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr],
     "ddf_bias_relu_dropout_forward": [c_ptr] * 3 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_ptr],
-    "ddf_bias_relu_dropout_backward": [c_ptr] * 3 + [c_i64, c_f32, c_ptr],
+    "ddf_bias_relu_dropout_backward": [c_ptr] * 4 + [c_i64, c_i64, c_f32, c_ptr],
     "ddf_add_dropout_layer_norm_forward": [c_ptr] * 8 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_f32, c_ptr],
     "ddf_add_dropout_layer_norm_backward": [c_ptr] * 9 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_ptr],
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],

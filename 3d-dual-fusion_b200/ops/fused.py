@@ -43,11 +43,17 @@ class _BiasReluDropout(Function):
         (out,) = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         gh = torch.empty_like(out)
+        C = out.shape[-1]
+        want_gb = ctx.has_bias and ctx.needs_input_grad[1]
+        in_kernel = want_gb and (C // 4) <= 256 and 256 % (C // 4) == 0
+        gb = torch.zeros(C, dtype=torch.float32, device=out.device) if in_kernel else None
         with torch.cuda.device(out.device):
             rc = _lib.get_lib().ddf_bias_relu_dropout_backward(_lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(gh),
-                                                               out.numel(), ctx.p, _lib.current_stream())
+                                                               _lib.ptr(gb), out.numel() // C, C, ctx.p,
+                                                               _lib.current_stream())
         _lib.check(rc, "bias_relu_dropout_backward")
-        gb = gh.reshape(-1, gh.shape[-1]).sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        if want_gb and not in_kernel:
+            gb = gh.reshape(-1, C).sum(0)
         return gh, gb, None
 
 

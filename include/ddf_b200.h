@@ -280,15 +280,16 @@ int ddf_sparse_bn_backward(const float* grad_y, const float* y, const float* x, 
  * aligned pointers.  Dropout is a counter-based hash of (seed, element index): p = drop probability
  * (0 in eval mode), kept values are scaled by 1/(1-p), nothing is stored for backward.
  *   ddf_bias_relu_dropout_forward : out[n, C] = dropout(relu(h + bias)); out may alias h; C % 4 == 0
- *   ddf_bias_relu_dropout_backward: grad_h = grad_out * (out != 0) / (1 - p)
+ *   ddf_bias_relu_dropout_backward: grad_h = grad_out * (out != 0) / (1 - p); grad_bias [C] (optional, C/4
+ *       must divide 256) is ACCUMULATED into: column sums of grad_h in the same pass
  *   ddf_add_dropout_layer_norm_forward : s = a + dropout(b) (b may be NULL), y = LayerNorm(s) * gamma
  *       + beta over the last dim C in {128, 256, 512}; s_out (optional), mean / rstd [rows] saved
  *   ddf_add_dropout_layer_norm_backward: grad_a, grad_b (either may be NULL); grad_gamma / grad_beta [C]
  *       are ACCUMULATED into (the caller zeroes them) */
 int ddf_bias_relu_dropout_forward(const float* h, const float* bias, float* out, int64_t n, int64_t C,
                                   float p, uint64_t seed, void* stream);
-int ddf_bias_relu_dropout_backward(const float* grad_out, const float* out, float* grad_h, int64_t numel,
-                                   float p, void* stream);
+int ddf_bias_relu_dropout_backward(const float* grad_out, const float* out, float* grad_h, float* grad_bias,
+                                   int64_t n, int64_t C, float p, void* stream);
 int ddf_add_dropout_layer_norm_forward(const float* a, const float* b, const float* gamma, const float* beta,
                                        float* s_out, float* y, float* mean, float* rstd, int64_t rows,
                                        int64_t C, float p, uint64_t seed, float eps, void* stream);
