@@ -232,14 +232,20 @@ class KernelTimer(object):
         for mod, name, orig in self.saved:
             setattr(mod, name, orig)
 
-    def conv_summary(self, kind):
+    def conv_summary(self, kind, by_width=None):
         ms = flops = byts = 0.0
         for a, b, (how, t, n_src, n_dst, cin, cout) in self.records[kind]:
             pairs = int((t >= 0).sum().item()) if how == "table" else int(t.sum().item())
             kvol = t.shape[1] if how == "table" else t.shape[0]
-            ms += a.elapsed_time(b)
-            flops += 2.0 * pairs * cin * cout
+            dt, fl = a.elapsed_time(b), 2.0 * pairs * cin * cout
+            ms += dt
+            flops += fl
             byts += 4.0 * (n_src * cin + n_dst * cout + kvol * cin * cout) + 8.0 * pairs
+            if by_width is not None:
+                w = by_width.setdefault("%d->%d" % (cin, cout), [0, 0.0, 0.0])
+                w[0] += 1
+                w[1] += dt
+                w[2] += fl
         return len(self.records[kind]), ms, flops, byts
 
     def msda_summary(self, kind):
@@ -356,7 +362,8 @@ def run_ours(args):
     ct.install()
     step(d_pts, d_feats)
     torch.cuda.synchronize()
-    n_launch, conv_ms, conv_flops, conv_bytes = ct.conv_summary("conv")
+    by_width = {}
+    n_launch, conv_ms, conv_flops, conv_bytes = ct.conv_summary("conv", by_width)
     n_wg, wg_ms, wg_flops, _ = ct.conv_summary("wgrad")
     n_mf, mf_ms, mf_bytes = ct.msda_summary("msda_fwd")
     n_mb, mb_ms, mb_bytes = ct.msda_summary("msda_bwd")
@@ -372,6 +379,10 @@ def run_ours(args):
         h2d = sum(p.numel() * 4 for p in h_pts) + h_feats.numel() * 4
         tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        traffic = None   # per-launch DRAM bytes of the conv family from the committed ncu capture of this workload
+        tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -384,11 +395,14 @@ def run_ours(args):
             "roofline": {
                 "kernel": "sparse-conv implicit GEMM, tcgen05 (forward + dgrad launches of one step)",
                 "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": tf / peak_tf if peak_tf else None, "traffic": None,
+                "frac": tf / peak_tf if peak_tf else None, "traffic": traffic,
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); kernel computes in tf32/fp32" % how,
                 "launches_per_step": n_launch, "avg_launch_ms": conv_ms / max(n_launch, 1),
                 "share_of_step": conv_ms / (ms_dev / args.steps),
                 "algorithmic_GFLOP_per_step": conv_flops / 1e9, "algorithmic_MB_per_step": conv_bytes / 1e6,
+                # contraction->output width of the launch (dgrad swaps them): launches, ms, TFLOP/s
+                "by_layer_width": {k: {"launches": v[0], "ms": v[1], "TFLOPs": v[2] / (v[1] / 1e3) / 1e12 if v[1] else None}
+                                   for k, v in sorted(by_width.items())},
             },
             # the other kernel families of the step, same method (achieved = algorithmic work / event time)
             "kernels": {
