@@ -10,8 +10,9 @@ updates, voxels seen by no camera are not queries; reference points are integer 
 divided by (W_f, H_f); voxel positions are voxel CORNERS (index * size + range_min); queries are the
 ``x_conv4`` voxels.  What is new: the B x 6 Python loops over boolean masks become one vectorised
 pass (projection of all voxels to all cameras, one stable sort by (sample, camera)).
-The IFAT image gate / segmentation auxiliary (``ifat_cfg`` / ``seg_cfg``) are "next" rows of the
-scope table and raise NotImplementedError here.
+The IFAT image gate (``ifat_cfg``, fusion/ifat.py) gates the camera planes with the voxel features of
+the configured backbone scales before the encoder samples them; the 2-D segmentation auxiliary
+(``seg_cfg``) is outside the hot path and raises NotImplementedError.
 """
 import numpy as np
 import torch
@@ -186,8 +187,8 @@ class VoxelWithPointProjection(nn.Module):
                  double_flip=False, layer_channel=None, pfat_cfg=None, lt_cfg=None, ifat_cfg=None, seg_cfg=None,
                  model_name="ACTR"):
         super().__init__()
-        if ifat_cfg or seg_cfg:
-            raise NotImplementedError("IFAT / segmentation auxiliary are 'next' rows (SURVEY.md 8f-2)")
+        if seg_cfg:
+            raise NotImplementedError("the 2-D segmentation auxiliary head (seg_cfg) is outside the hot path")
         if interpolate:
             raise NotImplementedError("interpolate=True (full-resolution image features) is not configured by 3D-DF")
         self.voxel_size = voxel_size
@@ -204,7 +205,42 @@ class VoxelWithPointProjection(nn.Module):
         elif self.fuse_mode not in ("sum", "mean"):
             raise NotImplementedError("fuse_mode %r" % (fuse_mode,))
         self.ifat_cfg = None
+        if ifat_cfg:
+            from . import ifat
+            self.ifat_cfg = ifat_cfg
+            cfg = dict(ifat_cfg)
+            self.ifat = ifat.__all__[cfg.pop("fusion_method")](**cfg)
         self.seg_cfg = None
+
+    def _queries(self, sp_tensor, d_factor, batch_dict, cams, Hf, Wf):
+        """(camera, voxel) queries of one backbone scale in (sample, camera)-major, voxel-minor order:
+        group id, feature-map pixel (x, y), voxel row, reverse-augmented xyz."""
+        indices = sp_tensor.indices
+        n_cam = len(cams)
+        pts = self.point_projector.lidar_points(indices, d_factor, batch_dict)
+        grid, _, mask = self.point_projector(indices, pts, self.image_scale, batch_dict, self.image_list)
+        b_idx = indices[:, 0].long()
+        raw = torch.stack([batch_dict["image_shape"][c].to(grid.device)[b_idx] for c in cams]).float()
+        gf = grid.float()
+        gx = (gf[..., 0] * (Wf / raw[..., 1])).long()
+        gy = (gf[..., 1] * (Hf / raw[..., 0])).long()
+        cam_id, vox = mask.nonzero(as_tuple=True)
+        group = b_idx[vox] * n_cam + cam_id
+        order = torch.sort(group, stable=True)[1]
+        cam_id, vox, group = cam_id[order], vox[order], group[order]
+        return group, gx[cam_id, vox], gy[cam_id, vox], vox, pts
+
+    def _gate_image_features(self, img, encoded_voxel_list, d_factor_list, batch_dict, cams, batch_size):
+        """IFAT (voxel_with_point_projection.py:277-293): gate every camera plane with the voxel features
+        of the configured backbone scales before the 3D-DF encoder samples it."""
+        Hf, Wf = img.shape[-2:]
+        feats, cells, coords = {}, {}, {}
+        for s in self.ifat.voxel_idx:
+            group, qx, qy, vox, pts = self._queries(encoded_voxel_list[s], d_factor_list[s], batch_dict, cams, Hf, Wf)
+            feats[s] = encoded_voxel_list[s].features[vox]
+            cells[s] = (group * Hf + qy) * Wf + qx
+            coords[s] = pts[vox]
+        return self.ifat(img, feats, cells, coords)
 
     def forward(self, batch_dict, example, encoded_voxel_list=None, layer_name=None, img_conv_func=None,
                 fuse_mode=None, d_factor_list=None):
@@ -231,6 +267,9 @@ class VoxelWithPointProjection(nn.Module):
         gf = grid.float()
         gx = (gf[..., 0] * (Wf / raw[..., 1])).long()
         gy = (gf[..., 1] * (Hf / raw[..., 0])).long()
+
+        if self.ifat_cfg is not None and fuse_mode == "pfat":
+            img = self._gate_image_features(img, encoded_voxel_list, d_factor_list, batch_dict, cams, batch_size)
 
         cam_id, vox = mask.nonzero(as_tuple=True)            # every (camera, voxel) query
         group = b_idx[vox] * n_cam + cam_id

@@ -189,6 +189,53 @@ def test_centerpoint_pfatv2_path_matches_cpu_oracle_path():
     assert float((out.cpu() - ref).abs().max()) < 2e-3 * float(ref.abs().max())
 
 
+def test_centerpoint_hybrid_ifat_path_matches_cpu_oracle_path():
+    """BASELINE configs[1]: CenterPoint + 3D-DF, hybrid dual-query encoder with the IFAT image gate
+    (nusc_centerpoint_voxelnet_0075voxel_fix_bn_z_multimodal_pfat_hybrid7_ifat.py:86-108), fwd + bwd."""
+    from ddf_b200.fusion.centerpoint import SpMiddleResNetFHDFusion, VoxelWithPointProjection
+    from ddf_b200.ops.voxel import Voxelization
+    from oracle import cpu_path
+    depth_thres = {"CAM_FRONT": 1, "CAM_FRONT_LEFT": 0, "CAM_FRONT_RIGHT": 0, "CAM_BACK": 0.5, "CAM_BACK_LEFT": 0, "CAM_BACK_RIGHT": 0}
+    torch.manual_seed(0)
+    backbone = SpMiddleResNetFHDFusion(num_input_features=5)
+    fuse = VoxelWithPointProjection(
+        "pfat", False, synth.NUSC_VOXEL, synth.NUSC_RANGE, synth.CP_CAMS, image_scale=2.0 / 3, depth_thres=depth_thres,
+        pfat_cfg=dict(fusion_method="sum", feature_modal="hybrid",
+                      hybrid_cfg=dict(attn_layer="BiGateSum1D_2", q_method="sum", q_rep_place=["weight"]),
+                      num_channels=[256], query_num_feat=128, num_enc_layers=1, max_num_ne_voxel=26000,
+                      pos_encode_method="depth"),
+        ifat_cfg=dict(fusion_method="Basicgate_patch_iv_multivoxel", img_num_channel=256, pts_num_channel=128,
+                      voxel_feat_channel=[32, 64, 128], voxel_idx=[0, 2]))
+    assert sorted(k for k in fuse.state_dict() if k.startswith("ifat.")) == sorted(
+        "ifat." + k for k in ("reduced_dim.0.weight", "reduced_dim.0.bias", "reduced_dim.1.weight", "reduced_dim.1.bias",
+                              "reduced_dim2.weight", "reduced_dim2.bias", "reduced_dim3.weight", "reduced_dim3.bias",
+                              "spatial_basic.weight", "spatial_basic.bias"))
+    backbone.eval(), fuse.eval()
+    g_backbone, g_fuse = copy.deepcopy(backbone).cuda(), copy.deepcopy(fuse).cuda()
+    B = 2
+    vox = Voxelization(synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 120000).eval()
+    vs, cs = [], []
+    for b in range(B):
+        v, c, n = vox(torch.from_numpy(synth.lidar_points(12000, seed=90 + b)).cuda())
+        vs.append(v.sum(1) / n[:, None].float())
+        cs.append(torch.nn.functional.pad(c, (1, 0), value=b))
+    feats, coors = torch.cat(vs), torch.cat(cs)
+    bd = synth.centerpoint_batch(B, seed=4)
+    bd_gpu = {k: ({kk: ({k3: v3.cuda() for k3, v3 in vv.items()} if isinstance(vv, dict) else vv.cuda()) for kk, vv in v.items()}) for k, v in bd.items()}
+    out, _ = g_backbone(feats, bd_gpu, coors, B, [1440, 1440, 40], {}, fuse_func=g_fuse)
+    out.square().mean().backward()
+    with cpu_path.reference_cpu_ops():
+        ref, _ = backbone(feats.cpu(), bd, coors.cpu(), B, [1440, 1440, 40], {}, fuse_func=fuse)
+        ref.square().mean().backward()
+    assert out.shape == ref.shape == (B, 256, 180, 180)
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) < 2e-3 * float(ref.abs().max())
+    # the gate is live: its parameters receive gradients that agree with the CPU path
+    for name in ("ifat.spatial_basic.weight", "ifat.reduced_dim2.weight", "ifat.reduced_dim.0.weight"):
+        gd, gc = dict(g_fuse.named_parameters())[name].grad.cpu(), dict(fuse.named_parameters())[name].grad
+        assert float(gc.abs().max()) > 0
+        assert float((gd - gc).norm() / gc.norm()) < 5e-2, name
+
+
 def test_voxelrcnn_actrv2_hybrid_path_fwd_bwd():
     """BASELINE configs[3]: Voxel-RCNN + 3D-DF, KITTI-shaped synthetic input (1 camera, 16k points,
     0.05 m voxels), MVX + ACTRv2 hybrid; parity of the forward against the oracle CPU path."""
