@@ -47,7 +47,8 @@ constexpr int kMaxKvol = 27;
 constexpr int kProducerWarps = 8;
 constexpr int kGroups = 2;         // gather4 producer groups; group g fills A stages n with n % 2 == g
 constexpr int kThreads = (kProducerWarps + kMaxT + 1) * 32;   // + one MMA issuer warp per tile + B producer
-constexpr int kStagesA = 8;         // split into per-tile rings of 8 / T slots (see below)
+constexpr int kStagesA = 8;         // at most; split into per-tile rings of n_slots / T slots (see below)
+constexpr int kMaxStagesB = 4;
 constexpr int kABytes = TM * KCH * 4;  // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -163,7 +164,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
 template <int CO>
 struct Cfg {
   // deep enough that a filter slice is requested several TMA latencies (about 2.5 us) ahead of its use
-  static constexpr int kStagesB = CO >= 128 ? 2 : 4;
+  static constexpr int kStagesB = CO >= 128 ? 2 : 4;   // large configuration (1 CTA per SM)
   static constexpr int kBBytes = CO * KCH * 4;
   static constexpr int kCols = CO < 32 ? 32 : CO;     // TMEM columns per tile
   static constexpr int kIdxBytes = kMaxT * TM * kMaxKvol * 4;
@@ -177,19 +178,19 @@ template <int CO, bool GATHER4>
 __global__ void __launch_bounds__(kThreads)
 spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_constant__ CUtensorMap map_w,
                   const float* __restrict__ feat, const int* __restrict__ table, const float* __restrict__ bias, float* __restrict__ out,
-                  int n_out, int n_in, int kvol, int cin, int cout, int T) {
+                  int n_out, int n_in, int kvol, int cin, int cout, int T, int n_slots, int n_sb) {
   using C = Cfg<CO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
-  uint8_t* b_base = smem + kStagesA * kABytes;
-  int* s_idx = reinterpret_cast<int*>(b_base + C::kStagesB * C::kBBytes);   // [kvol][T*TM]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_idx) + C::kIdxBytes);
+  uint8_t* b_base = smem + n_slots * kABytes;
+  int* s_idx = reinterpret_cast<int*>(b_base + n_sb * C::kBBytes);   // [kvol][T*TM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_idx) + T * TM * kMaxKvol * 4);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kStagesA;
   uint64_t* b_full = a_empty + kStagesA;
-  uint64_t* b_empty = b_full + C::kStagesB;
-  uint64_t* accum_bar = b_empty + C::kStagesB;
+  uint64_t* b_empty = b_full + kMaxStagesB;
+  uint64_t* accum_bar = b_empty + kMaxStagesB;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum_bar + 1);
   uint32_t* s_mask = s_tmem + 1;   // [kMaxT]
 
@@ -212,7 +213,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
       mbar_init(a_full + s, GATHER4 ? kProducerWarps / kGroups : 64);
       mbar_init(a_empty + s, 1);
     }
-    for (int s = 0; s < C::kStagesB; ++s) {
+    for (int s = 0; s < n_sb; ++s) {
       mbar_init(b_full + s, 1);
       mbar_init(b_empty + s, T);   // every issuer releases every filter slice
     }
@@ -254,7 +255,8 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
     any |= tmask[t];
   }
   const int n_chunks = cin / KCH;
-  const int ring_shift = T == 1 ? 3 : T == 2 ? 2 : 1;   // A slots per tile ring: 8, 4, 2 (T = 3: 2)
+  // A slots per tile ring: n_slots / T rounded down to a power of two (8 slots: 8, 4, 2, 2 for T = 1..4)
+  const int ring_shift = (n_slots == 8 ? 3 : 2) - (T == 1 ? 0 : T == 2 ? 1 : 2);
   const int ring = 1 << ring_shift;
 
   if (warp < kProducerWarps) {
@@ -423,7 +425,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
             // is counted in the right phase)
             mbar_arrive_elect(b_empty + sb);
           }
-          if (++sb == C::kStagesB) { sb = 0; pb ^= 1u; }
+          if (++sb == n_sb) { sb = 0; pb ^= 1u; }
         }
       }
       umma_commit_elect(accum_bar);
@@ -440,7 +442,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
           mbar_wait(b_empty + sb, pb ^ 1u);
           mbar_expect_tx(b_full + sb, (uint32_t)(cout * KCH * 4));
           tma_tile_2d(smem_u32(b_base + sb * C::kBBytes), &map_w, b_full + sb, c * KCH, k * cout);
-          if (++sb == C::kStagesB) { sb = 0; pb ^= 1u; }
+          if (++sb == n_sb) { sb = 0; pb ^= 1u; }
         }
       }
     }
@@ -804,7 +806,7 @@ int launch_tma(const float* feat, const float* wt, const int* table, const float
   using C = Cfg<CO>;
   static bool configured = false;
   if (!configured) {
-    DDF_CUDA(cudaFuncSetAttribute(spconv_tma_kernel<CO, GATHER4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DDF_CUDA(cudaFuncSetAttribute((spconv_tma_kernel<CO, GATHER4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::kSmemBytes));
     configured = true;
   }
@@ -819,9 +821,18 @@ int launch_tma(const float* feat, const float* wt, const int* table, const float
   const int tmax = 512 / C::kCols < kMaxT ? 512 / C::kCols : kMaxT;
   if (T > tmax) T = tmax;
   if (T < 1) T = 1;
+  int n_slots = kStagesA, n_sb = C::kStagesB;
+  if (CO <= 64 && ntiles >= 4 * ddf::kNumSM) {
+    // narrow output, many tiles: two CTAs per SM (2 tiles, 4 A slots, 2 filter slices each) so that the
+    // table load and the epilogue of one CTA overlap the main loop of the other
+    T = 2;
+    n_slots = 4;
+    n_sb = 2;
+  }
+  const int smem = n_slots * kABytes + n_sb * C::kBBytes + T * TM * kMaxKvol * 4 + 512 + 1024;
   const unsigned grid = (unsigned)ddf::cdiv(ntiles, T);
-  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4>), grid, kThreads, C::kSmemBytes, stream, map_feat, map_w, feat, table,
-             bias, out, (int)n_out, (int)n_in, kvol, cin, cout, T);
+  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
+             bias, out, (int)n_out, (int)n_in, kvol, cin, cout, T, n_slots, n_sb);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
