@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads)
 subm_tables_kernel(const int* __restrict__ indices, int n, ConvGeom g,
                    const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
                    unsigned mask, int* __restrict__ scatter_t, int* __restrict__ gather_t,
-                   int* __restrict__ flags) {
+                   int* __restrict__ flags, int symmetric) {
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= (long long)n * g.kvol) return;
   const int j = (int)(t / g.kvol), k = (int)(t % g.kvol);
@@ -101,8 +101,11 @@ subm_tables_kernel(const int* __restrict__ indices, int n, ConvGeom g,
       r = hash_lookup(keys, vals, mask, (unsigned long long)flat_in(g, c.x, z, y, x));
     scatter_t[t] = r;
     flags[(long long)k * n + j] = r >= 0;
+    // centred kernel (2*pad == (ksize-1)*dilation in every dim): the voxel that row j scatters to through
+    // offset k is the one it gathers from through the mirrored offset, so one hash lookup serves both tables
+    if (gather_t && symmetric) gather_t[(long long)j * g.kvol + (g.kvol - 1 - k)] = r;
   }
-  if (gather_t) {
+  if (gather_t && !symmetric) {
     const int z = c.y - g.pad[0] + kz * g.dil[0], y = c.z - g.pad[1] + ky * g.dil[1],
               x = c.w - g.pad[2] + kx * g.dil[2];
     int r = -1;
@@ -349,8 +352,10 @@ extern "C" int ddf_subm_indice_pairs(const int* indices, int64_t num_in, int64_t
       indices, n, g, w.keys, w.vals, slots - 1);
   int* st = scatter_table ? scatter_table : w.scatter_t;
   const long long nk = (long long)n * g.kvol;
+  int symmetric = 1;
+  for (int d = 0; d < 3; ++d) symmetric &= (2 * g.pad[d] == (g.ksize[d] - 1) * g.dil[d]) ? 1 : 0;
   DDF_LAUNCH(subm_tables_kernel, (unsigned)ddf::cdiv(nk, kThreads), kThreads, 0, stream, 
-      indices, n, g, w.keys, w.vals, slots - 1, st, gather_table, w.flags);
+      indices, n, g, w.keys, w.vals, slots - 1, st, gather_table, w.flags, symmetric);
   DDF_LAUNCH_CHECK();
   if (!indice_pairs) return DDF_OK;
   return emit_pairs(w, st, n, g.kvol, indice_pairs, indice_num, stream);
