@@ -267,10 +267,12 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: everything native libraries write to file descriptor 1 meanwhile
+    # (NCCL prints its version banner there at NCCL_DEBUG=VERSION, which this image sets) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from ddf_b200 import lib
     L = lib.get_lib()
@@ -428,7 +430,10 @@ def run_ours(args):
             except Exception as e:  # the oracle is a checker; its absence must not fake a number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: %r" % (e,)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
