@@ -192,3 +192,37 @@ def test_full_size_properties_nuscenes_grid():
     lhs = down(x12).features
     rhs = z.features + 3 * down(x2).features
     assert (lhs - rhs).abs().max() < 1e-3 * rhs.abs().max()
+
+
+@pytest.mark.parametrize("n_side,chan", [(3, 64), (9, 128), (40, 32), (71, 128), (80, 128), (97, 64), (120, 32)])
+def test_tile_schedules_agree_across_kernels(n_side, chan):
+    """The multi-tile tcgen05 kernel picks tiles per CTA (1..4), ring depths and CTAs per SM from the row
+    count and width; the table-driven wgrad splits rows and offsets over CTAs. Row counts from 72 to
+    115k rows (not multiples of the 128-row tile / 32-row sub-tile) must all give what the single-tile
+    cp.async kernel and the pair-list wgrad give: the same tf32 products, so only the fp32 summation
+    order may differ (<= 1e-5 of the largest value; 1e-4 for wgrad, a sum over all rows)."""
+    from ddf_b200 import lib
+    from ddf_b200.ops.spconv import ops
+    zz, yy, xx = torch.meshgrid(torch.arange(8), torch.arange(n_side), torch.arange(n_side), indexing="ij")
+    keep = ((zz * 7 + yy * 3 + xx) % 5) != 0                       # holes: not every offset in every tile
+    idx = torch.stack([torch.zeros_like(zz), zz, yy, xx], -1)[keep].int().cuda().contiguous()
+    n = idx.shape[0]
+    g = torch.Generator().manual_seed(n_side)
+    rb = ops.build_rulebook(idx, 1, [8, n_side, n_side], 3, 1, 1, 1, 0, True, False)
+    feat = ops.round_tf32(torch.randn(n, chan, generator=g).cuda())
+    go = ops.round_tf32(torch.randn(n, chan, generator=g).cuda())
+    w = (torch.randn(3, 3, 3, chan, chan, generator=g) / (27 * chan) ** 0.5).cuda()
+    L = lib.get_lib()
+    prev = L.ddf_set_tensor_cores(1)
+    try:
+        out = ops.sparse_conv_forward(feat, w, rb.gather_table, None, n)
+        gin = ops.sparse_conv_dgrad(w, go, rb.scatter_table, n)
+        gw = ops.sparse_conv_wgrad_table(feat, w, go, rb.gather_table)
+        L.ddf_set_tensor_cores(2)                                   # single-tile kernel, pair-list wgrad
+        out_ref = ops.sparse_conv_forward(feat, w, rb.gather_table, None, n)
+        gin_ref = ops.sparse_conv_dgrad(w, go, rb.scatter_table, n)
+        gw_ref = ops.sparse_conv_wgrad(feat, w, go, rb.indice_pairs, rb.indice_pair_num)
+    finally:
+        L.ddf_set_tensor_cores(prev)
+    for a, b, tol in ((out, out_ref, 1e-5), (gin, gin_ref, 1e-5), (gw, gw_ref, 1e-4)):
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max())
