@@ -46,6 +46,19 @@ void note_launches(int n);
     ddf::note_launches(1);                                 \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per DEVICE for a kernel (the attribute belongs to
+// the device's instance of the function; a process may drive several devices)
+#define DDF_SET_SMEM_ONCE(kernel, bytes)                                                                 \
+  do {                                                                                                   \
+    static bool done__[64] = {};                                                                         \
+    int dev__ = 0;                                                                                       \
+    DDF_CUDA(cudaGetDevice(&dev__));                                                                     \
+    if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                    \
+      DDF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                                \
+    }                                                                                                    \
+  } while (0)
+
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

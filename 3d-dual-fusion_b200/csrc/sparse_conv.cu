@@ -319,11 +319,7 @@ template <int CI, int CO>
 int launch_sparse_rows(const float* feat, const float* filt, const int* table, const float* bias, float* out,
                        int64_t n_out, int kvol, cudaStream_t stream) {
   const int smem = kvol * CI * CO * 4;
-  static bool configured = false;
-  if (!configured) {
-    DDF_CUDA(cudaFuncSetAttribute((spconv_sparse_rows_kernel<CI, CO>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  DDF_SET_SMEM_ONCE((spconv_sparse_rows_kernel<CI, CO>), 32 * CI * CO * 4);   // kvol <= 32
   long long grid = ddf::cdiv(n_out * 32, kThreads);
   const long long cap = (long long)ddf::kNumSM * (smem > 48 * 1024 ? 3 : 6);   // persistent: the filter bank is staged once per CTA
   if (grid > cap) grid = cap;

@@ -285,12 +285,7 @@ template <int CO>
 int launch_tc(const float* feat, const float* wt, const int* table, const float* bias, float* out,
               int64_t n_out, int kvol, int cin, int cout, cudaStream_t stream) {
   using Cfg = TcCfg<CO>;
-  static bool configured = false;
-  if (!configured) {
-    DDF_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    configured = true;
-  }
+  DDF_SET_SMEM_ONCE(spconv_tc_kernel<CO>, Cfg::kSmemBytes);
   const unsigned grid = (unsigned)ddf::cdiv(n_out, TM);
   DDF_LAUNCH(spconv_tc_kernel<CO>, grid, kThreadsTC, Cfg::kSmemBytes, stream, feat, wt, table, bias,
              out, (int)n_out, kvol, cin, cout);
@@ -514,12 +509,7 @@ template <int CO>
 int launch_wgrad_tc(const float* feat, const float* gout, const int* pairs, const int* num,
                     int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
                     cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    DDF_CUDA(cudaFuncSetAttribute(spconv_wgrad_tc_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kWgSmemBytes));
-    configured = true;
-  }
+  DDF_SET_SMEM_ONCE(spconv_wgrad_tc_kernel<CO>, kWgSmemBytes);
   // persistent grid: 2 CTAs per SM (100 KB of smem each), fewer when the lists are short
   long long grid = 2 * ddf::kNumSM;
   const long long max_useful = ddf::cdiv((long long)pair_stride * kvol, 256);

@@ -755,7 +755,7 @@ int launch_wgrad_table(const float* feat, const float* gout, const int* table, f
   constexpr int SR = CO == 32 ? 128 : 32;
   constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
   const int smem = kWgSlotsA * SR * cin * 4 + kWgSlotsB * SR * CO * 4 + kWgSlotsB * kTblBytes + 2048 + 512 + 1024;
-  DDF_CUDA(cudaFuncSetAttribute((spconv_wgrad_table_kernel<CO, SR>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  DDF_SET_SMEM_ONCE((spconv_wgrad_table_kernel<CO, SR>), smem);
   // two CTAs per SM when the rings are small; they then share the 512 TMEM columns
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   int KG = (512 / per_sm) / CO;
@@ -804,12 +804,7 @@ template <int CO, bool GATHER4>
 int launch_tma(const float* feat, const float* wt, const int* table, const float* bias, float* out,
                int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
   using C = Cfg<CO>;
-  static bool configured = false;
-  if (!configured) {
-    DDF_CUDA(cudaFuncSetAttribute((spconv_tma_kernel<CO, GATHER4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmemBytes));
-    configured = true;
-  }
+  DDF_SET_SMEM_ONCE((spconv_tma_kernel<CO, GATHER4>), C::kSmemBytes);
   CUtensorMap map_feat, map_w;
   if (!make_map(&map_feat, feat, n_in, cin, 1) || !make_map(&map_w, wt, (int64_t)kvol * cout, cin, cout)) {
     ddf::set_error("sparse conv: cuTensorMapEncodeTiled failed (n_in=%lld cin=%d cout=%d)", (long long)n_in, cin, cout);
