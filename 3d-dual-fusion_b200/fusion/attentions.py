@@ -21,25 +21,33 @@ class _BiGateBase(nn.Module):
 
 
 class BiGate1D(_BiGateBase):
+    """s1 = sigmoid(b(f1)), s2 = sigmoid(a(f2)); each stream is scaled by the OTHER stream's gate
+    (attentions.py:44-49)."""
+
     def forward(self, feat1, feat2):
         s1 = self._gate(self.b_conv1d, feat1)
         s2 = self._gate(self.a_conv1d, feat2)
-        return feat1 * s1, feat2 * s2
+        return feat1 * s2, feat2 * s1
 
 
 class BiGate1D_2(_BiGateBase):
-    def forward(self, feat1, feat2):
-        s1 = self._gate(self.b_conv1d, feat1)
-        s2 = self._gate(self.a_conv1d, feat2)
-        return feat1 + feat2 * s1, feat2 + feat1 * s2
+    """Gates from the summed streams, each stream scaled by its own gate (attentions.py:66-72)."""
 
-
-class BiGateSum1D(_BiGateBase):
     def forward(self, feat1, feat2):
         fuse = feat1 + feat2
         s1 = self._gate(self.b_conv1d, fuse)
         s2 = self._gate(self.a_conv1d, fuse)
         return feat1 * s1, feat2 * s2
+
+
+class BiGateSum1D(_BiGateBase):
+    """Per-stream gates, residual mix: out1 = f1 + f2 * sigmoid(b(f1)); out2 = f2 + f1 * sigmoid(a(f2))
+    (attentions.py:89-94)."""
+
+    def forward(self, feat1, feat2):
+        s1 = self._gate(self.b_conv1d, feat1)
+        s2 = self._gate(self.a_conv1d, feat2)
+        return feat1 + feat2 * s1, feat2 + feat1 * s2
 
 
 class BiGateSum1D_2(_BiGateBase):

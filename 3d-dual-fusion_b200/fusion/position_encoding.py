@@ -75,13 +75,17 @@ class PositionEmbeddingSineSparseDepth(PositionEmbeddingSine):
 
 
 class PositionEmbeddingLearnedDepth(nn.Module):
-    """Learned embedding over integer depth bins (position_encoding.py:122-140)."""
+    """Learned embedding over depth bins (position_encoding.py:122-140): bin = trunc(depth / 60 * num_bin),
+    parameter ``d_embed.weight [num_bin, F]``. The reference's ACTR calls it with one argument although the
+    class takes ``(feat, depth)`` and so raises (actr.py:161-163); ``feat`` is unused, hence optional here.
+    Depths >= 60 m index past the table in the reference (IndexError); they are clamped to the last bin."""
 
-    def __init__(self, num_pos_feats=256, num_bins=80):
+    def __init__(self, num_pos_feats=256, num_bin=120):
         super().__init__()
-        self.depth_embed = nn.Embedding(num_bins, num_pos_feats)
-        nn.init.uniform_(self.depth_embed.weight)
+        self.d_embed = nn.Embedding(num_bin, num_pos_feats)
+        self.num_bin = num_bin
+        nn.init.uniform_(self.d_embed.weight)
 
-    def forward(self, depth):
-        idx = depth.long().clamp_(0, self.depth_embed.num_embeddings - 1)
-        return self.depth_embed(idx).permute(0, 2, 1)
+    def forward(self, depth, feat=None):
+        idx = (depth / 60. * self.num_bin).to(torch.long).clamp_(0, self.num_bin - 1)
+        return self.d_embed(idx).permute(0, 2, 1)
