@@ -13,6 +13,7 @@
 //   wgrad   : gW[k]     = sum_{(i,o) in pairs[k]} in[i,:]^T gout[o,:]   (walks the pair lists)
 // The SubM centre tap needs no special case here (the reference treats arg-max offset as identity,
 // spconv_ops.h:271-303): its gather-table column is simply the identity.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,12 +26,12 @@ int spconv_tc_launch(const float* feat, const float* wt, const int* table, const
 // TMA-staged tcgen05 path (sparse_conv_tma.cu)
 bool spconv_tma_supported(int kvol, int cin, int cout);
 int spconv_tma_launch(const float* feat, const float* wt, const int* table, const float* bias, float* out,
-                      int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4,
+                      int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4, bool split,
                       cudaStream_t stream);
 bool spconv_wgrad_table_supported(int kvol, int cin, int cout);
 int spconv_wgrad_table_launch(const float* feat, const float* gout, const int* table, float* gw,
                               int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream);
-bool spconv_wgrad_tc_supported(int cin, int cout);
+bool spconv_wgrad_tc_supported(int kvol, int cin, int cout);
 int spconv_wgrad_tc_launch(const float* feat, const float* gout, const int* pairs, const int* num,
                            int64_t pair_stride, float* gw, int kvol, int cin, int cout, int inverse,
                            cudaStream_t stream);
@@ -43,18 +44,24 @@ namespace {
 // multi-tile kernel (filter slices by tiled TMA and shared by up to 4 row tiles, rows gathered by
 // cp.async from 16 warps) where the layer shape allows, else the single-tile cp.async kernel.
 // 2: tcgen05 tf32, single-tile cp.async kernel only. 3: as 1 with the rows gathered by TMA gather4.
+// 4 (default): as 1, but forward and dgrad of the layers the multi-tile kernel takes run "bf16x3": both operands
+// split into bf16 hi + lo halves, three MMAs per product pair (hi.hi + hi.lo + lo.hi), i.e. a 16-bit significand
+// per product instead of tf32's 11 bits - this is what keeps the whole 21-conv path inside 1e-3 of the fp32
+// reference (single-pass tf32 accumulates to about 1.8e-3 through the batch-statistics BatchNorms). wgrad stays tf32.
 int g_tc_state = -1;  // -1: not read yet
 int tc_mode_state() {
   if (g_tc_state < 0) {
     const char* e = getenv("DDF_DISABLE_TC");
-    g_tc_state = (e && e[0] == '1') ? 0 : 1;
+    const char* m = getenv("DDF_TC_MODE");
+    g_tc_state = (e && e[0] == '1') ? 0 : (m && m[0] >= '0' && m[0] <= '4') ? m[0] - '0' : 4;
   }
   return g_tc_state;
 }
 bool tc_enabled() { return tc_mode_state() != 0; }
 // the warp-per-row fp32 kernel for narrow, low-density layers (every mode except 2, the A/B baseline)
 bool sparse_rows_enabled() { return tc_mode_state() != 2; }
-bool tma_enabled() { return tc_mode_state() == 1 || tc_mode_state() == 3; }
+bool tma_enabled() { return tc_mode_state() == 1 || tc_mode_state() >= 3; }
+bool bf16x3_enabled() { return tc_mode_state() == 4; }
 bool gather4_enabled() { return tc_mode_state() == 3; }
 
 
@@ -259,6 +266,63 @@ round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long l
     for (long long i = n4 * 4; i < n; ++i) dst[i] = tf32_rn(src[i]);
 }
 
+// ---- bf16x3 operand layout -------------------------------------------------------------------------------------
+// A row of C fp32 channels (C % 32 == 0) becomes C/32 blocks of 128 bytes: [32 x bf16 hi | 32 x bf16 lo] with
+// hi = bf16_rn(x), lo = bf16_rn(x - hi): x = hi + lo up to 2^-17 |x|.  Same bytes per row as fp32.
+__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+
+// src fp32 [rows, cols] -> split (block layout above) and, when rounded != nullptr, the tf32-rounded copy the
+// wgrad kernels read.  One thread = 8 consecutive channels.
+__global__ void __launch_bounds__(kThreads)
+split_bf16x3_kernel(const float* __restrict__ src, uint8_t* __restrict__ split, float* __restrict__ rounded,
+                    long long n8, int cols) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n8) return;
+  const long long e = t * 8;
+  const long long row = e / cols;
+  const int col = (int)(e % cols);
+  float v[8];
+  *reinterpret_cast<float4*>(v) = reinterpret_cast<const float4*>(src)[t * 2];
+  *reinterpret_cast<float4*>(v + 4) = reinterpret_cast<const float4*>(src)[t * 2 + 1];
+  unsigned short hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16(v[i], hi[i], lo[i]);
+  uint8_t* dst = split + row * cols * 4 + (col >> 5) * 128 + (col & 31) * 2;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(dst + 64) = *reinterpret_cast<const uint4*>(lo);
+  if (rounded) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tf32_rn(v[i]);
+    reinterpret_cast<float4*>(rounded)[t * 2] = *reinterpret_cast<float4*>(v);
+    reinterpret_cast<float4*>(rounded)[t * 2 + 1] = *reinterpret_cast<float4*>(v + 4);
+  }
+}
+
+// filters [K, Cin, Cout] -> B operand of the bf16x3 kernel: rows (k, n), contraction c in split blocks.
+// transpose = true (forward): n over Cout, c over Cin; false (dgrad): n over Cin, c over Cout.
+__global__ void __launch_bounds__(kThreads)
+split_filters_kernel(const float* __restrict__ w, uint8_t* __restrict__ ws, int kvol, int cin, int cout,
+                     bool transpose) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long per = (long long)cin * cout;
+  if (t >= per * kvol) return;
+  const int k = (int)(t / per);
+  const int r = (int)(t % per);
+  const int nc = transpose ? cin : cout;         // contraction length
+  const int n = r / nc, c = r % nc;
+  const float v = transpose ? w[(long long)k * per + (long long)c * cout + n] : w[(long long)k * per + r];
+  unsigned short hi, lo;
+  split_bf16(v, hi, lo);
+  uint8_t* dst = ws + ((long long)k * per + (long long)n * nc) * 4 + (c >> 5) * 128 + (c & 31) * 2;
+  *reinterpret_cast<unsigned short*>(dst) = hi;
+  *reinterpret_cast<unsigned short*>(dst + 64) = lo;
+}
+
 // pair lists -> row-major table: table[row_of(col_sel)][k] = row_of(1-col_sel)
 __global__ void __launch_bounds__(kThreads)
 pairs_to_table_kernel(const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
@@ -375,11 +439,22 @@ int launch_gather_gemm(const float* feat, const float* filt, const int* table, c
 extern "C" int ddf_sparse_conv_forward(const float* features, const float* filters,
                                        const int* gather_table, const float* bias, float* out,
                                        float* filters_t_ws, int64_t n_out, int64_t n_in, int64_t kvol,
-                                       int64_t cin, int64_t cout, void* stream_) {
+                                       int64_t cin, int64_t cout, int operand_format, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DDF_CHECK_ARG(n_out >= 0 && n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_forward: bad sizes");
   if (n_out == 0) return DDF_OK;
   DDF_CHECK_ARG(features && filters && gather_table && out, "sparse_conv_forward: null pointer");
+  if (operand_format == 1) {
+    // features are already in the bf16 hi/lo block layout (ddf_split_bf16x3)
+    DDF_CHECK_ARG(filters_t_ws && ddf::spconv_tma_supported((int)kvol, (int)cin, (int)cout),
+                  "sparse_conv_forward: split operands need the multi-tile kernel (K=%lld Cin=%lld Cout=%lld)",
+                  (long long)kvol, (long long)cin, (long long)cout);
+    const long long nw = kvol * cin * cout;
+    DDF_LAUNCH(split_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, filters,
+               reinterpret_cast<uint8_t*>(filters_t_ws), (int)kvol, (int)cin, (int)cout, true);
+    return ddf::spconv_tma_launch(features, filters_t_ws, gather_table, bias, out, n_out, n_in, (int)kvol,
+                                  (int)cin, (int)cout, false, true, stream);
+  }
   if (sparse_rows_enabled() && sparse_rows_supported(kvol, cin, cout))
     return sparse_rows_dispatch(features, filters, gather_table, bias, out, n_out, (int)kvol, (int)cin, (int)cout, stream);
   if (filters_t_ws && tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) {
@@ -389,7 +464,7 @@ extern "C" int ddf_sparse_conv_forward(const float* features, const float* filte
                filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, true);
     if (tma_enabled() && ddf::spconv_tma_supported((int)kvol, (int)cin, (int)cout))
       return ddf::spconv_tma_launch(features, filters_t_ws, gather_table, bias, out, n_out, n_in, (int)kvol,
-                                    (int)cin, (int)cout, gather4_enabled(), stream);
+                                    (int)cin, (int)cout, gather4_enabled(), false, stream);
     return ddf::spconv_tc_launch(features, filters_t_ws, gather_table, bias, out, n_out, (int)kvol,
                                  (int)cin, (int)cout, stream);
   }
@@ -402,7 +477,7 @@ extern "C" int ddf_sparse_conv_forward(const float* features, const float* filte
 extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters,
                                      const int* scatter_table, float* grad_in, float* filters_t_ws,
                                      int64_t n_in, int64_t n_out, int64_t kvol, int64_t cin, int64_t cout,
-                                     void* stream_) {
+                                     int operand_format, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DDF_CHECK_ARG(n_in >= 0 && n_out >= -1 && kvol > 0 && cin > 0 && cout > 0, "sparse_conv_dgrad: bad sizes");
   if (n_in == 0) return DDF_OK;
@@ -410,6 +485,15 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
                 "sparse_conv_dgrad: null pointer");
   // dgrad contracts over Cout; filters [K, cin, cout] are already the K-major B operand [N=cin, K=cout]
   const long long nw = kvol * cin * cout;
+  if (operand_format == 1) {
+    DDF_CHECK_ARG(n_out >= 0 && ddf::spconv_tma_supported((int)kvol, (int)cout, (int)cin),
+                  "sparse_conv_dgrad: split operands need the multi-tile kernel (K=%lld Cin=%lld Cout=%lld)",
+                  (long long)kvol, (long long)cin, (long long)cout);
+    DDF_LAUNCH(split_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, filters,
+               reinterpret_cast<uint8_t*>(filters_t_ws), (int)kvol, (int)cin, (int)cout, false);
+    return ddf::spconv_tma_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, n_out, (int)kvol,
+                                  (int)cout, (int)cin, false, true, stream);
+  }
   if (sparse_rows_enabled() && sparse_rows_supported(kvol, cout, cin)) {
     DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
                filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, false);
@@ -421,7 +505,7 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
                filters_t_ws, nw / 4, nw);
     if (n_out >= 0 && tma_enabled() && ddf::spconv_tma_supported((int)kvol, (int)cout, (int)cin))
       return ddf::spconv_tma_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, n_out,
-                                    (int)kvol, (int)cout, (int)cin, gather4_enabled(), stream);
+                                    (int)kvol, (int)cout, (int)cin, gather4_enabled(), false, stream);
     return ddf::spconv_tc_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, (int)kvol,
                                  (int)cout, (int)cin, stream);
   }
@@ -433,17 +517,17 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
 }
 
 // grad_filters [K, cin, cout] (zeroed inside) from the reference-format pair lists.
-extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_out,
-                                     const int* indice_pairs, const int* indice_num,
-                                     int64_t pair_stride, float* grad_filters, int64_t kvol,
-                                     int64_t cin, int64_t cout, int inverse, void* stream_) {
+static int sparse_conv_wgrad_impl(const float* features, const float* grad_out,
+                                  const int* indice_pairs, const int* indice_num,
+                                  int64_t pair_stride, float* grad_filters, int64_t kvol,
+                                  int64_t cin, int64_t cout, int inverse, bool allow_tc, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DDF_CHECK_ARG(kvol > 0 && cin > 0 && cout > 0 && pair_stride >= 0, "sparse_conv_wgrad: bad sizes");
   DDF_CHECK_ARG(grad_filters != nullptr, "sparse_conv_wgrad: null grad_filters");
   DDF_CUDA(cudaMemsetAsync(grad_filters, 0, sizeof(float) * (size_t)(kvol * cin * cout), stream));
   if (pair_stride == 0) return DDF_OK;
   DDF_CHECK_ARG(features && grad_out && indice_pairs && indice_num, "sparse_conv_wgrad: null pointer");
-  if (tc_enabled() && ddf::spconv_wgrad_tc_supported((int)cin, (int)cout))
+  if (allow_tc && tc_enabled() && ddf::spconv_wgrad_tc_supported((int)kvol, (int)cin, (int)cout))
     return ddf::spconv_wgrad_tc_launch(features, grad_out, indice_pairs, indice_num, pair_stride,
                                        grad_filters, (int)kvol, (int)cin, (int)cout, inverse, stream);
   // enough (k, slice) CTAs for ~4 waves; slices bounded so each still has >= ~256 pairs
@@ -462,10 +546,18 @@ extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_ou
   return DDF_OK;
 }
 
+extern "C" int ddf_sparse_conv_wgrad(const float* features, const float* grad_out,
+                                     const int* indice_pairs, const int* indice_num,
+                                     int64_t pair_stride, float* grad_filters, int64_t kvol,
+                                     int64_t cin, int64_t cout, int inverse, void* stream_) {
+  return sparse_conv_wgrad_impl(features, grad_out, indice_pairs, indice_num, pair_stride, grad_filters, kvol, cin,
+                                cout, inverse, true, stream_);
+}
+
 // Runtime switch of the tensor-core conv kernels; returns the previous setting.
 extern "C" int ddf_set_tensor_cores(int on) {
   const int prev = tc_mode_state();
-  g_tc_state = on < 0 ? 0 : (on > 3 ? 3 : on);
+  g_tc_state = on < 0 ? 0 : (on > 4 ? 4 : on);
   return prev;
 }
 
@@ -490,7 +582,8 @@ extern "C" int ddf_sparse_conv_wgrad_table(const float* features, const float* g
 }
 
 // Which of the three conv kernels of a (kvol, cin, cout) layer run on the tensor cores:
-// bit 0 forward, bit 1 dgrad, bit 2 wgrad.  Callers use it to decide which operands to pre-round.
+// bit 0 forward, bit 1 dgrad, bit 2 wgrad (pair lists), bit 3 wgrad (table); bit 4 / bit 5: forward / dgrad take
+// their operands in the bf16 hi/lo block layout (operand_format 1).  Callers use it to prepare operands.
 extern "C" int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout) {
   if (!tc_enabled()) return 0;
   int m = 0;
@@ -498,8 +591,12 @@ extern "C" int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout) 
   const bool rows_d = sparse_rows_enabled() && sparse_rows_supported(kvol, cout, cin);
   if (!rows_f && ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) m |= 1;
   if (!rows_d && ddf::spconv_tc_supported((int)kvol, (int)cout, (int)cin)) m |= 2;
-  if (ddf::spconv_wgrad_tc_supported((int)cin, (int)cout)) m |= 4;
+  if (ddf::spconv_wgrad_tc_supported((int)kvol, (int)cin, (int)cout)) m |= 4;
   if (tc_mode_state() != 2 && ddf::spconv_wgrad_table_supported((int)kvol, (int)cin, (int)cout)) m |= 8;
+  if (bf16x3_enabled()) {
+    if ((m & 1) && ddf::spconv_tma_supported((int)kvol, (int)cin, (int)cout)) m |= 16;
+    if ((m & 2) && ddf::spconv_tma_supported((int)kvol, (int)cout, (int)cin)) m |= 32;
+  }
   return m;
 }
 
@@ -510,6 +607,20 @@ extern "C" int ddf_round_tf32(const float* src, float* dst, int64_t n, void* str
   DDF_CHECK_ARG(src && dst, "round_tf32: null pointer");
   DDF_LAUNCH(round_tf32_kernel, (unsigned)ddf::cdiv(n / 4 + 1, kThreads), kThreads, 0,
              (cudaStream_t)stream_, src, dst, n / 4, n);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// src fp32 [rows, cols] (cols % 32 == 0) -> split: the bf16 hi/lo block layout of the bf16x3 kernels (rows*cols*4
+// bytes); rounded (optional, may be NULL): the tf32-rounded copy for the wgrad kernels.
+extern "C" int ddf_split_bf16x3(const float* src, void* split, float* rounded, int64_t rows, int64_t cols,
+                                void* stream_) {
+  DDF_CHECK_ARG(rows >= 0 && cols > 0 && cols % 32 == 0, "split_bf16x3: cols must be a multiple of 32");
+  if (rows == 0) return DDF_OK;
+  DDF_CHECK_ARG(src && split, "split_bf16x3: null pointer");
+  const long long n8 = rows * cols / 8;
+  DDF_LAUNCH(split_bf16x3_kernel, (unsigned)ddf::cdiv(n8, kThreads), kThreads, 0, (cudaStream_t)stream_, src,
+             reinterpret_cast<uint8_t*>(split), rounded, n8, (int)cols);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
@@ -547,8 +658,10 @@ extern "C" int ddf_indice_conv_backward(const float* features, const float* filt
   (void)subm;
   cudaStream_t stream = (cudaStream_t)stream_;
   DDF_CHECK_ARG(n_in >= 0 && kvol > 0 && cin > 0 && cout > 0, "indice_conv_backward: bad sizes");
-  int rc = ddf_sparse_conv_wgrad(features, grad_out, indice_pairs, indice_num, pair_stride,
-                                 grad_filters, kvol, cin, cout, inverse, stream_);
+  // the reference-ABI entry points are the indice_conv*_fp32 contract: fp32 SIMT kernels in forward AND
+  // backward (the tensor-core kernels, which need prepared operands, are reached through ddf_sparse_conv_*)
+  int rc = sparse_conv_wgrad_impl(features, grad_out, indice_pairs, indice_num, pair_stride,
+                                  grad_filters, kvol, cin, cout, inverse, false, stream_);
   if (rc || n_in == 0) return rc;
   DDF_CHECK_ARG(grad_in && table_ws && filters_t_ws, "indice_conv_backward: null pointer");
   DDF_CUDA(cudaMemsetAsync(table_ws, 0xff, sizeof(int) * (size_t)(n_in * kvol), stream));
@@ -556,9 +669,11 @@ extern "C" int ddf_indice_conv_backward(const float* features, const float* filt
   if (np > 0)
     DDF_LAUNCH(pairs_to_table_kernel, (unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream, 
         indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 1 : 0, table_ws);
-  // this signature does not carry the row count of grad_out: n_out = -1 keeps dgrad off the TMA kernel
-  return ddf_sparse_conv_dgrad(grad_out, filters, table_ws, grad_in, filters_t_ws, n_in, -1, kvol, cin,
-                               cout, stream_);
+  const long long nw = kvol * cin * cout;
+  DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+             filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, false);
+  return launch_gather_gemm(grad_out, filters_t_ws, table_ws, nullptr, grad_in, n_in, (int)kvol, (int)cout,
+                            (int)cin, stream);
 }
 
 // ---- dense(): sparse [N, C] + indices [N, 4] -> dense NCDHW ------------------------------------

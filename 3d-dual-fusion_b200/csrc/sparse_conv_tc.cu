@@ -540,8 +540,9 @@ int spconv_tc_launch(const float* feat, const float* wt, const int* table, const
 }
 
 
-bool spconv_wgrad_tc_supported(int cin, int cout) {
-  return cin % 4 == 0 && cout % 16 == 0 && cin >= 4 && cin <= 128 && cout >= 16 && cout <= 128;  // kvol <= 100
+// kvol: the kernel keeps s_first[kvol + 1] in about 450 bytes of shared memory behind its barriers
+bool spconv_wgrad_tc_supported(int kvol, int cin, int cout) {
+  return kvol <= 100 && cin % 4 == 0 && cout % 16 == 0 && cin >= 4 && cin <= 128 && cout >= 16 && cout <= 128;
 }
 
 // gw must be zeroed by the caller; tiles are accumulated with red.global

@@ -132,6 +132,17 @@ __device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t a_desc
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with bf16 operands (fp32 accumulate), K = 16 per instruction
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -161,6 +172,11 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
+// c_format f32, a/b_format bf16 (mma_sm100 instruction descriptor: bits [4,6) D, [7,10) A, [10,13) B)
+__device__ __forceinline__ constexpr uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
 template <int CO>
 struct Cfg {
   // deep enough that a filter slice is requested several TMA latencies (about 2.5 us) ahead of its use
@@ -174,7 +190,14 @@ struct Cfg {
 // GATHER4 = false: the A tile is gathered by cp.async (LDGSTS, 16 bytes per thread, zero-fill for
 // missing neighbours) from all 16 producer warps; true: by TMA gather4 (kept selectable: measured
 // 1.7x slower than cp.async here because UTMALDG issue, not bandwidth, limits it).
-template <int CO, bool GATHER4>
+//
+// PREC = 0: operands are fp32 rows, MMA kind::tf32 (the hardware reads the top 19 bits).
+// PREC = 1 ("bf16x3"): every 128-byte chunk of an operand row holds 32 channels as [32 x bf16 hi | 32 x bf16 lo]
+// with hi = bf16(x), lo = bf16(x - hi) (ddf_split_bf16x3; same bytes per row as fp32, so the gather, the TMA
+// boxes and the stage bookkeeping are unchanged).  Per stage the issuer runs hi.hi + hi.lo + lo.hi as six
+// kind::f16 MMAs (K = 16): products carry a 16-bit significand (error about 2^-17 per product instead of 2^-11
+// for tf32) at 1.5x the tensor-pipe time of the tf32 stage, fp32 accumulation in TMEM either way.
+template <int CO, bool GATHER4, int PREC>
 __global__ void __launch_bounds__(kThreads)
 spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_constant__ CUtensorMap map_w,
                   const float* __restrict__ feat, const int* __restrict__ table, const float* __restrict__ bias, float* __restrict__ out,
@@ -389,7 +412,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
     if (t < T) {
       // all 32 lanes walk the loop; values that come from shared memory are passed through a warp
       // reduction, whose result the compiler knows to be uniform
-      constexpr uint32_t idesc = make_idesc_tf32(CO);
+      constexpr uint32_t idesc = PREC ? make_idesc_bf16(CO) : make_idesc_tf32(CO);
       const uint32_t mt = __reduce_or_sync(0xffffffffu, t == 0 ? tmask[0] : t == 1 ? tmask[1] : t == 2 ? tmask[2] : tmask[3]);
       const uint32_t any_u = __reduce_or_sync(0xffffffffu, any);
       const uint32_t d_tmem = __reduce_or_sync(0xffffffffu, tmem_base) + (uint32_t)(t * C::kCols);
@@ -411,11 +434,25 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_desc = make_desc_sw128(a_ring + (uint32_t)(slot * kABytes));
             const uint64_t b_desc = make_desc_sw128(smem_u32(b_base) + (uint32_t)(sb * C::kBBytes));
+            if constexpr (PREC == 0) {
 #pragma unroll
-            for (int ks = 0; ks < KCH / 8; ++ks) {
-              // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_tf32_elect(d_tmem, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, accumulate);
-              accumulate = 1;
+              for (int ks = 0; ks < KCH / 8; ++ks) {
+                // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+                umma_tf32_elect(d_tmem, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, accumulate);
+                accumulate = 1;
+              }
+            } else {
+              // 16 bf16 = 32 bytes per K step: steps 0,1 = hi halves of the 32 channels, steps 2,3 = lo halves
+#pragma unroll
+              for (int term = 0; term < 3; ++term) {
+                const int ao = term == 2 ? 4 : 0, bo = term == 1 ? 4 : 0;    // lo.hi last, hi.lo second
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  umma_bf16_elect(d_tmem, a_desc + (uint64_t)(ao + 2 * ks), b_desc + (uint64_t)(bo + 2 * ks), idesc,
+                                  accumulate);
+                  accumulate = 1;
+                }
+              }
             }
             umma_commit_elect(a_empty + t * ring + slot);
             umma_commit_elect(b_empty + sb);
@@ -800,11 +837,11 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CO, bool GATHER4>
+template <int CO, bool GATHER4, int PREC>
 int launch_tma(const float* feat, const float* wt, const int* table, const float* bias, float* out,
                int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
   using C = Cfg<CO>;
-  DDF_SET_SMEM_ONCE((spconv_tma_kernel<CO, GATHER4>), C::kSmemBytes);
+  DDF_SET_SMEM_ONCE((spconv_tma_kernel<CO, GATHER4, PREC>), C::kSmemBytes);
   CUtensorMap map_feat, map_w;
   if (!make_map(&map_feat, feat, n_in, cin, 1) || !make_map(&map_w, wt, (int64_t)kvol * cout, cin, cout)) {
     ddf::set_error("sparse conv: cuTensorMapEncodeTiled failed (n_in=%lld cin=%d cout=%d)", (long long)n_in, cin, cout);
@@ -826,7 +863,7 @@ int launch_tma(const float* feat, const float* wt, const int* table, const float
   }
   const int smem = n_slots * kABytes + n_sb * C::kBBytes + T * TM * kMaxKvol * 4 + 512 + 1024;
   const unsigned grid = (unsigned)ddf::cdiv(ntiles, T);
-  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
+  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4, PREC>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
              bias, out, (int)n_out, (int)n_in, kvol, cin, cout, T, n_slots, n_sb);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -842,13 +879,15 @@ bool spconv_tma_supported(int kvol, int cin, int cout) {
   return encode_fn() != nullptr && kvol <= kMaxKvol && cin % KCH == 0 && cout % 16 == 0 && cout >= 16 && cout <= 128;
 }
 
-// feat [n_in, cin]; wt [K, cout, cin] (K-major B operand); table [n_out, K]
+// feat [n_in, cin]; wt [K, cout, cin] (K-major B operand); table [n_out, K].  split = both operands are in the
+// bf16 hi/lo block layout (see the kernel comment), else fp32.
 int spconv_tma_launch(const float* feat, const float* wt, const int* table, const float* bias, float* out,
-                      int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4,
+                      int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4, bool split,
                       cudaStream_t stream) {
-#define DDF_TMA_CASE(CO)                                                                                   \
-  return gather4 ? launch_tma<CO, true>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream) \
-                 : launch_tma<CO, false>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream)
+#define DDF_TMA_CASE(CO)                                                                                         \
+  if (split) return launch_tma<CO, false, 1>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream); \
+  return gather4 ? launch_tma<CO, true, 0>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream)    \
+                 : launch_tma<CO, false, 0>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream)
   if (cout <= 16) { DDF_TMA_CASE(16); }
   if (cout <= 32) { DDF_TMA_CASE(32); }
   if (cout <= 64) { DDF_TMA_CASE(64); }

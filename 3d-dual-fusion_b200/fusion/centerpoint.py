@@ -26,6 +26,18 @@ from ..ops import sparse_norm
 from .sparse_block import build_norm_layer
 
 
+def _matvec(m, v):
+    """Per-row m[n] @ v[n] (or v[n] @ m for a shared 2-D m via ``_rowmat``) as explicit multiply-adds: geometry must
+    never be routed to a library GEMM, which runs tf32 under ``allow_tf32`` and moves projected pixels by up to a pixel."""
+    return (m * v[:, None, :]).sum(-1)
+
+
+def _rowmat(p, m):
+    """p (n, k) @ m (k, j) in exact fp32 multiply-adds."""
+    return (p[:, :, None] * m[None]).sum(1)
+
+
+
 def replace_feature(out, new_features):
     return out.replace_feature(new_features)
 
@@ -150,7 +162,7 @@ class Point2ImageProjection(nn.Module):
                 for aug_type in ["translate", "rescale", "rotate", "flip"]:
                     if aug_type in aug:
                         m = torch.as_tensor(np.asarray(aug[aug_type]), dtype=torch.float32, device=dev)
-                        p = p + m if aug_type == "translate" else p @ m
+                        p = p + m if aug_type == "translate" else _rowmat(p, m)
                 out[sel] = p
             pts = out
         return pts
@@ -165,10 +177,10 @@ class Point2ImageProjection(nn.Module):
             calib_key = cam_key.lower().lstrip("cam_")  # the reference's (quirky) key derivation
             l2c = batch_dict["calib"]["lidar2cam_" + calib_key].float()[b_idx]          # (N, 4, 4)
             K = batch_dict["calib"]["cam_intrinsic_" + calib_key].float()[b_idx]        # (N, 3, 3)
-            cam = torch.einsum("nij,nj->ni", l2c, homo)
+            cam = _matvec(l2c, homo)
             cam = cam[:, :3] / cam[:, 3:4]                                               # transform_points
             depth = cam[:, 2].clone()
-            img = torch.einsum("nij,nj->ni", K, cam)
+            img = _matvec(K, cam)
             img = img / img[:, 2:3]                                                      # camera_to_image
             grid = img[:, :2].long()
             grid = (image_scale * grid.float()).long()

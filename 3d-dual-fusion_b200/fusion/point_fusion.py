@@ -23,6 +23,18 @@ from ..registry import FUSION_LAYERS
 from .actr import build as build_actr
 
 
+def _matvec(m, v):
+    """Per-row m[n] @ v[n] (or v[n] @ m for a shared 2-D m via ``_rowmat``) as explicit multiply-adds: geometry must
+    never be routed to a library GEMM, which runs tf32 under ``allow_tf32`` and moves projected pixels by up to a pixel."""
+    return (m * v[:, None, :]).sum(-1)
+
+
+def _rowmat(p, m):
+    """p (n, k) @ m (k, j) in exact fp32 multiply-adds."""
+    return (p[:, :, None] * m[None]).sum(1)
+
+
+
 def reverse_3d_transformation(points, img_meta):
     """apply_3d_transformation(..., reverse=True) for LiDAR coordinates
     (TransFusion/mmdet3d/models/fusion_layers/coord_transform.py:8-75)."""
@@ -38,7 +50,7 @@ def reverse_3d_transformation(points, img_meta):
             pts = pts * (1.0 / img_meta.get("pcd_scale_factor", 1.))
         elif op == "R":
             rot = torch.as_tensor(img_meta.get("pcd_rotation", torch.eye(3)), dtype=dtype, device=device)
-            pts = pts @ rot.inverse()
+            pts = _rowmat(pts, rot.inverse())
         elif op == "HF":
             if img_meta.get("pcd_horizontal_flip", False):
                 pts = pts * pts.new_tensor([1., -1., 1.])
@@ -61,7 +73,9 @@ def project_to_cameras(points, img_meta):
     n_cam = l2i.shape[0]
     ori_h, ori_w = img_meta["ori_shape"][:2]
     homo = torch.cat([pts[:, :3], pts.new_ones(n, 1)], 1)                    # (n, 4)
-    cam_pts = torch.einsum("cij,nj->cni", l2i[:, :3, :], homo)                # (n_cam, n, 3)
+    # explicit multiply-add (never a library GEMM): a tf32 matmul here moves the projected pixel by up to a pixel
+    # and flips camera assignments / the //4 feature pick (measured: 0.23 relative error at the BEV output)
+    cam_pts = (l2i[:, None, :3, :] * homo[None, :, None, :]).sum(-1)         # (n_cam, n, 3)
     depth = cam_pts[..., 2]
     uv = cam_pts[..., :2] / depth[..., None]
     seen = ((depth > 1.0) & (uv[..., 0] > 1) & (uv[..., 0] < ori_w - 1)

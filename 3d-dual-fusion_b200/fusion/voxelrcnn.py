@@ -28,6 +28,18 @@ from ..ops import spconv
 from .actr import build as build_actr
 
 
+def _matvec(m, v):
+    """Per-row m[n] @ v[n] (or v[n] @ m for a shared 2-D m via ``_rowmat``) as explicit multiply-adds: geometry must
+    never be routed to a library GEMM, which runs tf32 under ``allow_tf32`` and moves projected pixels by up to a pixel."""
+    return (m * v[:, None, :]).sum(-1)
+
+
+def _rowmat(p, m):
+    """p (n, k) @ m (k, j) in exact fp32 multiply-adds."""
+    return (p[:, :, None] * m[None]).sum(1)
+
+
+
 def post_act_block(in_channels, out_channels, kernel_size, indice_key=None, stride=1, padding=0,
                    conv_type="subm", norm_fn=None):
     if conv_type == "subm":
@@ -139,7 +151,7 @@ class VoxelBackBone8xFusion(nn.Module):
         if "lidar2img" in batch_dict:
             P = torch.as_tensor(batch_dict["lidar2img"], dtype=xyz.dtype, device=xyz.device)[:, :3, :]
             homo = torch.cat([xyz, xyz.new_ones(xyz.shape[0], 1)], 1)
-            cam = torch.einsum("nij,nj->ni", P[b_idx], homo)
+            cam = _matvec(P[b_idx], homo)
             return cam[:, :2] / cam[:, 2:3]
         uv = xyz.new_zeros((xyz.shape[0], 2))
         for b, calib in enumerate(batch_dict["calib"]):   # reference path: KITTI calib object on the host

@@ -32,11 +32,12 @@ _SIGNATURES = {
     "ddf_conv_indice_pairs": [c_ptr, c_i64, c_i64] + [c_ptr] * 6 + [c_i64] + [c_ptr] * 6 + [c_i64, c_ptr],
     "ddf_indice_conv": [c_ptr] * 4 + [c_i64, c_ptr] + [c_i64] * 4 + [c_int, c_int, c_ptr, c_ptr],
     "ddf_indice_conv_backward": [c_ptr] * 5 + [c_i64, c_ptr, c_ptr] + [c_i64] * 4 + [c_int, c_int, c_ptr, c_ptr, c_ptr],
-    "ddf_sparse_conv_forward": [c_ptr] * 6 + [c_i64] * 5 + [c_ptr],
+    "ddf_sparse_conv_forward": [c_ptr] * 6 + [c_i64] * 5 + [c_int, c_ptr],
     "ddf_sparse_conv_tc_mode": [c_i64] * 3,
     "ddf_set_tensor_cores": [c_int],
     "ddf_round_tf32": [c_ptr, c_ptr, c_i64, c_ptr],
-    "ddf_sparse_conv_dgrad": [c_ptr] * 5 + [c_i64] * 5 + [c_ptr],
+    "ddf_sparse_conv_dgrad": [c_ptr] * 5 + [c_i64] * 5 + [c_int, c_ptr],
+    "ddf_split_bf16x3": [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr],
     "ddf_sparse_conv_wgrad_table": [c_ptr] * 4 + [c_i64] * 5 + [c_ptr],
     "ddf_sparse_conv_wgrad": [c_ptr] * 4 + [c_i64, c_ptr] + [c_i64] * 3 + [c_int, c_ptr],
     "ddf_furthest_point_sampling": [c_ptr] * 3 + [c_i64] * 3 + [c_ptr],

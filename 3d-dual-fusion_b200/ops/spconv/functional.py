@@ -85,16 +85,23 @@ class TableConvFunction(Function):
             cin += pad
         ctx.mode = mode = ops.tc_mode(kvol, cin, cout)
         saved = features
-        if mode & 5 and features.shape[0]:
-            # tensor-core operands are made exact tf32 once; forward and wgrad share the copy. A forward
-            # that runs in fp32 (narrow layers) keeps the unrounded features.
-            saved = ops.round_tf32(features)
-            if mode & 1:
-                features = saved
+        fmt = 0
+        if features.shape[0]:
+            if mode & 16:
+                # bf16x3 forward: hi/lo split operands; the same pass writes the tf32-rounded copy wgrad reads
+                features, rounded = ops.split_bf16x3(features, want_rounded=bool(mode & 12))
+                saved = rounded if rounded is not None else saved
+                fmt = 1
+            elif mode & 5:
+                # tensor-core operands are made exact tf32 once; forward and wgrad share the copy. A forward
+                # that runs in fp32 (narrow layers) keeps the unrounded features.
+                saved = ops.round_tf32(features)
+                if mode & 1:
+                    features = saved
         ctx.rulebook = rulebook
         ctx.has_bias = bias is not None
         ctx.save_for_backward(saved, filters)
-        return ops.sparse_conv_forward(features, filters, rulebook.gather_table, bias, num_activate_out)
+        return ops.sparse_conv_forward(features, filters, rulebook.gather_table, bias, num_activate_out, fmt)
 
     @staticmethod
     @once_differentiable
@@ -104,12 +111,21 @@ class TableConvFunction(Function):
         grad_output = grad_output.contiguous()
         gb = grad_output.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         grad_exact = grad_output
-        if ctx.mode & 6 and grad_output.shape[0]:
-            grad_output = ops.round_tf32(grad_output)  # shared by dgrad and wgrad
+        grad_split = None
+        if grad_output.shape[0]:
+            if ctx.mode & 32 and ctx.needs_input_grad[0]:
+                grad_split, rounded = ops.split_bf16x3(grad_output, want_rounded=bool(ctx.mode & 12)
+                                                       and ctx.needs_input_grad[1])
+                grad_output = rounded if rounded is not None else grad_output
+            elif ctx.mode & 14:
+                grad_output = ops.round_tf32(grad_output)  # shared by dgrad and wgrad
         gin = gw = None
         if ctx.needs_input_grad[0]:
-            gin = ops.sparse_conv_dgrad(filters, grad_output if ctx.mode & 2 else grad_exact, rb.scatter_table,
-                                        features.shape[0])
+            if grad_split is not None:
+                gin = ops.sparse_conv_dgrad(filters, grad_split, rb.scatter_table, features.shape[0], 1)
+            else:
+                gin = ops.sparse_conv_dgrad(filters, grad_output if ctx.mode & 2 else grad_exact, rb.scatter_table,
+                                            features.shape[0])
         if ctx.needs_input_grad[1]:
             if ctx.mode & 8 and getattr(rb, "subm", False) and grad_output.shape[0]:
                 # dense SubM layers: walk the output rows once through the gather table

@@ -190,7 +190,8 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
 
 
 def tc_mode(kvol, cin, cout):
-    """Bit mask of the conv kernels of this layer that run on the tensor cores (1 fwd, 2 dgrad, 4 wgrad)."""
+    """Bit mask of the conv kernels of this layer that run on the tensor cores (1 fwd, 2 dgrad, 4 wgrad, 8 table
+    wgrad; 16 / 32: fwd / dgrad take bf16x3 split operands)."""
     return int(_lib.get_lib().ddf_sparse_conv_tc_mode(int(kvol), int(cin), int(cout)))
 
 
@@ -213,7 +214,21 @@ def round_tf32(x):
     return out
 
 
-def sparse_conv_forward(features, filters, gather_table, bias, n_out):
+def split_bf16x3(x, want_rounded=False):
+    """``x`` fp32 [rows, C] (C % 32 == 0) -> (split, rounded): ``split`` holds every row as blocks of
+    [32 x bf16 hi | 32 x bf16 lo] (same bytes as fp32; carried in a float32 tensor of x's shape), the operand
+    layout of the bf16x3 conv kernels; ``rounded`` = tf32-rounded copy for the wgrad kernels (or None)."""
+    x = x.contiguous()
+    split = torch.empty_like(x)
+    rounded = torch.empty_like(x) if want_rounded else None
+    with torch.cuda.device(x.device):
+        rc = _lib.get_lib().ddf_split_bf16x3(_lib.ptr(x), _lib.ptr(split), _lib.ptr(rounded), x.shape[0], x.shape[1],
+                                             _lib.current_stream())
+    _lib.check(rc, "split_bf16x3")
+    return split, rounded
+
+
+def sparse_conv_forward(features, filters, gather_table, bias, n_out, operand_format=0):
     _check_conv_args(features, filters)
     cin, cout = filters.shape[-2], filters.shape[-1]
     kvol = gather_table.shape[1] if gather_table.numel() else filters.numel() // (cin * cout)
@@ -222,12 +237,13 @@ def sparse_conv_forward(features, filters, gather_table, bias, n_out):
     with torch.cuda.device(features.device):
         rc = _lib.get_lib().ddf_sparse_conv_forward(
             _lib.ptr(features), _lib.ptr(filters), _lib.ptr(gather_table), _lib.ptr(bias), _lib.ptr(out),
-            _lib.ptr(wt_ws), n_out, features.shape[0], kvol, cin, cout, _lib.current_stream())
+            _lib.ptr(wt_ws), n_out, features.shape[0], kvol, cin, cout, int(operand_format),
+            _lib.current_stream())
     _lib.check(rc, "sparse_conv_forward")
     return out
 
 
-def sparse_conv_dgrad(filters, grad_out, scatter_table, n_in):
+def sparse_conv_dgrad(filters, grad_out, scatter_table, n_in, operand_format=0):
     cin, cout = filters.shape[-2], filters.shape[-1]
     kvol = filters.numel() // (cin * cout)
     gin = torch.empty((n_in, cin), dtype=grad_out.dtype, device=grad_out.device)
@@ -236,7 +252,7 @@ def sparse_conv_dgrad(filters, grad_out, scatter_table, n_in):
         rc = _lib.get_lib().ddf_sparse_conv_dgrad(_lib.ptr(grad_out), _lib.ptr(filters),
                                                   _lib.ptr(scatter_table), _lib.ptr(gin), _lib.ptr(wt_ws),
                                                   n_in, grad_out.shape[0], kvol, cin, cout,
-                                                  _lib.current_stream())
+                                                  int(operand_format), _lib.current_stream())
     _lib.check(rc, "sparse_conv_dgrad")
     return gin
 

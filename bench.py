@@ -211,10 +211,10 @@ class KernelTimer(object):
             return ("table", table, n_src, n_dst, cin, cout)
 
         self._wrap(ops, "sparse_conv_forward", "conv",
-                   lambda f, w, t, b, n_out: conv_meta(t, f.shape[0], n_out, w.shape[-2], w.shape[-1]))
+                   lambda f, w, t, b, n_out, *fmt: conv_meta(t, f.shape[0], n_out, w.shape[-2], w.shape[-1]))
         # dgrad timing includes the small filter-rounding launch that precedes the conv kernel
         self._wrap(ops, "sparse_conv_dgrad", "conv",
-                   lambda w, g, t, n_in: conv_meta(t, g.shape[0], n_in, w.shape[-1], w.shape[-2]))
+                   lambda w, g, t, n_in, *fmt: conv_meta(t, g.shape[0], n_in, w.shape[-1], w.shape[-2]))
         self._wrap(ops, "sparse_conv_wgrad", "wgrad",
                    lambda f, w, g, pairs, num: ("pairs", num, f.shape[0], g.shape[0], w.shape[-2], w.shape[-1]))
         self._wrap(ops, "sparse_conv_wgrad_table", "wgrad",
@@ -391,7 +391,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.fp32_gemm else "tf32 tensor-core inputs, f32 accumulate/storage",
+            "dtype": "f32 storage/accumulate; sparse convs bf16x3 (hi/lo split operands, 16-bit significand products) on "
+                     "tcgen05, wgrad tf32; library GEMMs " + ("f32" if args.fp32_gemm else "tf32"),
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

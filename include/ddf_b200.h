@@ -173,28 +173,34 @@ int ddf_indice_conv_backward(const float* features, const float* filters, const 
                              float* filters_t_ws, void* stream);
 
 /* filters_t_ws: optional float [K*Cin*Cout] scratch; when given (and Cin % 32 == 0, Cout <= 128,
- * K <= 27) the tcgen05 tf32 implicit-GEMM kernel runs, otherwise the fp32 SIMT kernel. */
+ * K <= 27) a tcgen05 implicit-GEMM kernel runs, otherwise the fp32 SIMT kernel.
+ * operand_format 0: features are fp32 rows (tcgen05 kind::tf32). 1: features are in the bf16 hi/lo block
+ * layout written by ddf_split_bf16x3 ("bf16x3": three bf16 MMAs per product pair, 16-bit significand,
+ * fp32 accumulation); only where ddf_sparse_conv_tc_mode reports bit 4 (forward) / bit 5 (dgrad). */
 int ddf_sparse_conv_forward(const float* features, const float* filters, const int* gather_table,
                             const float* bias, float* out, float* filters_t_ws, int64_t n_out,
-                            int64_t n_in, int64_t kvol, int64_t cin, int64_t cout, void* stream);
+                            int64_t n_in, int64_t kvol, int64_t cin, int64_t cout, int operand_format,
+                            void* stream);
 
 /* Tensor-core bookkeeping: ddf_sparse_conv_tc_mode returns a bit mask of the kernels of a layer
- * that run as tcgen05 tf32 implicit GEMMs (1 forward, 2 dgrad, 4 wgrad, 8 table-driven wgrad
- * available; 0 with DDF_DISABLE_TC=1).
+ * that run as tcgen05 implicit GEMMs (1 forward, 2 dgrad, 4 wgrad, 8 table-driven wgrad
+ * available, 16 / 32 forward / dgrad expect operand_format 1; 0 with DDF_DISABLE_TC=1).
  * tf32 keeps 10 mantissa bits and the hardware TRUNCATES fp32 operands; ddf_round_tf32 rounds a
  * tensor to the nearest tf32 first (dst may alias src) so the error is unbiased. Filters are
  * rounded inside the conv calls. */
 int ddf_sparse_conv_tc_mode(int64_t kvol, int64_t cin, int64_t cout);
-/* Conv kernel selection: 1 (default) tcgen05 tf32, multi-tile kernel (filter slices by tiled TMA,
+/* Conv kernel selection: 4 (default; env DDF_TC_MODE overrides) as 1, with forward and dgrad of the layers
+ * the multi-tile kernel takes in bf16x3 (wgrad stays tf32); 1 tcgen05 tf32, multi-tile kernel (filter slices by tiled TMA,
  * shared by up to 4 row tiles; rows gathered by cp.async) where the layer shape allows, else the
  * single-tile cp.async kernel; 2 single-tile cp.async kernel only; 3 as 1 with rows gathered by TMA
  * gather4; 0 fp32 SIMT kernels (full fp32 products). Returns the previous setting. Not thread-safe
  * against concurrent conv calls. */
 int ddf_set_tensor_cores(int on);
 int ddf_round_tf32(const float* src, float* dst, int64_t n, void* stream);
+/* src fp32 [rows, cols], cols % 32 == 0 -> split [rows*cols*4 bytes]: per row, per 32 channels, 128 bytes
+ * [32 x bf16 hi | 32 x bf16 lo], hi = bf16(x), lo = bf16(x - hi); rounded (may be NULL): tf32-rounded copy. */
+int ddf_split_bf16x3(const float* src, void* split, float* rounded, int64_t rows, int64_t cols, void* stream);
 
-/* n_out = rows of grad_out (-1 when unknown: the TMA-staged kernel, whose tensor map needs the
- * height of the gathered tensor, is then not used). */
 /* wgrad through the forward gather table [n_out, K] instead of the pair lists (tcgen05; Cin, Cout in
  * {32, 64, 128}, K <= 27): output rows walked once, grad_out read densely. grad_filters is zeroed
  * inside. ddf_sparse_conv_tc_mode bit 3 (8) says whether a layer shape is supported. */
@@ -202,9 +208,12 @@ int ddf_sparse_conv_wgrad_table(const float* features, const float* grad_out, co
                                 float* grad_filters, int64_t n_out, int64_t n_in, int64_t kvol,
                                 int64_t cin, int64_t cout, void* stream);
 
+/* n_out = rows of grad_out (-1 when unknown: the TMA-staged kernel, whose tensor map needs the
+ * height of the gathered tensor, is then not used). operand_format as in ddf_sparse_conv_forward
+ * (1: grad_out is in the bf16 hi/lo block layout). */
 int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters, const int* scatter_table,
                           float* grad_in, float* filters_t_ws, int64_t n_in, int64_t n_out, int64_t kvol,
-                          int64_t cin, int64_t cout, void* stream);
+                          int64_t cin, int64_t cout, int operand_format, void* stream);
 
 int ddf_sparse_conv_wgrad(const float* features, const float* grad_out, const int* indice_pairs,
                           const int* indice_num, int64_t pair_stride, float* grad_filters,

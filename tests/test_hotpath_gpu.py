@@ -4,12 +4,15 @@ own CPU code (oracle/cpu_path.py: reference voxelization / spconv extensions fro
 present, else the C restatements; pure-PyTorch MSDA).
 
 Tolerances (max |a - b| / max |b|), written per mode:
-  * fp32 mode (``ddf_set_tensor_cores(0)``: every conv product in full fp32): 1e-3, the north_star bar,
-    for outputs; 1e-2 for parameter gradients (long mixed-sign sums over all voxels).
-  * tf32 tensor-core mode (the benchmarked default: tcgen05 kind::tf32, operands rounded to nearest,
-    fp32 accumulation): every single conv is within 1e-3 of the oracle (tests/test_spconv_gpu.py); the
-    21-conv chain with batch-statistics BatchNorm between them compounds to <= 3e-3 at the BEV output
-    in train mode (1.8e-3 measured), 1e-3 in eval mode."""
+  * default mode = what bench.py times (``ddf_set_tensor_cores(4)``: forward / dgrad of the wide convs as bf16x3 on
+    tcgen05 - 16-bit significand per product, fp32 accumulation -, narrow convs fp32, wgrad tf32; library GEMMs of the
+    fusion encoder under ``allow_tf32 = True`` exactly as bench.py sets it): BEV output within 1e-3 (north_star bar;
+    measured 1.7e-4 train / 4.9e-4 eval on B200), whole-model gradient within 5e-3 relative L2 (2.1e-3 measured),
+    every parameter gradient within 5e-2 of its max (3.3e-2: tf32 wgrad of small-gradient layers), cosine > 0.999.
+  * fp32 mode (``ddf_set_tensor_cores(0)``, library GEMMs in fp32): 1e-3 outputs, 1e-2 every parameter gradient.
+  * single-pass tf32 convs (mode 1, not the default any more): 1.3e-3 at the BEV output in train mode - above the bar,
+    which is why bf16x3 is the default; kept as a looser regression check (3e-3).
+  * one full-size frame (260k points, the bench workload's shape) against the CPU oracle in the default mode."""
 import copy
 import os
 import sys
@@ -52,20 +55,45 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-def test_forward_eval_matches_reference_cpu_path():
+def _bench_arithmetic(on=True):
+    # exactly what bench.py:run_ours sets for the library GEMMs
+    torch.backends.cuda.matmul.allow_tf32 = on
+    torch.backends.cudnn.allow_tf32 = on
+
+
+def _forward_eval(n_points=8000, batch=2, tol=1e-3):
     from oracle import cpu_path
     m_cpu = build().eval()
     m_gpu = copy.deepcopy(m_cpu).cuda().eval()
-    pts, feats, metas = inputs(2, 8000)
+    pts, feats, metas = inputs(batch, n_points)
     with torch.no_grad():
         with cpu_path.reference_cpu_ops():
             ref = m_cpu(pts, [feats], metas)
         out = m_gpu([p.cuda() for p in pts], [feats.cuda()], metas).cpu()
-    assert out.shape == ref.shape == (2, 256, 180, 180)
+    assert out.shape == ref.shape == (batch, 256, 180, 180)
     # same active BEV cells, up to ReLU outputs that sit at +-0 within rounding
     differ = (out != 0) != (ref != 0)
-    assert float(torch.maximum(out.abs(), ref.abs())[differ].max() if differ.any() else 0.0) < 1e-3 * float(ref.abs().max())
-    assert rel(out, ref) < 1e-3
+    assert float(torch.maximum(out.abs(), ref.abs())[differ].max() if differ.any() else 0.0) < tol * float(ref.abs().max())
+    assert rel(out, ref) < tol
+
+
+def test_forward_eval_matches_reference_cpu_path():
+    """Default conv mode + the benchmark's library-GEMM arithmetic."""
+    _bench_arithmetic(True)
+    try:
+        _forward_eval()
+    finally:
+        _bench_arithmetic(False)
+
+
+def test_full_size_frame_matches_reference_cpu_path():
+    """One frame of the bench workload's size (260k points, 6 x 256 x 112 x 200 camera features) against the CPU
+    oracle, in the benchmarked arithmetic (about 20 s of host time)."""
+    _bench_arithmetic(True)
+    try:
+        _forward_eval(n_points=260000, batch=1)
+    finally:
+        _bench_arithmetic(False)
 
 
 @pytest.fixture
@@ -76,27 +104,44 @@ def fp32_convs():
     lib.get_lib().ddf_set_tensor_cores(prev)
 
 
+@pytest.fixture
+def tf32_convs():
+    from ddf_b200 import lib
+    prev = lib.get_lib().ddf_set_tensor_cores(1)
+    yield
+    lib.get_lib().ddf_set_tensor_cores(prev)
+
+
 def test_forward_eval_fp32_mode_matches_reference_cpu_path(fp32_convs):
-    test_forward_eval_matches_reference_cpu_path()
+    _bench_arithmetic(False)
+    _forward_eval()
 
 
 def test_train_step_fp32_mode_gradients_match_reference_cpu_path(fp32_convs):
-    _train_step_parity(out_tol=1e-3, grad_max_tol=1e-2, grad_l2_tol=1e-2)
+    _train_step_parity(out_tol=1e-3, grad_max_tol=1e-2, grad_l2_tol=1e-2, min_cos=0.9999)
 
 
 def test_train_step_gradients_match_reference_cpu_path():
-    # tf32 products through 21 convs and their batch-statistics BatchNorm backward: on this small
-    # frame the error reaching the first layers is up to ~20% of a single small parameter gradient;
-    # checked here: every non-negligible parameter gradient points the same way (cosine > 0.9) and
-    # the whole-model gradient is within 5% (relative L2).  Element-wise max-norm parity is asserted
-    # in fp32 mode (test above) and per conv in tests/test_spconv_gpu.py.
-    _train_step_parity(out_tol=3e-3, grad_max_tol=None, grad_l2_tol=0.05)
+    """The benchmarked arithmetic: bf16x3 convs (default mode) + tf32 library GEMMs."""
+    _train_step_parity(out_tol=1e-3, grad_max_tol=5e-2, grad_l2_tol=5e-3, min_cos=0.999, bench_gemms=True)
 
 
-def _train_step_parity(out_tol, grad_max_tol, grad_l2_tol):
+def test_train_step_single_pass_tf32_convs(tf32_convs):
+    # tf32 products through 21 convs and their batch-statistics BatchNorm backward compound to 1.3e-3 at the output
+    _train_step_parity(out_tol=3e-3, grad_max_tol=None, grad_l2_tol=0.05, min_cos=0.9)
+
+
+def _train_step_parity(out_tol, grad_max_tol, grad_l2_tol, min_cos, bench_gemms=False):
     from oracle import cpu_path
-    torch.backends.cudnn.allow_tf32 = False   # the 1x1 Conv2d input_proj runs through cuDNN
-    torch.backends.cuda.matmul.allow_tf32 = False
+    _bench_arithmetic(bench_gemms)   # the 1x1 Conv2d input_proj runs through cuDNN, the Linears through cuBLAS
+    try:
+        _train_step_parity_body(out_tol, grad_max_tol, grad_l2_tol, min_cos)
+    finally:
+        _bench_arithmetic(False)
+
+
+def _train_step_parity_body(out_tol, grad_max_tol, grad_l2_tol, min_cos):
+    from oracle import cpu_path
     m_cpu = build(seed=1).train()
     for mod in m_cpu.modules():
         if isinstance(mod, torch.nn.Dropout):
@@ -128,9 +173,9 @@ def _train_step_parity(out_tol, grad_max_tol, grad_l2_tol):
             r_max = float((gd - gc).abs().max() / max(float(gc.abs().max()), 1e-3 * gmax))
             if not r_max < grad_max_tol:
                 bad.append((name, r_max, float(gc.abs().max())))
-        elif float(gc.norm()) > 1e-3 * gmax:
+        if float(gc.norm()) > 1e-3 * gmax:
             cos = float((gd * gc).sum() / (gd.norm() * gc.norm()).clamp_min(1e-300))
-            if not cos > 0.9:
+            if not cos > min_cos:
                 bad.append((name, cos, float(gc.abs().max())))
     assert not bad, sorted(bad, key=lambda t: -t[1])[:8]
     assert (num / den) ** 0.5 < grad_l2_tol, (num / den) ** 0.5   # whole-model gradient, relative L2

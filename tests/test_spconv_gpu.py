@@ -62,17 +62,21 @@ def test_conv_fwd_bwd_vs_oracle(geom, chan):
     ref_gi, ref_gw = osp.indice_conv_backward(feat, w, go, o_pairs, o_num)
 
     rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, dil, 0, subm, False)
-    # fp32 SIMT kernels: 1e-4.  Layers that run as tcgen05 implicit GEMMs multiply tf32 operands
-    # (10-bit mantissa, rounded to nearest) with fp32 accumulation: 1e-3 relative, the north_star bar.
+    # fp32 SIMT kernels: 1e-4.  Layers that run as tcgen05 implicit GEMMs: bf16x3 forward / dgrad (default mode,
+    # 16-bit significand per product, fp32 accumulation) also hold 1e-4; single-pass tf32 (wgrad; forward / dgrad in
+    # mode 1) multiplies 10-bit mantissas rounded to nearest: 1e-3 relative, the north_star bar.
     kv = int(np.prod(ks))
-    tol = 1e-3 if ops.tc_mode(kv, ops.padded_cin(kv, cin, cout), cout) else 1e-4
+    mode = ops.tc_mode(kv, ops.padded_cin(kv, cin, cout), cout)
+    tol = 1e-3 if mode else 1e-4
+    tol_f = 1e-4 if (mode & 16 or not mode & 1) else 1e-3
+    tol_d = 1e-4 if (mode & 32 or not mode & 2) else 1e-3
     # (a) hot path: table-driven Function
     f = torch.from_numpy(feat).cuda().requires_grad_()
     wt = torch.from_numpy(w).cuda().requires_grad_()
     out = Fsp.table_conv(f, wt, None, rb, len(o_out))
     out.backward(torch.from_numpy(go).cuda())
-    assert rel_err(out.detach().cpu().numpy(), ref) < tol
-    assert rel_err(f.grad.cpu().numpy(), ref_gi) < tol
+    assert rel_err(out.detach().cpu().numpy(), ref) < tol_f
+    assert rel_err(f.grad.cpu().numpy(), ref_gi) < tol_d
     assert rel_err(wt.grad.cpu().numpy(), ref_gw) < tol
     # (b) drop-in path: reference-named Functions on the reference-format rulebook
     f2 = torch.from_numpy(feat).cuda().requires_grad_()
@@ -80,9 +84,84 @@ def test_conv_fwd_bwd_vs_oracle(geom, chan):
     fn = Fsp.indice_subm_conv if subm else Fsp.indice_conv
     out2 = fn(f2, w2, rb.indice_pairs, rb.indice_pair_num, len(o_out))
     out2.backward(torch.from_numpy(go).cuda())
-    assert rel_err(out2.detach().cpu().numpy(), ref) < 1e-4  # drop-in forward stays fp32 SIMT
-    assert rel_err(f2.grad.cpu().numpy(), ref_gi) < tol
-    assert rel_err(w2.grad.cpu().numpy(), ref_gw) < tol
+    # the reference-ABI entry points are the indice_conv*_fp32 contract: fp32 SIMT forward and backward
+    assert rel_err(out2.detach().cpu().numpy(), ref) < 1e-4
+    assert rel_err(f2.grad.cpu().numpy(), ref_gi) < 1e-4
+    assert rel_err(w2.grad.cpu().numpy(), ref_gw) < 1e-4
+
+
+@pytest.mark.parametrize("tc", [1, 4])
+@pytest.mark.parametrize("chan", [(32, 32), (64, 128), (128, 64), (32, 64)])
+def test_conv_precision_modes(tc, chan):
+    """tf32 (mode 1) vs bf16x3 (mode 4) forward / dgrad on the multi-tile kernel against the oracle."""
+    from ddf_b200 import lib
+    from ddf_b200.ops.spconv import functional as Fsp, ops
+    from oracle import spconv as osp
+    shape, ks, st, pad, dil, subm = GEOMS[0]
+    cin, cout = chan
+    rng = np.random.default_rng(5)
+    idx = random_voxels(2500, 2, shape, seed=6)
+    o_out, o_pairs, o_num, _ = osp.get_indice_pairs(idx, 2, shape, ks, st, pad, dil, subm, order="gpu")
+    feat = (rng.standard_normal((len(idx), cin)) * np.exp(rng.uniform(-4, 4, (len(idx), 1)))).astype(np.float32)
+    w = (rng.standard_normal((*ks, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    go = rng.standard_normal((len(o_out), cout)).astype(np.float32)
+    ref = osp.indice_conv(feat, w, o_pairs, o_num, len(o_out))
+    ref_gi, ref_gw = osp.indice_conv_backward(feat, w, go, o_pairs, o_num)
+    prev = lib.get_lib().ddf_set_tensor_cores(tc)
+    try:
+        mode = ops.tc_mode(int(np.prod(ks)), cin, cout)
+        assert bool(mode & 16) == (tc == 4) and bool(mode & 32) == (tc == 4)
+        rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 2, shape, ks, st, pad, dil, 0, subm, False)
+        f = torch.from_numpy(feat).cuda().requires_grad_()
+        wt = torch.from_numpy(w).cuda().requires_grad_()
+        out = Fsp.table_conv(f, wt, None, rb, len(o_out))
+        out.backward(torch.from_numpy(go).cuda())
+    finally:
+        lib.get_lib().ddf_set_tensor_cores(prev)
+    tol = 5e-5 if tc == 4 else 1e-3
+    assert rel_err(out.detach().cpu().numpy(), ref) < tol
+    assert rel_err(f.grad.cpu().numpy(), ref_gi) < tol
+    assert rel_err(wt.grad.cpu().numpy(), ref_gw) < 1e-3     # wgrad is tf32 in both modes
+
+
+def test_split_bf16x3_layout():
+    """ddf_split_bf16x3: [32 x bf16 hi | 32 x bf16 lo] per 32 channels, hi + lo == x to 2^-16, tf32 copy rounded."""
+    from ddf_b200.ops.spconv import ops
+    x = torch.randn(257, 96, device="cuda") * torch.exp(torch.empty(257, 1, device="cuda").uniform_(-20, 20))
+    split, rounded = ops.split_bf16x3(x, want_rounded=True)
+    blocks = split.view(torch.bfloat16).view(257, 3, 2, 32)
+    hi, lo = blocks[:, :, 0].float(), blocks[:, :, 1].float()
+    xb = x.view(257, 3, 32)
+    assert torch.equal(hi, xb.bfloat16().float())
+    assert torch.equal(lo, (xb - hi).bfloat16().float())
+    assert float(((hi + lo - xb).abs() / xb.abs().clamp_min(1e-30)).max()) < 2.0 ** -16
+    assert float(((rounded - x).abs() / x.abs().clamp_min(1e-30)).max()) <= 2.0 ** -11
+    assert torch.equal(rounded.view(torch.int32) & 0x1FFF, torch.zeros_like(rounded, dtype=torch.int32))
+
+
+def test_large_kernel_volume_falls_back_to_fp32_wgrad():
+    """5x5x5 SubM kernel (K = 125 > 100): the pair-list tensor-core wgrad keeps per-offset bookkeeping for at most
+    100 offsets in shared memory, larger kernel volumes must take the fp32 kernel (and stay correct)."""
+    from ddf_b200.ops.spconv import functional as Fsp, ops
+    from oracle import spconv as osp
+    shape, ks = [9, 20, 20], [5, 5, 5]
+    rng = np.random.default_rng(3)
+    idx = random_voxels(600, 1, shape, seed=8)
+    o_out, o_pairs, o_num, _ = osp.get_indice_pairs(idx, 1, shape, ks, [1] * 3, [2] * 3, [1] * 3, True, order="gpu")
+    feat = rng.standard_normal((len(idx), 16)).astype(np.float32)
+    w = (rng.standard_normal((*ks, 16, 16)) / 4).astype(np.float32)
+    go = rng.standard_normal((len(o_out), 16)).astype(np.float32)
+    ref = osp.indice_conv(feat, w, o_pairs, o_num, len(o_out))
+    ref_gi, ref_gw = osp.indice_conv_backward(feat, w, go, o_pairs, o_num)
+    assert not ops.tc_mode(125, 16, 16) & 4
+    rb = ops.build_rulebook(torch.from_numpy(idx).cuda(), 1, shape, ks, [1] * 3, [2] * 3, [1] * 3, 0, True, False)
+    f = torch.from_numpy(feat).cuda().requires_grad_()
+    wt = torch.from_numpy(w).cuda().requires_grad_()
+    out = Fsp.table_conv(f, wt, None, rb, len(o_out))
+    out.backward(torch.from_numpy(go).cuda())
+    assert rel_err(out.detach().cpu().numpy(), ref) < 1e-3
+    assert rel_err(f.grad.cpu().numpy(), ref_gi) < 1e-3
+    assert rel_err(wt.grad.cpu().numpy(), ref_gw) < 1e-3
 
 
 def test_inverse_conv_roundtrip_shapes_and_values():
@@ -173,8 +252,16 @@ def test_full_size_properties_nuscenes_grid():
     with torch.no_grad():
         conv64.weight.zero_()
         conv64.weight[1, 1, 1] = torch.eye(64)
-    # tensor-core layers (tf32 inputs): identity weights return the tf32-rounded input
-    assert torch.equal(conv64(x64).features, ops.round_tf32(x64.features))
+    # tensor-core layers, bf16x3 (default): identity weights return hi + lo = the input to 16 bits, exactly
+    # bf16(x) + bf16(x - bf16(x)); single-pass tf32 (mode 1) returns the tf32-rounded input
+    hi = x64.features.bfloat16().float()
+    assert torch.equal(conv64(x64).features, hi + (x64.features - hi).bfloat16().float())
+    from ddf_b200 import lib
+    prev = lib.get_lib().ddf_set_tensor_cores(1)
+    try:
+        assert torch.equal(conv64(x64).features, ops.round_tf32(x64.features))
+    finally:
+        lib.get_lib().ddf_set_tensor_cores(prev)
     ones = sp.SparseConvTensor(torch.ones(n, 1, device="cuda"), idx, shape, 2)
     c1 = sp.SubMConv3d(1, 1, 3, bias=False).cuda()
     with torch.no_grad():

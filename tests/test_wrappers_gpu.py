@@ -186,7 +186,7 @@ def test_centerpoint_pfatv2_path_matches_cpu_oracle_path():
         with cpu_path.reference_cpu_ops():
             ref, _ = backbone(feats.cpu(), bd, coors.cpu(), B, [1440, 1440, 40], {}, fuse_func=fuse)
     assert out.shape == ref.shape == (B, 256, 180, 180)
-    assert float((out.cpu() - ref).abs().max()) < 2e-3 * float(ref.abs().max())
+    assert float((out.cpu() - ref).abs().max()) < 1e-3 * float(ref.abs().max())
 
 
 def test_centerpoint_hybrid_ifat_path_matches_cpu_oracle_path():
@@ -228,7 +228,7 @@ def test_centerpoint_hybrid_ifat_path_matches_cpu_oracle_path():
         ref, _ = backbone(feats.cpu(), bd, coors.cpu(), B, [1440, 1440, 40], {}, fuse_func=fuse)
         ref.square().mean().backward()
     assert out.shape == ref.shape == (B, 256, 180, 180)
-    assert float((out.detach().cpu() - ref.detach()).abs().max()) < 2e-3 * float(ref.abs().max())
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) < 1e-3 * float(ref.abs().max())
     # the gate is live: its parameters receive gradients that agree with the CPU path
     for name in ("ifat.spatial_basic.weight", "ifat.reduced_dim2.weight", "ifat.reduced_dim.0.weight"):
         gd, gc = dict(g_fuse.named_parameters())[name].grad.cpu(), dict(fuse.named_parameters())[name].grad
@@ -271,7 +271,7 @@ def test_voxelrcnn_actrv2_hybrid_path_fwd_bwd():
             d_ref = ref.dense()
     assert out.spatial_shape == ref.spatial_shape == [2, 200, 176]
     d_out = out.dense().cpu()
-    assert float((d_out - d_ref).abs().max()) < 2e-3 * float(d_ref.abs().max())
+    assert float((d_out - d_ref).abs().max()) < 1e-3 * float(d_ref.abs().max())
     # fwd + bwd in train mode runs and produces finite gradients for every live parameter
     m.train()
     out = m(dict(bd_gpu, img_dict={k: v.cuda() for k, v in img_dict.items()}))["encoded_spconv_tensor"]

@@ -162,8 +162,16 @@ def bench_spconv(args):
         go = ops.round_tf32(torch.randn(n_out, cout, device="cuda"))
         flops = 2.0 * pairs * cin * cout
         byts = 4.0 * (n * cin + n_out * cout + 27 * cin * cout) + 8.0 * pairs
-        for kind, fn in (("fwd", lambda: ops.sparse_conv_forward(feat, w, rb.gather_table, None, n_out)),
-                         ("dgrad", lambda: ops.sparse_conv_dgrad(w, go, rb.scatter_table, n)),
+        mode = ops.tc_mode(27, cin, cout)
+        # bf16x3 layers take pre-split operands (the split pass is timed separately as "split")
+        f_in, f_fmt = (ops.split_bf16x3(feat)[0], 1) if mode & 16 else (feat, 0)
+        g_in, g_fmt = (ops.split_bf16x3(go)[0], 1) if mode & 32 else (go, 0)
+        if mode & 16:
+            med, best = time_cuda(lambda: ops.split_bf16x3(feat, want_rounded=True), args.iters)
+            print(json.dumps(dict(kernel="split_bf16x3 %s" % name, ms_median=med, alg_MB=12.0 * n * cin / 1e6,
+                                  GBs=12.0 * n * cin / med / 1e6, hbm_frac=12.0 * n * cin / med / 1e6 / hbm)))
+        for kind, fn in (("fwd", lambda: ops.sparse_conv_forward(f_in, w, rb.gather_table, None, n_out, f_fmt)),
+                         ("dgrad", lambda: ops.sparse_conv_dgrad(w, g_in, rb.scatter_table, n, g_fmt)),
                          ("wgrad", lambda: ops.sparse_conv_wgrad(feat, w, go, rb.indice_pairs, rb.indice_pair_num)),
                          ("wgrad_table", (lambda: ops.sparse_conv_wgrad_table(feat, w, go, rb.gather_table))
                           if (subm and ops.tc_mode(27, cin, cout) & 8) else None)):
@@ -228,7 +236,7 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--stages", default="", help="spconv: comma list of SubM stage names to run (strided convs always run)")
     ap.add_argument("--warm", type=int, default=3, help="untimed warm-up launches (0 for ncu captures)")
-    ap.add_argument("--tc-mode", type=int, default=1, help="conv kernels: 1 TMA+tcgen05 (default), 2 cp.async+tcgen05, 0 fp32 SIMT")
+    ap.add_argument("--tc-mode", type=int, default=4, help="conv kernels: 4 bf16x3 fwd/dgrad on TMA+tcgen05 (default), 1 tf32 TMA+tcgen05, 2 cp.async+tcgen05, 0 fp32 SIMT")
     a = ap.parse_args()
     WARM = a.warm
     from ddf_b200 import lib as _l
