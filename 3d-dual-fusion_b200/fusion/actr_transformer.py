@@ -11,6 +11,7 @@ from torch import nn
 from torch.nn.init import normal_
 
 from ..ops import fused
+from ..ops import msda as _msda
 from .attentions import attn_dict
 from .ms_deform_attn import MSDeformAttn
 
@@ -60,9 +61,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, self.linear2(hidden))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
-                padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None):
+                padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None, plan=None):
         src2 = self.self_attn(_with_pos(q_feat, q_pos), reference_points, src, spatial_shapes,
-                              level_start_index, padding_mask)
+                              level_start_index, padding_mask, plan=plan)
         q_feat = fused.add_dropout_layer_norm(self.norm1, self.dropout1, q_feat, src2)
         return self.forward_ffn(q_feat), q_i_feat
 
@@ -115,9 +116,9 @@ class DeformableTransformerFusionEncoderLayer(nn.Module):
         return fused.add_dropout_layer_norm(self.norm3, self.dropout5, src, src2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
-                padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None):
+                padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None, plan=None):
         src2 = self.self_attn(_with_pos(q_feat, q_pos), reference_points, src, spatial_shapes,
-                              level_start_index, padding_mask, i_query=_with_pos(q_i_feat, q_pos))
+                              level_start_index, padding_mask, i_query=_with_pos(q_i_feat, q_pos), plan=plan)
         q_i_feat = fused.add_dropout_layer_norm(self.norm1, self.dropout1, q_i_feat, src2)
         if self.gate_first:
             q_feat, q_i_feat = self.fusion_layer(q_feat, q_i_feat)
@@ -133,6 +134,7 @@ class DeformableTransformerEncoder(nn.Module):
         self.layers = _get_clones(encoder_layer, num_layers)
         self.num_layers = num_layers
         self.model_name = model_name
+        self.spatial_hw = None   # (H, W) of the single feature level, set by DeformableTransformerACTR.forward
         if model_name == "ACTRv2":
             from .pointformer import LocalTransformer
             get = lt_cfg.get if hasattr(lt_cfg, "get") else lambda k, d=None: getattr(lt_cfg, k, d)
@@ -148,12 +150,23 @@ class DeformableTransformerEncoder(nn.Module):
         if q_reference_points is None:
             raise NotImplementedError("image->point direction (IACTR) is not part of the 3D-DF hot path")
         reference_points = q_reference_points[:, :, None] * valid_ratios[:, None]
+        plan = self._tile_plan(src, reference_points, spatial_shapes)
         for idx, layer in enumerate(self.layers):
             if self.model_name == "ACTRv2":
                 q_feat = self.lidar_attns[idx](q_lidar_grid, q_feat.permute(0, 2, 1))
             q_feat, q_i_feat = layer(src, pos, reference_points, spatial_shapes, level_start_index,
-                                     padding_mask, q_pos=q_pos, q_feat=q_feat, q_i_feat=q_i_feat)
+                                     padding_mask, q_pos=q_pos, q_feat=q_feat, q_i_feat=q_i_feat, plan=plan)
         return q_feat
+
+    def _tile_plan(self, src, reference_points, spatial_shapes):
+        """One tile binning of the queries for all layers (and their backward): the reference points do not change
+        inside the encoder. None when the shape is not the tile kernels' (then every layer takes the generic op)."""
+        attn = self.layers[0].self_attn
+        if (not src.is_cuda or src.dtype != torch.float32 or reference_points.shape[-1] != 2
+                or self.spatial_hw is None
+                or not _msda.tile_supported(attn.n_heads, attn.d_model // attn.n_heads, attn.n_levels, attn.n_points)):
+            return None
+        return _msda.TilePlan(reference_points, *self.spatial_hw)
 
 
 class DeformableTransformerACTR(nn.Module):
@@ -212,6 +225,7 @@ class DeformableTransformerACTR(nn.Module):
             if masks is not None:
                 mask_flatten.append(masks[lvl].flatten(1))
         src_flatten = torch.cat(src_flatten, 1) if len(src_flatten) > 1 else src_flatten[0]
+        self.encoder.spatial_hw = spatial_shapes[0] if len(spatial_shapes) == 1 else None   # python ints: no sync
         device = src_flatten.device
         spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=device)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)),

@@ -10,6 +10,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
+from ..ops import msda as _msda
 from ..ops.msda import MSDeformAttnFunction
 from .attentions import attn_dict
 
@@ -63,7 +64,7 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.0)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
-                input_level_start_index, input_padding_mask=None, i_query=None):
+                input_level_start_index, input_padding_mask=None, i_query=None, plan=None):
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
         assert input_spatial_shapes.shape[0] == self.n_levels
@@ -94,6 +95,11 @@ class MSDeformAttn(nn.Module):
 
         sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
         attention_weights = self.attention_weights(weight_query).view(N, Len_q, M, L * P)
+        if plan is not None:
+            # hot path: softmax, the location arithmetic and the sampling run as ONE tile-staged kernel
+            # (csrc/msda_tile.cu); ``plan`` (ops.msda.TilePlan) carries the reference points binned by image tile
+            output = _msda.MSDeformAttnTileFunction.apply(value, sampling_offsets, attention_weights, plan)
+            return self.output_proj(output)
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.stack(

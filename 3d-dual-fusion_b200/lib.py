@@ -23,6 +23,11 @@ _SIGNATURES = {
     "ddf_launch_count": [c_int],
     "ddf_ms_deform_attn_forward": [c_ptr] * 6 + [c_i64] * 8 + [c_int, c_ptr],
     "ddf_ms_deform_attn_backward": [c_ptr] * 9 + [c_i64] * 8 + [c_int, c_ptr],
+    "ddf_msda_tile_supported": [c_i64] * 4,
+    "ddf_msda_plan_bytes": [c_i64] * 4,
+    "ddf_msda_plan": [c_ptr, c_ptr] + [c_i64] * 4 + [c_ptr],
+    "ddf_msda_tile_forward": [c_ptr] * 6 + [c_i64] * 6 + [c_ptr],
+    "ddf_msda_tile_backward": [c_ptr] * 9 + [c_i64] * 6 + [c_ptr],
     "ddf_hard_voxelize_workspace_bytes": [c_i64] * 3,
     "ddf_hard_voxelize": [c_ptr] * 7 + [c_i64] * 4 + [c_ptr, c_i64, c_ptr],
     "ddf_dynamic_voxelize": [c_ptr] * 4 + [c_i64] * 2 + [c_ptr],
@@ -56,7 +61,7 @@ _SIGNATURES = {
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_dense_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
 }
-_RESTYPES = {"ddf_launch_count": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64,
+_RESTYPES = {"ddf_launch_count": c_i64, "ddf_msda_plan_bytes": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64,
              "ddf_sparse_bn_workspace_bytes": c_i64}
 
 

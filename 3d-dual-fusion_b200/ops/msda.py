@@ -87,3 +87,80 @@ class MSDeformAttnFunction(Function):
         grad_value, grad_loc, grad_attn = ms_deform_attn_backward(
             value, shapes, lsi, loc, attn, grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_loc, grad_attn, None
+
+
+# ---- tile-staged dual-query form (hot path) -------------------------------------------------------
+def tile_supported(M, D, L, P, dtype=torch.float32):
+    """True when the fused tile-staged kernels take this shape (one level, 4 points, D in {8, 16}, fp32)."""
+    return dtype == torch.float32 and bool(_lib.get_lib().ddf_msda_tile_supported(int(M), int(D), int(L), int(P)))
+
+
+class TilePlan(object):
+    """Queries binned by feature-map tile (ddf_msda_plan). Built once per encoder forward from the reference
+    points; shared by every layer's forward and backward."""
+
+    def __init__(self, reference_points, H, W):
+        ref = reference_points
+        if ref.dim() == 4:           # (N, Lq, L=1, 2)
+            ref = ref[:, :, 0]
+        _lib.require_cuda(ref)
+        self.ref = ref.detach().contiguous().float()
+        self.N, self.Lq = self.ref.shape[0], self.ref.shape[1]
+        self.H, self.W = int(H), int(W)
+        L = _lib.get_lib()
+        nbytes = int(L.ddf_msda_plan_bytes(self.N, self.Lq, self.H, self.W))
+        self.buf = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=ref.device)
+        with torch.cuda.device(ref.device):
+            rc = L.ddf_msda_plan(_lib.ptr(self.ref), _lib.ptr(self.buf), self.N, self.Lq, self.H, self.W,
+                                 _lib.current_stream())
+        _lib.check(rc, "msda_plan")
+
+
+def msda_tile_forward(value, plan, offsets, logits):
+    N, S, M, D = value.shape
+    out = torch.empty((N, plan.Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.get_lib().ddf_msda_tile_forward(
+            _lib.ptr(value), _lib.ptr(plan.ref), _lib.ptr(offsets), _lib.ptr(logits), _lib.ptr(plan.buf),
+            _lib.ptr(out), N, plan.H, plan.W, M, D, plan.Lq, _lib.current_stream())
+    _lib.check(rc, "msda_tile_forward")
+    return out
+
+
+def msda_tile_backward(value, plan, offsets, logits, grad_out):
+    N, S, M, D = value.shape
+    grad_value = torch.empty_like(value)   # zeroed inside the library call
+    grad_off = torch.empty_like(offsets)
+    grad_logit = torch.empty_like(logits)
+    with torch.cuda.device(value.device):
+        rc = _lib.get_lib().ddf_msda_tile_backward(
+            _lib.ptr(value), _lib.ptr(plan.ref), _lib.ptr(offsets), _lib.ptr(logits), _lib.ptr(grad_out),
+            _lib.ptr(plan.buf), _lib.ptr(grad_value), _lib.ptr(grad_off), _lib.ptr(grad_logit), N, plan.H, plan.W,
+            M, D, plan.Lq, _lib.current_stream())
+    _lib.check(rc, "msda_tile_backward")
+    return grad_value, grad_off, grad_logit
+
+
+class MSDeformAttnTileFunction(Function):
+    """out = MSDA(value, loc = ref + offsets / (W, H), softmax(logits)): the module arithmetic of
+    ops/modules/ms_deform_attn.py:149-188 as one op. value (N, H*W, M, D), offsets (N, Lq, M, 1, 4, 2) raw,
+    logits (N, Lq, M, 4); reference points live in ``plan`` (no gradient flows to them)."""
+
+    @staticmethod
+    def forward(ctx, value, offsets, logits, plan):
+        for t in (value, offsets, logits):
+            if t.dtype != torch.float32 or not t.is_cuda:
+                raise RuntimeError("msda tile kernels: CUDA float32 tensors only")
+        value, offsets, logits = value.contiguous(), offsets.contiguous(), logits.contiguous()
+        if value.shape[0] != plan.N or value.shape[1] != plan.H * plan.W or offsets.shape[1] != plan.Lq:
+            raise RuntimeError("msda tile kernels: plan was built for another problem size")
+        ctx.plan = plan
+        ctx.save_for_backward(value, offsets, logits)
+        return msda_tile_forward(value, plan, offsets, logits)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, offsets, logits = ctx.saved_tensors
+        gv, go, gl = msda_tile_backward(value, ctx.plan, offsets, logits, grad_output.contiguous())
+        return gv, go, gl, None

@@ -228,6 +228,15 @@ class KernelTimer(object):
         self._wrap(msda, "ms_deform_attn_forward", "msda_fwd", msda_meta)
         self._wrap(msda, "ms_deform_attn_backward", "msda_bwd", msda_meta)
 
+        def tile_meta(value, plan, *rest):
+            N, S, M, D = value.shape
+            return (N, S, M, D, plan.Lq, 1, 4)
+
+        # the tile-staged dual-query kernels (what the encoder runs): same algorithmic bytes, the softmax / location
+        # arithmetic of the module is inside the kernel
+        self._wrap(msda, "msda_tile_forward", "msda_fwd", tile_meta)
+        self._wrap(msda, "msda_tile_backward", "msda_bwd", tile_meta)
+
     def remove(self):
         for mod, name, orig in self.saved:
             setattr(mod, name, orig)

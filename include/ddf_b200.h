@@ -75,6 +75,27 @@ int ddf_ms_deform_attn_backward(const void* value, const int64_t* spatial_shapes
                                 int64_t D, int64_t L, int64_t Lq, int64_t P,
                                 int64_t im2col_step, int dtype, void* stream);
 
+/* ---- tile-staged dual-query deformable attention (one level, 4 points, D in {8, 16}, fp32) --------------
+ * Fuses what the reference module does around the op (ops/modules/ms_deform_attn.py:149-166: softmax over the
+ * L*P logits, sampling_locations = reference_points + offsets / (W, H)) with the sampling kernel
+ * (ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299) and its backward (:301-403).  Queries are binned by image
+ * tile once per encoder forward (ddf_msda_plan; reference points are shared by all layers and by backward),
+ * every CTA stages its tile + halo of `value` in shared memory with one 4-D TMA box load.
+ *   value [N, H*W, M, D]; reference_points [N, Lq, 2]; offsets [N, Lq, M, 1, 4, 2] (raw Linear output, pixels);
+ *   logits [N, Lq, M, 4]; out [N, Lq, M*D].  Backward returns grads wrt value, offsets and logits.
+ * ddf_msda_tile_supported: 1 when (M, D, L, P) is handled here (else use ddf_ms_deform_attn_*). */
+int ddf_msda_tile_supported(int64_t M, int64_t D, int64_t L, int64_t P);
+int64_t ddf_msda_plan_bytes(int64_t N, int64_t Lq, int64_t H, int64_t W);
+int ddf_msda_plan(const float* reference_points, void* plan, int64_t N, int64_t Lq, int64_t H, int64_t W,
+                  void* stream);
+int ddf_msda_tile_forward(const float* value, const float* reference_points, const float* offsets,
+                          const float* logits, const void* plan, float* out, int64_t N, int64_t H, int64_t W,
+                          int64_t M, int64_t D, int64_t Lq, void* stream);
+int ddf_msda_tile_backward(const float* value, const float* reference_points, const float* offsets,
+                           const float* logits, const float* grad_out, const void* plan, float* grad_value,
+                           float* grad_offsets, float* grad_logits, int64_t N, int64_t H, int64_t W, int64_t M,
+                           int64_t D, int64_t Lq, void* stream);
+
 /* ---- Voxelization ---------------------------------------------------------------------
  * Replaces mmdet3d.ops.voxel.voxel_layer.hard_voxelize / dynamic_voxelize
  *   reference: TransFusion/mmdet3d/ops/voxel/src/voxelization.h:51-69 (hard), :71-86 (dynamic)

@@ -85,6 +85,22 @@ def bench_msda(args):
                           alg_MB=bwd_bytes / 1e6, GBs=bwd_bytes / med / 1e6, frac=bwd_bytes / med / 1e6 / hbm, peak=how)))
 
 
+    if P == 4 and msda.tile_supported(M, D, 1, P):
+        # tile-staged dual-query form (the hot path): raw offsets + logits + reference points
+        refp = torch.rand(N, Lq, 2, device=dev)
+        off = torch.randn(N, Lq, M, 1, P, 2, device=dev) * 2.0
+        logit = torch.randn(N, Lq, M, P, device=dev)
+        med, best = time_cuda(lambda: msda.TilePlan(refp, H, W), args.iters)
+        print(json.dumps(dict(kernel="msda_tile_plan", shape=args.shape, ms_median=med, ms_best=best)))
+        plan = msda.TilePlan(refp, H, W)
+        med, best = time_cuda(lambda: msda.msda_tile_forward(value, plan, off, logit), args.iters)
+        print(json.dumps(dict(kernel="msda_tile_fwd", shape=args.shape, ms_median=med, ms_best=best,
+                              alg_MB=fwd_bytes / 1e6, GBs=fwd_bytes / med / 1e6, frac=fwd_bytes / med / 1e6 / hbm, peak=how)))
+        med, best = time_cuda(lambda: msda.msda_tile_backward(value, plan, off, logit, gout), args.iters)
+        print(json.dumps(dict(kernel="msda_tile_bwd", shape=args.shape, ms_median=med, ms_best=best,
+                              alg_MB=bwd_bytes / 1e6, GBs=bwd_bytes / med / 1e6, frac=bwd_bytes / med / 1e6 / hbm, peak=how)))
+
+
 def _tf_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
