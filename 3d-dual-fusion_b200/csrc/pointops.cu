@@ -264,6 +264,49 @@ index_rows_grad_kernel(const float* __restrict__ gout, const int* __restrict__ i
   atomicAdd(gfeat + ((long long)b * C + c) * N + j, gout[((long long)b * C + c) * E + e]);
 }
 
+// ---- LocalTransformer.scatter, "unique" / "replace" rule (<proj>/models/model_utils/pointformer.py:319-347) ----
+// Every voxel that occurs in the ball-query index tensor takes the transformed feature of its FIRST occurrence in
+// flattened (group, slot) order (what the reference's unique + flip + scatter_ yields on the CPU; its CUDA scatter_
+// with duplicate indices is nondeterministic).  first[b, n] = min position of voxel n.
+__global__ void __launch_bounds__(256) fill_int_kernel(int* __restrict__ p, int v, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+first_occurrence_kernel(const int* __restrict__ idx, int* __restrict__ first, int N, long long E) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.y;
+  if (e >= E) return;
+  atomicMin(first + (long long)b * N + idx[(long long)b * E + e], (int)e);
+}
+
+// out[b, c, n] = feats[b, c, first[b, n]] where voxel n was hit (first < E); other columns keep their value
+__global__ void __launch_bounds__(256)
+scatter_first_kernel(const float* __restrict__ feats, const int* __restrict__ first, float* __restrict__ out,
+                     int C, int N, long long E) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (n >= N) return;
+  const int f = first[(long long)b * N + n];
+  if (f < E) out[((long long)b * C + c) * N + n] = feats[((long long)b * C + c) * E + f];
+}
+
+// backward: grad_feats[b, c, first[b, n]] = grad_out[b, c, n] (positions are distinct: no atomics; grad_feats is
+// zeroed by the caller), grad_features[b, c, n] = hit ? 0 : grad_out[b, c, n]
+__global__ void __launch_bounds__(256)
+scatter_first_grad_kernel(const float* __restrict__ gout, const int* __restrict__ first,
+                          float* __restrict__ gfeats, float* __restrict__ gfeatures, int C, int N, long long E) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (n >= N) return;
+  const int f = first[(long long)b * N + n];
+  const long long o = ((long long)b * C + c) * N + n;
+  const float g = gout[o];
+  if (f < E) gfeats[((long long)b * C + c) * E + f] = g;
+  gfeatures[o] = f < E ? 0.f : g;
+}
+
 int launch_index_rows(const float* feat, const int* idx, float* out, int64_t B, int64_t C, int64_t N,
                       int64_t E, cudaStream_t stream, bool grad) {
   if (B * C * E == 0) return DDF_OK;
@@ -359,4 +402,50 @@ extern "C" int ddf_gather_points_grad(const float* grad_out, const int* idx, flo
     DDF_CUDA(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)(B * C * N), stream));
   }
   return launch_index_rows(grad_out, idx, grad_points, B, C, N, npoints, stream, true);
+}
+
+// first [B, N] int32 <- first flattened position (< E = npoints * nsample) of every voxel in idx [B, E]; E = not hit
+extern "C" int ddf_first_occurrence(const int* idx, int* first, int64_t B, int64_t N, int64_t E, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(B >= 0 && N >= 0 && E >= 0 && E < (1ll << 31) && B <= 65535, "first_occurrence: bad sizes");
+  if (B * N == 0) return DDF_OK;
+  DDF_CHECK_ARG(first != nullptr, "first_occurrence: null first");
+  // fill with E: 0x7f7f7f7f would also do, but E keeps the "hit" test exact for any E
+  DDF_LAUNCH(fill_int_kernel, (unsigned)ddf::cdiv(B * N, 256), 256, 0, stream, first, (int)E, (long long)(B * N));
+  if (E == 0) return DDF_OK;
+  DDF_CHECK_ARG(idx != nullptr, "first_occurrence: null idx");
+  dim3 grid((unsigned)ddf::cdiv(E, 256), (unsigned)B);
+  DDF_LAUNCH(first_occurrence_kernel, grid, 256, 0, stream, idx, first, (int)N, (long long)E);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// inout [B, C, N]: columns of hit voxels replaced by feats [B, C, E] at their first occurrence
+extern "C" int ddf_scatter_first(const float* feats, const int* first, float* inout, int64_t B, int64_t C, int64_t N,
+                                 int64_t E, void* stream_) {
+  DDF_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && E >= 0 && C <= 65535 && B <= 65535, "scatter_first: bad sizes");
+  if (B * C * N == 0 || E == 0) return DDF_OK;
+  DDF_CHECK_ARG(feats && first && inout, "scatter_first: null pointer");
+  dim3 grid((unsigned)ddf::cdiv(N, 256), (unsigned)C, (unsigned)B);
+  DDF_LAUNCH(scatter_first_kernel, grid, 256, 0, (cudaStream_t)stream_, feats, first, inout, (int)C, (int)N, (long long)E);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+extern "C" int ddf_scatter_first_grad(const float* grad_out, const int* first, float* grad_feats,
+                                      float* grad_features, int64_t B, int64_t C, int64_t N, int64_t E,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && E >= 0 && C <= 65535 && B <= 65535, "scatter_first_grad: bad sizes");
+  if (B * C * E > 0) {
+    DDF_CHECK_ARG(grad_feats != nullptr, "scatter_first_grad: null grad_feats");
+    DDF_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * (size_t)(B * C * E), stream));
+  }
+  if (B * C * N == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_out && first && grad_features, "scatter_first_grad: null pointer");
+  dim3 grid((unsigned)ddf::cdiv(N, 256), (unsigned)C, (unsigned)B);
+  DDF_LAUNCH(scatter_first_grad_kernel, grid, 256, 0, stream, grad_out, first, grad_feats, grad_features, (int)C, (int)N,
+             (long long)E);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
 }

@@ -735,3 +735,59 @@ extern "C" int ddf_dense_to_sparse(const float* grad_dense, const int* indices,
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
+
+// ---- BEV hand-off: sparse [N, C] + indices [N, 4] -> the 2-D backbone's input in bf16, channels-last ----------
+// The reference hands dense() (fp32 NCDHW) viewed as [B, C*D, H, W] to SECOND (sparse_encoder.py:366-367,
+// backbones/second.py).  For a bf16 channels-last 2-D backbone the same map is written directly as the physical
+// layout [B, H, W, C*D] (channel index c * D + z), half the bytes and no permute.
+namespace {
+__global__ void __launch_bounds__(kThreads)
+bev_nhwc_bf16_scatter_kernel(const float* __restrict__ feat, const int* __restrict__ indices, int n, int C, int D,
+                             int H, int W, __nv_bfloat16* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int row = (int)(t >> 5), lane = (int)(t & 31);
+  if (row >= n) return;
+  const int4 c = reinterpret_cast<const int4*>(indices)[row];      // b, z, y, x
+  __nv_bfloat16* base = out + (((long long)c.x * H + c.z) * W + c.w) * ((long long)C * D) + c.y;
+  for (int ch = lane; ch < C; ch += 32) base[(long long)ch * D] = __float2bfloat16_rn(feat[(long long)row * C + ch]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+bev_nhwc_bf16_gather_kernel(const __nv_bfloat16* __restrict__ gdense, const int* __restrict__ indices, int n, int C,
+                            int D, int H, int W, float* __restrict__ gfeat) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int row = (int)(t >> 5), lane = (int)(t & 31);
+  if (row >= n) return;
+  const int4 c = reinterpret_cast<const int4*>(indices)[row];
+  const __nv_bfloat16* base = gdense + (((long long)c.x * H + c.z) * W + c.w) * ((long long)C * D) + c.y;
+  for (int ch = lane; ch < C; ch += 32) gfeat[(long long)row * C + ch] = __bfloat162float(base[(long long)ch * D]);
+}
+}  // namespace
+
+// out: bf16 [B, H, W, C*D] (zeroed inside) = channels-last storage of the logical [B, C*D, H, W] BEV map
+extern "C" int ddf_sparse_to_bev_nhwc_bf16(const float* features, const int* indices, void* out, int64_t n,
+                                           int64_t C, int64_t B, int64_t D, int64_t H, int64_t W, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "sparse_to_bev_nhwc_bf16: bad sizes");
+  DDF_CHECK_ARG(out != nullptr, "sparse_to_bev_nhwc_bf16: null out");
+  DDF_CUDA(cudaMemsetAsync(out, 0, 2 * (size_t)(B * C * D * H * W), stream));
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(features && indices, "sparse_to_bev_nhwc_bf16: null pointer");
+  DDF_LAUNCH(bev_nhwc_bf16_scatter_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, features,
+             indices, (int)n, (int)C, (int)D, (int)H, (int)W, reinterpret_cast<__nv_bfloat16*>(out));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+extern "C" int ddf_bev_nhwc_bf16_to_sparse(const void* grad_dense, const int* indices, float* grad_features,
+                                           int64_t n, int64_t C, int64_t B, int64_t D, int64_t H, int64_t W,
+                                           void* stream_) {
+  DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "bev_nhwc_bf16_to_sparse: bad sizes");
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(grad_dense && indices && grad_features, "bev_nhwc_bf16_to_sparse: null pointer");
+  DDF_LAUNCH(bev_nhwc_bf16_gather_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, (cudaStream_t)stream_,
+             reinterpret_cast<const __nv_bfloat16*>(grad_dense), indices, (int)n, (int)C, (int)D, (int)H, (int)W,
+             grad_features);
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}

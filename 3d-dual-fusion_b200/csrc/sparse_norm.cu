@@ -283,6 +283,8 @@ extern "C" int ddf_sparse_bn_forward(const float* x, const float* residual, cons
   const long long n4 = n * C / 4;
   if (training) {
     DDF_CHECK_ARG(workspace && save_mean && save_invstd, "sparse_bn_forward: training needs workspace and save buffers");
+    // the arrival counter is reset by the last CTA of a launch; an aborted launch must not poison the next one
+    DDF_CUDA(cudaMemsetAsync(ws_counter(workspace, C), 0, sizeof(unsigned), stream));
     DDF_LAUNCH(bn_stats_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, x, (int)n,
                (int)C, (double*)workspace, ws_counter(workspace, C), save_mean, save_invstd,
                running_mean, running_var, momentum, eps);
@@ -318,6 +320,7 @@ extern "C" int ddf_sparse_bn_backward(const float* grad_y, const float* y, const
                     aligned16(weight) && aligned16(mean) && aligned16(invstd),
                 "sparse_bn_backward: tensors must be 16-byte aligned");
   float* coef = ws_coef(workspace, C);
+  DDF_CUDA(cudaMemsetAsync(ws_counter(workspace, C), 0, sizeof(unsigned), stream));
   DDF_LAUNCH(bn_bwd_reduce_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, grad_y, y, x,
              mean, invstd, (int)n, (int)C, relu, training, (double*)workspace, ws_counter(workspace, C),
              grad_weight, grad_bias, coef);

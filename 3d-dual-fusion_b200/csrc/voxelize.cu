@@ -163,6 +163,42 @@ vox_gather_kernel(const float* __restrict__ points, Grid3 g, int F, int T,
   }
 }
 
+// K4', fused HardSimpleVFE (TransFusion/mmdet3d/models/voxel_encoders/voxel_encoder.py:27-44): instead of writing the
+// padded [M, T, F] voxel tensor only for a reduction kernel to read it back, sum the (at most T) points of a voxel in
+// list order and divide by the count.  One thread per (voxel, feature < NF); coors / num_points as in K4.
+__global__ void __launch_bounds__(kThreads)
+vox_mean_kernel(const float* __restrict__ points, Grid3 g, int F, int T, int NF,
+                const int* __restrict__ first_point, const int* __restrict__ slot_of_point,
+                const int* __restrict__ keys, const int* __restrict__ lists,
+                const int* __restrict__ cut_p, const int* __restrict__ voxel_num_p,
+                float* __restrict__ mean, int* __restrict__ coors, int* __restrict__ num_points, long long total) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= total) return;
+  const int v = (int)(t / NF);
+  if (v >= *voxel_num_p) return;
+  const int f = (int)(t % NF);
+  const int h = slot_of_point[first_point[v]];
+  const int cut = *cut_p;
+  float sum = 0.f;
+  int cnt = 0;
+  for (int k = 0; k < T; ++k) {
+    const int pi = lists[(long long)h * T + k];
+    if (pi < cut) {     // lists are sorted ascending: the valid entries come first
+      sum += points[(long long)pi * F + f];
+      ++cnt;
+    }
+  }
+  mean[t] = sum / (float)cnt;
+  if (f == 0) {
+    num_points[v] = cnt;
+    const int key = keys[h];
+    const int x = key % g.gx, y = (key / g.gx) % g.gy, z = key / (g.gx * g.gy);
+    coors[3 * v] = z;
+    coors[3 * v + 1] = y;
+    coors[3 * v + 2] = x;
+  }
+}
+
 int make_grid(const float* voxel_size, const float* range, Grid3* g) {
   g->vx = voxel_size[0];
   g->vy = voxel_size[1];
@@ -236,12 +272,15 @@ extern "C" int ddf_dynamic_voxelize(const float* points, int* coors, const float
   return DDF_OK;
 }
 
-extern "C" int ddf_hard_voxelize(const float* points, float* voxels, int* coors,
-                                 int* num_points_per_voxel, int* voxel_num,
-                                 const float* voxel_size_host, const float* coors_range_host,
-                                 int64_t num_points, int64_t num_features, int64_t max_points,
-                                 int64_t max_voxels, void* workspace, int64_t workspace_bytes,
-                                 void* stream_) {
+namespace {
+// voxels != NULL: the padded voxel tensor (reference contract); else mean != NULL: per-voxel mean of the first
+// mean_features point features (fused HardSimpleVFE)
+int hard_voxelize_impl(const float* points, float* voxels, float* mean, int64_t mean_features, int* coors,
+                       int* num_points_per_voxel, int* voxel_num,
+                       const float* voxel_size_host, const float* coors_range_host,
+                       int64_t num_points, int64_t num_features, int64_t max_points,
+                       int64_t max_voxels, void* workspace, int64_t workspace_bytes,
+                       void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Grid3 g;
   DDF_CHECK_ARG(voxel_size_host && coors_range_host, "hard_voxelize: null voxel_size/range");
@@ -255,7 +294,9 @@ extern "C" int ddf_hard_voxelize(const float* points, float* voxels, int* coors,
     DDF_CUDA(cudaMemsetAsync(voxel_num, 0, sizeof(int), stream));
     return DDF_OK;
   }
-  DDF_CHECK_ARG(points && voxels && coors && num_points_per_voxel, "hard_voxelize: null pointer");
+  DDF_CHECK_ARG(points && (voxels || mean) && coors && num_points_per_voxel, "hard_voxelize: null pointer");
+  DDF_CHECK_ARG(voxels || (mean_features > 0 && mean_features <= num_features),
+                "hard_voxelize_mean: need 0 < mean_features <= num_features");
   const int n = (int)num_points, F = (int)num_features, T = (int)max_points;
   VoxWs w = carve(workspace, n, T, (int)max_voxels);
   DDF_CHECK_ARG(workspace && (size_t)workspace_bytes >= w.bytes,
@@ -274,10 +315,43 @@ extern "C" int ddf_hard_voxelize(const float* points, float* voxels, int* coors,
                                                w.first_point, w.cut, voxel_num);
   // upper bound on voxels = min(n, max_voxels); threads beyond the device-side voxel_num exit
   const long long vmax = n < max_voxels ? n : max_voxels;
-  const long long total = vmax * T * F;
-  DDF_LAUNCH(vox_gather_kernel, (unsigned)ddf::cdiv(total, kThreads), kThreads, 0, stream, 
-      points, g, F, T, w.first_point, w.slot, w.keys, w.lists, w.cut, voxel_num, voxels, coors,
-      num_points_per_voxel, total);
+  if (voxels) {
+    const long long total = vmax * T * F;
+    DDF_LAUNCH(vox_gather_kernel, (unsigned)ddf::cdiv(total, kThreads), kThreads, 0, stream,
+        points, g, F, T, w.first_point, w.slot, w.keys, w.lists, w.cut, voxel_num, voxels, coors,
+        num_points_per_voxel, total);
+  } else {
+    const long long total = vmax * mean_features;
+    DDF_LAUNCH(vox_mean_kernel, (unsigned)ddf::cdiv(total, kThreads), kThreads, 0, stream,
+        points, g, F, T, (int)mean_features, w.first_point, w.slot, w.keys, w.lists, w.cut, voxel_num, mean, coors,
+        num_points_per_voxel, total);
+  }
   DDF_LAUNCH_CHECK();
   return DDF_OK;
+}
+}  // namespace
+
+extern "C" int ddf_hard_voxelize(const float* points, float* voxels, int* coors,
+                                 int* num_points_per_voxel, int* voxel_num,
+                                 const float* voxel_size_host, const float* coors_range_host,
+                                 int64_t num_points, int64_t num_features, int64_t max_points,
+                                 int64_t max_voxels, void* workspace, int64_t workspace_bytes,
+                                 void* stream_) {
+  DDF_CHECK_ARG(num_points == 0 || max_voxels == 0 || voxels != nullptr, "hard_voxelize: null voxels");
+  return hard_voxelize_impl(points, voxels, nullptr, 0, coors, num_points_per_voxel, voxel_num, voxel_size_host,
+                            coors_range_host, num_points, num_features, max_points, max_voxels, workspace,
+                            workspace_bytes, stream_);
+}
+
+// Hard voxelization fused with HardSimpleVFE: mean [max_voxels, mean_features] = mean over the (<= max_points)
+// points of each voxel of the first mean_features point features; the padded voxel tensor is never written.
+extern "C" int ddf_hard_voxelize_mean(const float* points, float* mean, int* coors, int* num_points_per_voxel,
+                                      int* voxel_num, const float* voxel_size_host, const float* coors_range_host,
+                                      int64_t num_points, int64_t num_features, int64_t mean_features,
+                                      int64_t max_points, int64_t max_voxels, void* workspace,
+                                      int64_t workspace_bytes, void* stream_) {
+  DDF_CHECK_ARG(num_points == 0 || max_voxels == 0 || mean != nullptr, "hard_voxelize_mean: null mean");
+  return hard_voxelize_impl(points, nullptr, mean, mean_features, coors, num_points_per_voxel, voxel_num,
+                            voxel_size_host, coors_range_host, num_points, num_features, max_points, max_voxels,
+                            workspace, workspace_bytes, stream_);
 }

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops import pointops as _pointops
 from ..ops.pointops import Points_Sampler, QueryAndGroup, gather_points
 
 
@@ -76,8 +77,12 @@ class _EncoderStack(nn.Module):
 
 
 def first_occurrence_scatter(attn_features, feats, idxs):
-    """attn_features (B, C, N) is updated IN PLACE: for every voxel that appears in ``idxs``
-    (B, np, ns), take the grouped feature of its first occurrence in flattened order."""
+    """For every voxel that appears in ``idxs`` (B, np, ns), take the grouped feature of its first occurrence in
+    flattened order; returns the updated (B, C, N) tensor. CUDA: two device kernels (atomicMin on the flattened
+    position, then a column gather; ops.pointops.scatter_first). Host tensors (the oracle-driven CPU path of the
+    tests): per-row scatter_reduce, updating ``attn_features`` in place like the reference."""
+    if attn_features.is_cuda:
+        return _pointops.scatter_first(attn_features, feats, idxs)
     B, C, N = attn_features.shape
     for b in range(B):
         idx_f = idxs[b].reshape(-1).long()
@@ -87,6 +92,7 @@ def first_occurrence_scatter(attn_features, feats, idxs):
         first.scatter_reduce_(0, idx_f, pos, reduce="amin", include_self=True)
         hit = first < idx_f.numel()
         attn_features[b][:, hit] = feat_f[:, first[hit]]
+    return attn_features
 
 
 class LocalTransformer(nn.Module):
@@ -113,7 +119,7 @@ class LocalTransformer(nn.Module):
 
     def scatter(self, attn_features, feats, idxs):
         if self.attn_feat_agg_method == "unique":
-            first_occurrence_scatter(attn_features, feats, idxs)
+            return first_occurrence_scatter(attn_features, feats, idxs)
         elif self.attn_feat_agg_method == "sum":
             B, C, N = attn_features.shape
             for b in range(B):
@@ -122,6 +128,7 @@ class LocalTransformer(nn.Module):
                 cnt = torch.bincount(idx_f, minlength=N)
                 nz = cnt > 0
                 attn_features[b][:, nz] = (attn_features[b][:, nz] + summed[:, nz]) / cnt[nz]
+            return attn_features
         else:
             raise NotImplementedError(self.attn_feat_agg_method)
 
@@ -136,11 +143,10 @@ class LocalTransformer(nn.Module):
         tokens = input_features.permute(0, 2, 1, 3).reshape(-1, D, ns).permute(2, 0, 1)
         transformed = self.chunk(tokens).permute(1, 2, 0).reshape(B, n_p, D, ns).transpose(1, 2)
         if self.feat_agg_method == "replace":
-            features = features.clone() if features.requires_grad else features
-            self.scatter(features, transformed, group_idx)
+            features = features.clone() if (features.requires_grad and not features.is_cuda) else features
+            features = self.scatter(features, transformed, group_idx)
         elif self.feat_agg_method == "sum":
-            attn_features = torch.zeros_like(features)
-            self.scatter(attn_features, transformed, group_idx)
+            attn_features = self.scatter(torch.zeros_like(features), transformed, group_idx)
             features = features + attn_features
         else:
             raise NotImplementedError(self.feat_agg_method)

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "ddf_msda_tile_backward": [c_ptr] * 9 + [c_i64] * 6 + [c_ptr],
     "ddf_hard_voxelize_workspace_bytes": [c_i64] * 3,
     "ddf_hard_voxelize": [c_ptr] * 7 + [c_i64] * 4 + [c_ptr, c_i64, c_ptr],
+    "ddf_hard_voxelize_mean": [c_ptr] * 7 + [c_i64] * 5 + [c_ptr, c_i64, c_ptr],
     "ddf_dynamic_voxelize": [c_ptr] * 4 + [c_i64] * 2 + [c_ptr],
     "ddf_indice_pairs_workspace_bytes": [c_i64, c_i64] + [c_ptr] * 6 + [c_int],
     "ddf_subm_indice_pairs": [c_ptr, c_i64, c_i64] + [c_ptr] * 8 + [c_i64, c_ptr],
@@ -51,6 +52,11 @@ _SIGNATURES = {
     "ddf_group_points_grad": [c_ptr] * 3 + [c_i64] * 5 + [c_ptr],
     "ddf_gather_points": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
     "ddf_gather_points_grad": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
+    "ddf_first_occurrence": [c_ptr, c_ptr] + [c_i64] * 3 + [c_ptr],
+    "ddf_scatter_first": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
+    "ddf_scatter_first_grad": [c_ptr] * 4 + [c_i64] * 4 + [c_ptr],
+    "ddf_sparse_to_bev_nhwc_bf16": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
+    "ddf_bev_nhwc_bf16_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_sparse_bn_workspace_bytes": [c_i64],
     "ddf_sparse_bn_forward": [c_ptr] * 9 + [c_i64, c_i64, c_int, c_f32, c_f32, c_int, c_ptr, c_ptr],
     "ddf_sparse_bn_backward": [c_ptr] * 10 + [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr],

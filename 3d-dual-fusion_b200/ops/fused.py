@@ -64,8 +64,12 @@ def ffn_hidden(linear, dropout, x):
         _lib.require_cuda(x)
         return dropout(F.relu(linear(x)))
     h = F.linear(x, linear.weight)           # fresh tensor: safe to overwrite in place
+    if h.dtype != torch.float32 or (linear.bias is not None and linear.bias.dtype != torch.float32):
+        # e.g. under torch.autocast the GEMM returns half precision: the fp32 kernels must not see it
+        h = h if linear.bias is None else h + linear.bias.to(h.dtype)
+        return dropout(F.relu(h))
     p = dropout.p if dropout.training else 0.0
-    return _BiasReluDropout.apply(h, linear.bias, p)
+    return _BiasReluDropout.apply(h.contiguous(), linear.bias, p)
 
 
 class _AddDropoutLayerNorm(Function):
@@ -115,7 +119,9 @@ def add_dropout_layer_norm(norm, dropout, a, b):
     """``norm(a + dropout(b))`` with ``norm`` an ``nn.LayerNorm`` over the last dim."""
     C = a.shape[-1]
     if (a.dtype != torch.float32 or C not in (128, 256, 512) or not norm.elementwise_affine
-            or norm.bias is None or tuple(norm.normalized_shape) != (C,)):
+            or norm.bias is None or tuple(norm.normalized_shape) != (C,)
+            or (b is not None and (b.dtype != torch.float32 or b.shape != a.shape))
+            or norm.weight.dtype != torch.float32 or norm.bias.dtype != torch.float32):
         _lib.require_cuda(a)
         return norm(a + dropout(b))
     p = dropout.p if (dropout is not None and dropout.training) else 0.0

@@ -8,6 +8,7 @@ from typing import List
 import torch
 from torch import nn
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from .. import lib as _lib
 
@@ -122,6 +123,50 @@ class GatherPoints(Function):
 
 
 gather_points = GatherPoints.apply
+
+
+class ScatterFirst(Function):
+    """LocalTransformer.scatter with the 'unique' rule as device kernels: ``features`` (B, C, N) with the columns of
+    every voxel that occurs in ``idx`` (B, npoint, nsample) replaced by ``feats`` (B, C, npoint, nsample) at the
+    voxel's first occurrence in flattened order. Returns a new tensor (the reference overwrites in place)."""
+
+    @staticmethod
+    def forward(ctx, features, feats, idx):
+        _lib.require_cuda(features, feats, idx)
+        B, C, N = features.shape
+        E = idx.shape[1] * idx.shape[2]
+        feats = feats.contiguous().view(B, C, E)
+        idx = idx.contiguous()
+        if features.dtype != torch.float32 or feats.dtype != torch.float32 or idx.dtype != torch.int32:
+            raise RuntimeError("scatter_first: float32 features / int32 indices only")
+        out = features.clone(memory_format=torch.contiguous_format)
+        first = torch.empty((B, N), dtype=torch.int32, device=features.device)
+        L = _lib.get_lib()
+        with torch.cuda.device(features.device):
+            rc = L.ddf_first_occurrence(_lib.ptr(idx), _lib.ptr(first), B, N, E, _lib.current_stream())
+            _lib.check(rc, "first_occurrence")
+            rc = L.ddf_scatter_first(_lib.ptr(feats), _lib.ptr(first), _lib.ptr(out), B, C, N, E, _lib.current_stream())
+        _lib.check(rc, "scatter_first")
+        ctx.save_for_backward(first)
+        ctx.dims = (B, C, N, E, idx.shape[1], idx.shape[2])
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (first,) = ctx.saved_tensors
+        B, C, N, E, npoint, nsample = ctx.dims
+        grad_out = grad_out.contiguous()
+        g_feats = torch.empty((B, C, E), dtype=grad_out.dtype, device=grad_out.device)
+        g_features = torch.empty_like(grad_out)
+        with torch.cuda.device(grad_out.device):
+            rc = _lib.get_lib().ddf_scatter_first_grad(_lib.ptr(grad_out), _lib.ptr(first), _lib.ptr(g_feats),
+                                                       _lib.ptr(g_features), B, C, N, E, _lib.current_stream())
+        _lib.check(rc, "scatter_first_grad")
+        return g_features, g_feats.view(B, C, npoint, nsample), None
+
+
+scatter_first = ScatterFirst.apply
 
 
 class DFPS_Sampler(nn.Module):

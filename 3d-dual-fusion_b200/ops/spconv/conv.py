@@ -97,6 +97,9 @@ class SparseConvolution(SparseModule):
             rb = ops.build_rulebook(input.indices, input.batch_size, input.spatial_shape,
                                     self.kernel_size, self.stride, self.padding, self.dilation,
                                     self.output_padding, self.subm, self.transposed, with_pairs=need_pairs)
+            # the auto key holds indices.data_ptr(): keep that tensor alive as long as the cached rulebook, or a freed
+            # and re-allocated buffer with the same address / row count would hit a stale entry
+            rb.key_indices = input.indices
             input.indice_dict[("__rulebook__", key)] = rb
             if self.indice_key is not None:  # the reference's 5-tuple, for code that reads it
                 input.indice_dict[self.indice_key] = _IndiceTuple(rb, input.indices, input.spatial_shape)

@@ -42,7 +42,7 @@ class Rulebook(object):
     """Reference-format rulebook + the row-major tables of the fused kernels. For SubM layers whose
     three conv kernels all walk the tables the pair lists are built only when somebody reads them."""
     __slots__ = ("outids", "_pairs", "_num", "gather_table", "scatter_table", "out_spatial_shape", "subm",
-                 "kvol", "_build_pairs")
+                 "kvol", "_build_pairs", "key_indices")
 
     def __init__(self, outids, indice_pairs, indice_pair_num, gather_table, scatter_table,
                  out_spatial_shape, kvol=None, build_pairs=None):
@@ -55,6 +55,7 @@ class Rulebook(object):
         self.subm = False
         self.kvol = kvol if kvol is not None else indice_pairs.shape[0]
         self._build_pairs = build_pairs
+        self.key_indices = None     # input indices the cache key was derived from (kept alive by SparseConvolution)
 
     def _ensure_pairs(self):
         if self._pairs is None:

@@ -41,6 +41,41 @@ class _ToDense(Function):
         return gfeat, None, None, None
 
 
+class _ToBevNhwcBf16(Function):
+    """[N, C] fp32 rows -> the BEV map [B, C*D, H, W] in bf16 with channels-last storage, one kernel
+    (ddf_sparse_to_bev_nhwc_bf16); backward gathers the bf16 gradient back into fp32 rows."""
+
+    @staticmethod
+    def forward(ctx, features, indices, spatial_shape, batch_size):
+        _lib.require_cuda(features, indices)
+        features = features.contiguous()
+        if features.dtype != torch.float32:
+            raise RuntimeError("dense_bev_bf16(): float32 features only")
+        n, C = features.shape
+        D, H, W = [int(s) for s in spatial_shape]
+        out = torch.empty((batch_size, C * D, H, W), dtype=torch.bfloat16, device=features.device,
+                          memory_format=torch.channels_last)
+        with torch.cuda.device(features.device):
+            rc = _lib.get_lib().ddf_sparse_to_bev_nhwc_bf16(_lib.ptr(features), _lib.ptr(indices), _lib.ptr(out),
+                                                            n, C, batch_size, D, H, W, _lib.current_stream())
+        _lib.check(rc, "sparse_to_bev_nhwc_bf16")
+        ctx.save_for_backward(indices)
+        ctx.dims = (n, C, batch_size, D, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (indices,) = ctx.saved_tensors
+        n, C, B, D, H, W = ctx.dims
+        grad_out = grad_out.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gfeat = torch.empty((n, C), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            rc = _lib.get_lib().ddf_bev_nhwc_bf16_to_sparse(_lib.ptr(grad_out), _lib.ptr(indices), _lib.ptr(gfeat),
+                                                            n, C, B, D, H, W, _lib.current_stream())
+        _lib.check(rc, "bev_nhwc_bf16_to_sparse")
+        return gfeat, None, None, None
+
+
 def scatter_nd(indices, updates, shape):
     """Same contract as structure.py:5-18 (index-put into zeros), kept for API parity; the hot
     path (SparseConvTensor.dense) uses the fused kernel instead."""
@@ -85,6 +120,13 @@ class SparseConvTensor(object):
         if channels_first:
             return res
         return res.permute(0, 2, 3, 4, 1).contiguous()
+
+    def dense_bev_bf16(self):
+        """``dense().view(B, C*D, H, W)`` for a bf16 channels-last 2-D backbone: same values rounded to bf16, written
+        directly in channels-last storage (no fp32 NCDHW tensor, no permute)."""
+        if len(self.spatial_shape) != 3:
+            raise RuntimeError("dense_bev_bf16(): 3-D sparse tensors only")
+        return _ToBevNhwcBf16.apply(self.features, self.indices, self.spatial_shape, self.batch_size)
 
     @property
     def sparity(self):

@@ -71,6 +71,32 @@ def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors
                                     coors_range, max_points, max_voxels).item())
 
 
+def hard_voxelize_mean(points, voxel_size, coors_range, max_points, max_voxels, num_features):
+    """Hard voxelization fused with ``HardSimpleVFE``: returns (mean [M, num_features], coors [M, 3], num_points [M])
+    without materialising the padded [M, max_points, F] voxel tensor (one D2H read of the voxel count, like
+    ``hard_voxelize``)."""
+    points = _check_points(points)
+    L = _lib.get_lib()
+    n, f = points.shape
+    cap = min(int(max_voxels), n)
+    mean = points.new_empty((cap, int(num_features)))
+    coors = points.new_empty((cap, 3), dtype=torch.int)
+    num = points.new_empty((cap,), dtype=torch.int)
+    ws_bytes = L.ddf_hard_voxelize_workspace_bytes(n, max_points, cap)
+    if ws_bytes < 0:
+        raise RuntimeError("hard_voxelize_mean: bad sizes")
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=points.device)
+    voxel_num = torch.empty(1, dtype=torch.int32, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = L.ddf_hard_voxelize_mean(
+            _lib.ptr(points), _lib.ptr(mean), _lib.ptr(coors), _lib.ptr(num), _lib.ptr(voxel_num),
+            _f32_array(voxel_size, 3), _f32_array(coors_range, 6), n, f, int(num_features), int(max_points), cap,
+            _lib.ptr(ws), int(ws_bytes), _lib.current_stream())
+    _lib.check(rc, "hard_voxelize_mean")
+    m = int(voxel_num.item())
+    return mean[:m], coors[:m], num[:m]
+
+
 class _Voxelization(Function):
     """Drop-in for voxelize.py:11-58."""
 
@@ -117,6 +143,12 @@ class Voxelization(nn.Module):
         max_voxels = self.max_voxels[0] if self.training else self.max_voxels[1]
         return voxelization(input, self.voxel_size, self.point_cloud_range, self.max_num_points,
                             max_voxels)
+
+    def forward_mean(self, input, num_features):
+        """``HardSimpleVFE(num_features)(*self(input))`` as one pass (ddf_hard_voxelize_mean)."""
+        max_voxels = self.max_voxels[0] if self.training else self.max_voxels[1]
+        return hard_voxelize_mean(input, self.voxel_size, self.point_cloud_range, self.max_num_points, max_voxels,
+                                  num_features)
 
     def __repr__(self):
         tmpstr = self.__class__.__name__ + '('

@@ -122,6 +122,15 @@ int ddf_hard_voxelize(const float* points, float* voxels, int* coors, int* num_p
                       int64_t num_points, int64_t num_features, int64_t max_points,
                       int64_t max_voxels, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Hard voxelization fused with HardSimpleVFE (TransFusion/mmdet3d/models/voxel_encoders/voxel_encoder.py:27-44):
+ * mean [max_voxels, mean_features] float32 = sum of the first mean_features features over the voxel's points (list
+ * order) / num_points; same coors / num_points / voxel_num / order contract as ddf_hard_voxelize, the padded
+ * [max_voxels, max_points, F] tensor is never materialised. */
+int ddf_hard_voxelize_mean(const float* points, float* mean, int* coors, int* num_points_per_voxel, int* voxel_num,
+                           const float* voxel_size_host, const float* coors_range_host, int64_t num_points,
+                           int64_t num_features, int64_t mean_features, int64_t max_points, int64_t max_voxels,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 int ddf_dynamic_voxelize(const float* points, int* coors, const float* voxel_size_host,
                          const float* coors_range_host, int64_t num_points, int64_t num_features,
                          void* stream);
@@ -252,6 +261,14 @@ int ddf_dense_to_sparse(const float* grad_dense, const int* indices, float* grad
                         int64_t n, int64_t C, int64_t B, int64_t D, int64_t H, int64_t W,
                         void* stream);
 
+/* BEV hand-off to a bf16 channels-last 2-D backbone (the step after the path: sparse_encoder.py:366-367 ->
+ * backbones/second.py): out = bf16 [B, H, W, C*D], the channels-last storage of the logical [B, C*D, H, W] map
+ * (channel c*D + z), zeroed inside; the backward gathers a bf16 gradient of the same layout into fp32 rows. */
+int ddf_sparse_to_bev_nhwc_bf16(const float* features, const int* indices, void* out, int64_t n, int64_t C,
+                                int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
+int ddf_bev_nhwc_bf16_to_sparse(const void* grad_dense, const int* indices, float* grad_features, int64_t n,
+                                int64_t C, int64_t B, int64_t D, int64_t H, int64_t W, void* stream);
+
 /* ---- Point-set ops of the 3D local self-attention (LocalTransformer) ---------------------
  * Replace furthest_point_sample_ext / ball_query_ext / group_points_ext / gather_points_ext
  *   reference: <proj>/ops/furthest_point_sample/src/furthest_point_sample.cpp (wrapper),
@@ -282,6 +299,17 @@ int ddf_gather_points(const float* points, const int* idx, float* out, int64_t B
                       int64_t N, int64_t npoints, void* stream);
 int ddf_gather_points_grad(const float* grad_out, const int* idx, float* grad_points, int64_t B,
                            int64_t C, int64_t N, int64_t npoints, void* stream);
+
+/* LocalTransformer.scatter, 'unique' aggregation (<proj>/models/model_utils/pointformer.py:319-347): every voxel
+ * takes the grouped feature of its FIRST occurrence in flattened (group, slot) order.
+ *   ddf_first_occurrence: idx [B, E] (E = npoint*nsample, values in [0, N)) -> first [B, N] (E where never hit)
+ *   ddf_scatter_first:    inout [B, C, N]: hit columns replaced by feats [B, C, E][:, first]
+ *   ddf_scatter_first_grad: grad_feats [B, C, E] (zeroed inside), grad_features [B, C, N] (0 at hit columns) */
+int ddf_first_occurrence(const int* idx, int* first, int64_t B, int64_t N, int64_t E, void* stream);
+int ddf_scatter_first(const float* feats, const int* first, float* inout, int64_t B, int64_t C, int64_t N,
+                      int64_t E, void* stream);
+int ddf_scatter_first_grad(const float* grad_out, const int* first, float* grad_feats, float* grad_features,
+                           int64_t B, int64_t C, int64_t N, int64_t E, void* stream);
 
 /* ---- BatchNorm1d over sparse-voxel features [N, C], fused with the residual add and ReLU -----------
  * Replaces the elementwise chain conv -> BN1d -> [+ identity] -> ReLU of the reference's sparse

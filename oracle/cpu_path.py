@@ -71,6 +71,13 @@ def cpu_voxelization(points, voxel_size, coors_range, max_points=35, max_voxels=
     return torch.from_numpy(v), torch.from_numpy(c), torch.from_numpy(n)
 
 
+def cpu_hard_voxelize_mean(points, voxel_size, coors_range, max_points, max_voxels, num_features):
+    """Reference voxelization followed by the reference's HardSimpleVFE arithmetic (voxel_encoder.py:42-44)."""
+    v, c, n = cpu_voxelization(points, voxel_size, coors_range, max_points, max_voxels)
+    mean = v[:, :, :num_features].sum(dim=1, keepdim=False) / n.type_as(v).view(-1, 1)
+    return mean.contiguous(), c, n
+
+
 # ---- sparse conv -------------------------------------------------------------------------------
 class _CpuRulebook(object):
     def __init__(self, outids, pairs, num, out_shape):
@@ -228,6 +235,7 @@ def reference_cpu_ops():
              (m_conv.Fsp, "table_conv", m_conv.Fsp.table_conv),
              (m_struct.SparseConvTensor, "dense", m_struct.SparseConvTensor.dense),
              (m_voxel, "voxelization", m_voxel.voxelization),
+             (m_voxel, "hard_voxelize_mean", m_voxel.hard_voxelize_mean),
              (m_norm, "batch_norm_act", m_norm.batch_norm_act),
              (m_fused, "ffn_hidden", m_fused.ffn_hidden),
              (m_fused, "add_dropout_layer_norm", m_fused.add_dropout_layer_norm),
@@ -242,6 +250,7 @@ def reference_cpu_ops():
         m_conv.Fsp.table_conv = _cpu_table_conv
         m_struct.SparseConvTensor.dense = _cpu_dense
         m_voxel.voxelization = cpu_voxelization
+        m_voxel.hard_voxelize_mean = cpu_hard_voxelize_mean
         m_norm.batch_norm_act = _cpu_batch_norm_act
         m_fused.ffn_hidden = _cpu_ffn_hidden
         m_fused.add_dropout_layer_norm = _cpu_add_dropout_layer_norm

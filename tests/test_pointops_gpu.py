@@ -98,3 +98,32 @@ def test_local_transformer_matches_oracle_cpu_path():
     # voxels outside every ball keep their input feature (feat_agg_method='replace')
     untouched = (out == feats.permute(0, 2, 1)).all(-1)
     assert bool(untouched.any()) and not bool(untouched.all())
+
+
+def test_scatter_first_occurrence_kernel_matches_reference_rule():
+    """LocalTransformer.scatter 'unique' rule (pointformer.py:319-347): first occurrence in flattened (group, slot)
+    order wins; forward and backward against the host implementation (which reproduces the reference's
+    unique + flip + scatter_ result on the CPU)."""
+    from ddf_b200.fusion.pointformer import first_occurrence_scatter
+    from ddf_b200.ops import pointops
+    torch.manual_seed(0)
+    B, C, N, npnt, ns = 3, 16, 500, 64, 8
+    idx = torch.randint(0, N // 2, (B, npnt, ns), dtype=torch.int32)          # duplicates; the upper half is never hit
+    idx[0, 0, :] = torch.tensor([5, 3, 5, 7, 3, 3, 9, 5], dtype=torch.int32)  # SURVEY 3.3 example
+    feats = torch.randn(B, C, npnt, ns)
+    base = torch.randn(B, C, N)
+    ref_base = base.clone().requires_grad_()
+    ref_feats = feats.clone().requires_grad_()
+    ref = first_occurrence_scatter(ref_base.clone(), ref_feats, idx)
+    g = torch.randn(B, C, N)
+    ref.backward(g)
+    d_base = base.cuda().requires_grad_()
+    d_feats = feats.cuda().requires_grad_()
+    out = pointops.scatter_first(d_base, d_feats, idx.cuda())
+    out.backward(g.cuda())
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    assert torch.equal(d_base.grad.cpu(), ref_base.grad) and torch.equal(d_feats.grad.cpu(), ref_feats.grad)
+    # the worked example: voxels 5, 3, 7, 9 take flattened positions 0, 1, 3, 6 of group 0
+    for v, pos in ((5, 0), (3, 1), (7, 3), (9, 6)):
+        assert torch.equal(out[0, :, v].cpu(), feats[0, :, 0, pos])
+    assert torch.equal(d_base.detach().cpu(), base)   # input not modified

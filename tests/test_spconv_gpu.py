@@ -313,3 +313,21 @@ def test_tile_schedules_agree_across_kernels(n_side, chan):
         L.ddf_set_tensor_cores(prev)
     for a, b, tol in ((out, out_ref, 1e-5), (gin, gin_ref, 1e-5), (gw, gw_ref, 1e-4)):
         assert float((a - b).abs().max()) <= tol * float(b.abs().max())
+
+
+def test_bev_bf16_channels_last_handoff():
+    """dense_bev_bf16() == dense().view(B, C*D, H, W) rounded to bf16, stored channels-last; backward gathers."""
+    import ddf_b200.ops.spconv as sp
+    shape = [2, 18, 20]
+    idx = random_voxels(400, 3, shape, seed=5)
+    feat = torch.randn(len(idx), 128, device="cuda", requires_grad=True)
+    x = sp.SparseConvTensor(feat, torch.from_numpy(idx).cuda(), shape, 3)
+    bev = x.dense_bev_bf16()
+    assert bev.dtype == torch.bfloat16 and bev.shape == (3, 256, 18, 20)
+    assert bev.is_contiguous(memory_format=torch.channels_last)
+    ref = x.dense().view(3, 256, 18, 20)
+    assert torch.equal(bev.float(), ref.detach().bfloat16().float())
+    g = torch.randn(3, 256, 18, 20, device="cuda").bfloat16()
+    bev.backward(g)
+    g_ref, = torch.autograd.grad(ref, feat, g.float())
+    assert torch.equal(feat.grad, g_ref)

@@ -82,3 +82,20 @@ def test_full_size_properties_200k():
 def test_empty_input():
     v, c, n = run_cuda(np.zeros((0, 5), np.float32), synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 100)
     assert v.shape == (0, 10, 5) and c.shape == (0, 3) and n.shape == (0,)
+
+
+@pytest.mark.parametrize("n,max_voxels", [(30000, 120000), (262144, 120000), (5000, 700)])
+def test_fused_vfe_mean_matches_voxelize_then_hard_simple_vfe(n, max_voxels):
+    """ddf_hard_voxelize_mean (a-2 fused into the a-1 epilogue) == oracle voxelization followed by the reference's
+    HardSimpleVFE arithmetic (voxel_encoder.py:42-44); coors / counts / order bit-exact, means to fp32 rounding."""
+    from ddf_b200.ops.voxel import hard_voxelize_mean
+    from oracle import voxel
+    pts = synth.lidar_points(n, seed=11)
+    mean, c, cnt = hard_voxelize_mean(torch.from_numpy(pts).cuda(), synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, max_voxels, 5)
+    ov, oc, on = voxel.hard_voxelize(pts, synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, max_voxels)
+    assert np.array_equal(c.cpu().numpy(), oc) and np.array_equal(cnt.cpu().numpy(), on)
+    ref = torch.from_numpy(ov)[:, :, :5].sum(dim=1) / torch.from_numpy(on).float().view(-1, 1)
+    assert mean.shape == ref.shape
+    assert float((mean.cpu() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    empty = hard_voxelize_mean(torch.zeros(0, 5).cuda(), synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, 100, 5)
+    assert empty[0].shape == (0, 5) and empty[1].shape == (0, 3)
