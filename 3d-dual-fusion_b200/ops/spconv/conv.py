@@ -93,7 +93,10 @@ class SparseConvolution(SparseModule):
         if rb is None:
             kvol = int(np.prod(self.kernel_size))
             # SubM layers whose wgrad walks the gather table never read the pair lists
-            need_pairs = not (self.subm and ops.tc_mode(kvol, self.in_channels, self.out_channels) & 8)
+            # (host tensors only occur in the oracle-driven CPU path of the tests / the reference arm of bench.py, which
+            # must not touch the CUDA library)
+            need_pairs = not (self.subm and input.indices.is_cuda
+                              and ops.tc_mode(kvol, self.in_channels, self.out_channels) & 8)
             rb = ops.build_rulebook(input.indices, input.batch_size, input.spatial_shape,
                                     self.kernel_size, self.stride, self.padding, self.dilation,
                                     self.output_padding, self.subm, self.transposed, with_pairs=need_pairs)

@@ -30,10 +30,7 @@ import torch  # noqa: E402
 
 METRIC = "TransFusion-L+3D-DF hot path fwd+bwd samples/sec"
 UNIT = "samples/s"
-BATCH_PER_GPU = 2
-POINTS_PER_SAMPLE = 260000   # nuScenes 10-sweep cloud
 N_CAM = 6
-FEAT_HW = (112, 200)         # FPN level 0 of a 448x800 input
 
 
 def parse():
@@ -42,32 +39,227 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="tf", choices=sorted(WORKLOADS),
+                    help="tf = BASELINE configs[2] (the headline: what N=1 and the scaling run measure); cp / cp_pfatv2 = "
+                         "configs[1] (CenterPoint hybrid+IFAT / its ACTRv2 variant); kitti = configs[3]; dense200k = configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp32-gemm", action="store_true",
                     help="keep the library GEMMs (nn.Linear / 1x1 conv) in full fp32 instead of tf32")
     return ap.parse_args()
 
 
-def workload_config(n_gpus):
-    return {
-        "workload": "TransFusion-L+3D-DF (transfusion_nusc_voxel_F) hot path: voxelize+VFE+SparseEncoderFusion"
-                    "(ACTR hybrid, 2 enc layers)+dense BEV, fwd+bwd+clip+AdamW",
-        "per_gpu_batch": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
-        "points_per_sample": POINTS_PER_SAMPLE, "cams": N_CAM, "cam_feat": [256, *FEAT_HW],
-        "sparse_shape": [41, 1440, 1440], "parallelism": "dp%d" % n_gpus,
-        "l2": "inputs larger than L2 (285 MB of points + camera features per step)",
-    }
+# ---- workloads: BASELINE.json configs as (model, synthetic host batch, forward) -------------------------------
+class Workload(object):
+    """One BASELINE config. ``host_batch`` returns (tensors: dict name -> CPU tensor or list of tensors, static: any)
+    - the tensors are what a step copies host->device end to end; ``forward`` maps (model, device tensors, static)
+    to the tensor the loss is taken of."""
+    name = batch = points = None
+    metric = METRIC
+
+    def describe(self, n_gpus):
+        raise NotImplementedError
+
+    def build(self, device):
+        raise NotImplementedError
+
+    def host_batch(self, rank, batch=None):
+        raise NotImplementedError
+
+    def forward(self, model, t, static):
+        raise NotImplementedError
 
 
-def build_model(device):
-    import configs
-    import ddf_b200.fusion.point_fusion  # noqa: F401  (registers FUSION_LAYERS['ACTR'])
-    import ddf_b200.fusion.sparse_encoder  # noqa: F401
-    import ddf_b200.fusion.voxel_encoder  # noqa: F401
+class TransFusionWorkload(Workload):
+    """configs[2]: TransFusion-L + 3D-DF (transfusion_nusc_voxel_F), bs 2 / GPU."""
+    name, batch, points, feat_hw, uniform = "tf", 2, 260000, (112, 200), False
+
+    def describe(self, n_gpus):
+        return {
+            "workload": "TransFusion-L+3D-DF (transfusion_nusc_voxel_F) hot path: voxelize+VFE+SparseEncoderFusion"
+                        "(ACTR hybrid, 2 enc layers)+dense BEV, fwd+bwd+clip+AdamW",
+            "per_gpu_batch": self.batch, "global_batch": self.batch * n_gpus,
+            "points_per_sample": self.points, "cams": N_CAM, "cam_feat": [256, *self.feat_hw],
+            "sparse_shape": [41, 1440, 1440], "parallelism": "dp%d" % n_gpus,
+            "l2": "inputs larger than L2 (%d MB of points + camera features per step)"
+                  % ((self.batch * (self.points * 20 + N_CAM * 256 * self.feat_hw[0] * self.feat_hw[1] * 4)) // 1000000),
+        }
+
+    def build(self, device):
+        import configs
+        import ddf_b200.fusion.point_fusion  # noqa: F401  (registers FUSION_LAYERS['ACTR'])
+        import ddf_b200.fusion.sparse_encoder  # noqa: F401
+        import ddf_b200.fusion.voxel_encoder  # noqa: F401
+        from ddf_b200.fusion.detector import TransFusionPtsBranch
+        torch.manual_seed(0)
+        return TransFusionPtsBranch(**configs.transfusion_f()).to(device).train()
+
+    def host_batch(self, rank, batch=None):
+        import synth
+        batch = batch or self.batch
+        if self.uniform:
+            pts = [torch.from_numpy(synth.uniform_points(self.points, synth.NUSC_RANGE, seed=1000 * rank + b))
+                   for b in range(batch)]
+        else:
+            pts = [torch.from_numpy(synth.lidar_points(self.points, seed=1000 * rank + b)) for b in range(batch)]
+        feats = torch.from_numpy(synth.camera_features(batch, N_CAM, self.feat_hw, seed=rank))
+        return {"pts": pts, "feats": feats}, [synth.nusc_img_meta(N_CAM) for _ in range(batch)]
+
+    def forward(self, model, t, metas):
+        return model(t["pts"], [t["feats"]], metas)
+
+
+class Dense200kWorkload(TransFusionWorkload):
+    """configs[4]: the TransFusion-L + 3D-DF stack on a 200k-point dense (uniform, no duplicate cells) sweep, bs 1 /
+    GPU. The reference has no Swin-T code or config (README 'TBD'): camera features are synthetic 256-channel maps."""
+    name, batch, points, uniform = "dense200k", 1, 200000, True
+
+    def describe(self, n_gpus):
+        d = super().describe(n_gpus)
+        d["workload"] = "TransFusion-L+3D-DF hot path on a 200k-point dense sweep (uniform points: worst case for the " \
+                        "voxel hash / rulebooks), bs 1/GPU, fwd+bwd+clip+AdamW"
+        return d
+
+
+class CenterPointWorkload(Workload):
+    """configs[1]: CenterPoint + 3D-DF (nusc_centerpoint_voxelnet_0075voxel_fix_bn_z_multimodal_pfat_hybrid7_ifat.py),
+    bs 4: GPU voxelization + mean VFE (the reference voxelizes in the data loader), SpMiddleResNetFHDFusion with
+    VoxelWithPointProjection (hybrid dual-query encoder + IFAT gate), DeepLabV3-layer1-shaped camera features."""
+    name, batch, points, feat_hw, v2 = "cp", 4, 260000, (150, 267), False
+
+    def describe(self, n_gpus):
+        return {"workload": "CenterPoint+3D-DF hot path: voxelize+mean VFE+SpMiddleResNetFHDFusion+VoxelWithPointProjection("
+                            + ("lidar modal, ACTRv2 = 3D local self-attention live" if self.v2 else "hybrid encoder + IFAT gate")
+                            + ")+dense BEV, fwd+bwd+clip+AdamW",
+                "per_gpu_batch": self.batch, "global_batch": self.batch * n_gpus, "points_per_sample": self.points,
+                "cams": N_CAM, "cam_feat": [256, *self.feat_hw], "sparse_shape": [41, 1440, 1440],
+                "parallelism": "dp%d" % n_gpus, "l2": "inputs larger than L2"}
+
+    def build(self, device):
+        import synth
+        from ddf_b200.fusion.centerpoint import SpMiddleResNetFHDFusion, VoxelWithPointProjection
+        from ddf_b200.ops.voxel import Voxelization
+        depth_thres = {"CAM_FRONT": 1, "CAM_FRONT_LEFT": 0, "CAM_FRONT_RIGHT": 0, "CAM_BACK": 0.5, "CAM_BACK_LEFT": 0,
+                       "CAM_BACK_RIGHT": 0}
+        torch.manual_seed(0)
+        common = dict(image_scale=2.0 / 3, depth_thres=depth_thres)
+        if self.v2:   # ..._pfatv2.py:75-90
+            fuse = VoxelWithPointProjection(
+                "pfat", False, synth.NUSC_VOXEL, synth.NUSC_RANGE, synth.CP_CAMS, model_name="ACTRv2",
+                pfat_cfg=dict(fusion_method="sum", num_bins=80, num_channels=[256], query_num_feat=128, num_enc_layers=1,
+                              max_num_ne_voxel=26000, pos_encode_method="depth"),
+                lt_cfg=dict(npoint=2048, radius=2.0, nsample=32, num_layers=1, attn_feat_agg_method="unique",
+                            feat_agg_method="replace"), **common)
+        else:         # ..._pfat_hybrid7_ifat.py:86-108
+            fuse = VoxelWithPointProjection(
+                "pfat", False, synth.NUSC_VOXEL, synth.NUSC_RANGE, synth.CP_CAMS,
+                pfat_cfg=dict(fusion_method="sum", feature_modal="hybrid",
+                              hybrid_cfg=dict(attn_layer="BiGateSum1D_2", q_method="sum", q_rep_place=["weight"]),
+                              num_channels=[256], query_num_feat=128, num_enc_layers=1, max_num_ne_voxel=26000,
+                              pos_encode_method="depth"),
+                ifat_cfg=dict(fusion_method="Basicgate_patch_iv_multivoxel", img_num_channel=256, pts_num_channel=128,
+                              voxel_feat_channel=[32, 64, 128], voxel_idx=[0, 2]), **common)
+        m = torch.nn.ModuleDict(dict(vox=Voxelization(synth.NUSC_VOXEL, synth.NUSC_RANGE, 10, (120000, 160000)),
+                                     backbone=SpMiddleResNetFHDFusion(num_input_features=5), fuse=fuse))
+        return m.to(device).train()
+
+    def host_batch(self, rank, batch=None):
+        import synth
+        batch = batch or self.batch
+        bd = synth.centerpoint_batch(batch, feat_hw=self.feat_hw, seed=rank)
+        t = {"pts": [torch.from_numpy(synth.lidar_points(self.points, seed=1000 * rank + b)) for b in range(batch)]}
+        for cam, f in bd["img_feat"]["layer1_ori_feat2d"].items():
+            t["img:" + cam] = f
+        return t, {"calib": bd["calib"], "image_shape": bd["image_shape"]}
+
+    def forward(self, m, t, static):
+        import torch.nn.functional as F
+        from ddf_b200.ops import voxel as vops
+        dev = t["pts"][0].device
+        feats, coors = [], []
+        for b, p in enumerate(t["pts"]):
+            if p.is_cuda:
+                f, c, _ = m["vox"].forward_mean(p, 5)
+            else:   # the reference arm: oracle-patched ops
+                f, c, _ = vops.hard_voxelize_mean(p, m["vox"].voxel_size, m["vox"].point_cloud_range, 10, 120000, 5)
+            feats.append(f)
+            coors.append(F.pad(c, (1, 0), value=b))
+        key = "_dev_static_%s" % dev
+        if key not in static:
+            static[key] = {k: {kk: vv.to(dev) for kk, vv in v.items()} for k, v in static.items() if not k.startswith("_")}
+        bd = dict(static[key], img_feat={"layer1_ori_feat2d": {k[4:]: v for k, v in t.items() if k.startswith("img:")}})
+        out, _ = m["backbone"](torch.cat(feats), bd, torch.cat(coors), len(t["pts"]), [1440, 1440, 40], {},
+                               fuse_func=m["fuse"])
+        return out
+
+
+class CenterPointV2Workload(CenterPointWorkload):
+    name, v2 = "cp_pfatv2", True
+
+
+class KittiWorkload(Workload):
+    """configs[3]: Voxel-RCNN + 3D-DF (voxel_rcnn_car_mm_mvx+actrv2_hybrid_ifat.yaml:43-76), KITTI-shaped synthetic input
+    (1 camera 375 x 1242 -> 256 x 94 x 311 features, 16k points, 0.05 m voxels), bs 2: GPU voxelization + mean VFE,
+    VoxelBackBone8xFusion with MVX + ACTRv2 hybrid (d_model 64, 4 encoder layers, 3D local self-attention live),
+    up to encoded_spconv_tensor (the RoI head is outside the path)."""
+    name, batch, points, feat_hw = "kitti", 2, 16384, (94, 311)
+    metric = "Voxel-RCNN+3D-DF hot path fwd+bwd samples/sec"
+
+    def describe(self, n_gpus):
+        return {"workload": "Voxel-RCNN+3D-DF hot path: voxelize+mean VFE+VoxelBackBone8xFusion(MVX+ACTRv2 hybrid, 4 enc "
+                            "layers, LocalTransformer 2048x32), fwd+bwd+clip+AdamW",
+                "per_gpu_batch": self.batch, "global_batch": self.batch * n_gpus, "points_per_sample": self.points,
+                "cams": 1, "cam_feat": [256, *self.feat_hw], "sparse_shape": [41, 1600, 1408],
+                "parallelism": "dp%d" % n_gpus,
+                "l2": "L2 flushed between timed steps (inputs are smaller than L2)"}
+
+    def build(self, device):
+        import synth
+        from ddf_b200.fusion.voxelrcnn import VoxelBackBone8xFusion
+        from ddf_b200.ops.voxel import Voxelization
+        cfg = dict(FUSION_POS=[1, 4], FUSION_METHOD="MVX+ACTRv2", FEATURE_LEVELS=[0],
+                   LT_CFG=dict(npoint=2048, radius=2.0, nsample=32, num_layers=2),
+                   ACTR_CFG=dict(fusion_method="sum", feature_modal="hybrid", num_bins=80, num_channels=[256],
+                                 query_num_feat=64, num_enc_layers=4, max_num_ne_voxel=20000, pos_encode_method="depth"),
+                   HYBRID_CFG=dict(attn_layer="BiGateSum1D_2", q_method="sum", q_rep_place=["weight"]))
+        torch.manual_seed(0)
+        m = torch.nn.ModuleDict(dict(vox=Voxelization(synth.KITTI_VOXEL, synth.KITTI_RANGE, 5, (16000, 40000)),
+                                     backbone=VoxelBackBone8xFusion(cfg, 4, [1408, 1600, 40])))
+        return m.to(device).train()
+
+    def host_batch(self, rank, batch=None):
+        import synth
+        batch = batch or self.batch
+        rng = np.random.default_rng(rank)
+        t = {"pts": [torch.from_numpy(synth.lidar_points(self.points, seed=1000 * rank + b, nfeat=4, rng_m=70.0,
+                                                         forward_only=True)) for b in range(batch)],
+             "layer1_feat2d": torch.from_numpy(rng.standard_normal((batch, 256, *self.feat_hw), dtype=np.float32)),
+             "mvx_layer1_feat2d": torch.from_numpy(rng.standard_normal((batch, 16, *self.feat_hw), dtype=np.float32))}
+        return t, {"lidar2img": torch.from_numpy(np.repeat(synth.kitti_lidar2img()[None], batch, 0))}
+
+    def forward(self, m, t, static):
+        import torch.nn.functional as F
+        from ddf_b200.ops import voxel as vops
+        feats, coors = [], []
+        for b, p in enumerate(t["pts"]):
+            if p.is_cuda:
+                f, c, _ = m["vox"].forward_mean(p, 4)
+            else:
+                f, c, _ = vops.hard_voxelize_mean(p, m["vox"].voxel_size, m["vox"].point_cloud_range, 5, 16000, 4)
+            feats.append(f)
+            coors.append(F.pad(c, (1, 0), value=b))
+        bd = dict(batch_size=len(t["pts"]), image_hw=(375, 1242), lidar2img=static["lidar2img"],
+                  voxel_features=torch.cat(feats), voxel_coords=torch.cat(coors),
+                  img_dict={"layer1_feat2d": t["layer1_feat2d"], "mvx_layer1_feat2d": t["mvx_layer1_feat2d"]})
+        return m["backbone"](bd)["encoded_spconv_tensor"].features
+
+
+WORKLOADS = {w.name: w for w in (TransFusionWorkload, Dense200kWorkload, CenterPointWorkload, CenterPointV2Workload,
+                                 KittiWorkload)}
+
+
+def build_model(wl, device):
     from ddf_b200.fusion import structurally_unused_parameters
-    from ddf_b200.fusion.detector import TransFusionPtsBranch
-    torch.manual_seed(0)
-    model = TransFusionPtsBranch(**configs.transfusion_f()).to(device).train()
+    model = wl.build(device)
     frozen = set(structurally_unused_parameters(model))
     for n, p in model.named_parameters():
         if n in frozen:
@@ -75,12 +267,12 @@ def build_model(device):
     return model
 
 
-def host_batch(rank, batch):
-    import synth
-    pts = [torch.from_numpy(synth.lidar_points(POINTS_PER_SAMPLE, seed=1000 * rank + b)) for b in range(batch)]
-    feats = torch.from_numpy(synth.camera_features(batch, N_CAM, FEAT_HW, seed=rank))
-    metas = [synth.nusc_img_meta(N_CAM) for _ in range(batch)]
-    return pts, feats, metas
+def map_tensors(t, fn):
+    return {k: ([fn(x) for x in v] if isinstance(v, list) else fn(v)) for k, v in t.items()}
+
+
+def flat_tensors(t):
+    return [x for v in t.values() for x in (v if isinstance(v, list) else [v])]
 
 
 class ClockSampler(threading.Thread):
@@ -138,19 +330,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def cpu_reference_run(steps, warmup, batch=1):
-    """The reference's own CPU implementation of the path (oracle/cpu_path.py) on the host cores."""
+def cpu_reference_run(wl, steps, warmup, batch):
+    """The reference's own CPU implementation of the path (oracle/cpu_path.py: the reference's CPU extensions from
+    oracle/_ref + PyTorch CPU ops) on the host cores, all threads. Nothing of the CUDA library is touched."""
     from oracle import cpu_path
     torch.set_num_threads(os.cpu_count())
-    model = build_model("cpu")
+    model = build_model(wl, "cpu")
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01)
-    pts, feats, metas = host_batch(0, batch)
+    t, static = wl.host_batch(0, batch)
     times = []
     with cpu_path.reference_cpu_ops():
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            out = model(pts, [feats], metas)
-            loss = out.square().mean()
+            loss = wl.forward(model, t, static).square().mean()
             opt.zero_grad(set_to_none=True)
             loss.backward()
             torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
@@ -160,33 +352,52 @@ def cpu_reference_run(steps, warmup, batch=1):
                 times.append(dt)
     t = float(np.mean(times))
     return {"value": batch / t, "unit": UNIT, "cores": os.cpu_count(), "kind": cpu_path.kind(),
-            "sample": "%d frame(s) x %d points + %d cam maps, fwd+bwd+clip+AdamW, %d timed step(s) after %d warm-up; "
-                      "%.1f s/step" % (batch, POINTS_PER_SAMPLE, N_CAM, steps, warmup, t)}, t
+            "sample": "%d frame(s) x %d points + camera maps per step, fwd+bwd+clip+AdamW, %d timed step(s) after %d "
+                      "warm-up; %.1f s/step" % (batch, wl.points, steps, warmup, t)}, t
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.config]()
+    # bounded: at most 2 timed steps of the SAME per-GPU batch (about 20 s of host time per nuScenes-sized frame)
     steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
-    base, t = cpu_reference_run(steps, warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    base, t = cpu_reference_run(wl, steps, warmup, wl.batch)
+    line = {"impl": "reference", "metric": wl.metric, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.describe(args.gpus),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    line["config"]["reference_sample"] = "1 frame per step on the host cores (bounded sample of the bs=2/GPU workload)"
+            "gpu_launches": 0,
+            "reference_sample": "rank 0 only: %d step(s) of the per-GPU batch (%d frames) on the host cores" % (steps, wl.batch)}
     print(json.dumps(line))
 
 
 class KernelTimer(object):
-    """Per-launch CUDA-event timing of this library's kernel families on the launching stream (one
-    extra step after the timed region), with their algorithmic FLOPs / bytes."""
+    """Per-launch CUDA-event timing of this library's kernel families on the launching stream (extra steps after the
+    timed region), with their algorithmic FLOPs / bytes. ``finish_step`` closes one step; the summary
+    takes, launch by launch, the MEDIAN over the recorded steps (a single step is at the mercy of one stalled launch)."""
+    KINDS = ("conv", "wgrad", "msda_fwd", "msda_bwd")
 
     def __init__(self):
-        self.records = {"conv": [], "wgrad": [], "msda_fwd": [], "msda_bwd": []}
+        self.records = {k: [] for k in self.KINDS}
+        self.steps = []
         self.saved = []
+
+    def finish_step(self):
+        torch.cuda.synchronize()
+        self.steps.append({k: [(a.elapsed_time(b), m) for a, b, m in v] for k, v in self.records.items()})
+        self.records = {k: [] for k in self.KINDS}
+
+    def launches(self, kind):
+        """[(median ms, meta)] per launch of a step; falls back to the last step when the launch count varies."""
+        runs = [st[kind] for st in self.steps]
+        if not runs:
+            return []
+        if len({len(r) for r in runs}) != 1:
+            return runs[-1]
+        return [(float(np.median([r[i][0] for r in runs])), runs[-1][i][1]) for i in range(len(runs[-1]))]
 
     def _wrap(self, mod, name, kind, meta):
         orig = getattr(mod, name)
@@ -212,7 +423,7 @@ class KernelTimer(object):
 
         self._wrap(ops, "sparse_conv_forward", "conv",
                    lambda f, w, t, b, n_out, *fmt: conv_meta(t, f.shape[0], n_out, w.shape[-2], w.shape[-1]))
-        # dgrad timing includes the small filter-rounding launch that precedes the conv kernel
+        # dgrad timing includes the small filter-preparation launch that precedes the conv kernel
         self._wrap(ops, "sparse_conv_dgrad", "conv",
                    lambda w, g, t, n_in, *fmt: conv_meta(t, g.shape[0], n_in, w.shape[-1], w.shape[-2]))
         self._wrap(ops, "sparse_conv_wgrad", "wgrad",
@@ -243,10 +454,11 @@ class KernelTimer(object):
 
     def conv_summary(self, kind, by_width=None):
         ms = flops = byts = 0.0
-        for a, b, (how, t, n_src, n_dst, cin, cout) in self.records[kind]:
+        recs = self.launches(kind)
+        for dt, (how, t, n_src, n_dst, cin, cout) in recs:
             pairs = int((t >= 0).sum().item()) if how == "table" else int(t.sum().item())
             kvol = t.shape[1] if how == "table" else t.shape[0]
-            dt, fl = a.elapsed_time(b), 2.0 * pairs * cin * cout
+            fl = 2.0 * pairs * cin * cout
             ms += dt
             flops += fl
             byts += 4.0 * (n_src * cin + n_dst * cout + kvol * cin * cout) + 8.0 * pairs
@@ -255,17 +467,18 @@ class KernelTimer(object):
                 w[0] += 1
                 w[1] += dt
                 w[2] += fl
-        return len(self.records[kind]), ms, flops, byts
+        return len(recs), ms, flops, byts
 
     def msda_summary(self, kind):
         ms = byts = 0.0
-        for a, b, (N, S, M, D, Lq, L, P) in self.records[kind]:
-            ms += a.elapsed_time(b)
+        recs = self.launches(kind)
+        for dt, (N, S, M, D, Lq, L, P) in recs:
+            ms += dt
             if kind == "msda_fwd":
                 byts += 4.0 * (N * S * M * D + 3 * N * Lq * M * L * P + N * Lq * M * D)
             else:
                 byts += 4.0 * (2 * N * S * M * D + 2 * N * Lq * M * D + 6 * N * Lq * M * L * P)
-        return len(self.records[kind]), ms, byts
+        return len(recs), ms, byts
 
 
 def run_ours(args):
@@ -289,20 +502,37 @@ def run_ours(args):
     # GEMMs of the fusion encoder (value_proj, FFNs, 1x1 input_proj) the same arithmetic
     torch.backends.cuda.matmul.allow_tf32 = not args.fp32_gemm
     torch.backends.cudnn.allow_tf32 = not args.fp32_gemm
-    model = build_model(dev)
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    wl = WORKLOADS[args.config]()
+    model = build_model(wl, dev)
+    h_t, static = wl.host_batch(rank)
+
+    class StepModule(torch.nn.Module):
+        """The workload's forward as a module, so that DDP hooks the gradient all-reduce onto it."""
+
+        def __init__(self):
+            super().__init__()
+            self.model = model
+
+        def forward(self, t):
+            return wl.forward(self.model, t, static)
+
+    net = StepModule()
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
     # same optimizer as the reference config (AdamW lr 1e-4 wd 0.01), PyTorch's single-kernel variant
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01, fused=True)
 
-    h_pts, h_feats, metas = host_batch(rank, BATCH_PER_GPU)
-    h_pts = [p.pin_memory() for p in h_pts]
-    h_feats = h_feats.pin_memory()
+    h_t = map_tensors(h_t, lambda x: x.pin_memory())
     h_loss = torch.zeros(1).pin_memory()
-    d_pts = [p.to(dev) for p in h_pts]
-    d_feats = h_feats.to(dev)
+    d_t = map_tensors(h_t, lambda x: x.to(dev))
+    h2d = sum(x.numel() * x.element_size() for x in flat_tensors(h_t))
+    # inputs smaller than L2 (the KITTI-shaped config): evict them between timed steps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if h2d < (192 << 20) else None
 
-    def step(pts, feats):
-        out = net(pts, [feats], metas)
+    def step(t):
+        if flush is not None:
+            flush.fill_(1)
+        out = net(t)
         loss = out.square().mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -323,20 +553,25 @@ def run_ours(args):
             fn()
         b.record()
         barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        own = a.elapsed_time(b)
+        ms = torch.tensor([own], device=dev)
+        per_rank = [own]
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank = [float(x.item()) for x in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), per_rank
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
-        step(d_pts, d_feats)
+        step(d_t)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # (1) device-resident inputs
     L.ddf_launch_count(1)
-    ms_dev = timed(lambda: step(d_pts, d_feats), args.steps)
+    ms_dev, ranks_dev = timed(lambda: step(d_t), args.steps)
     launches = int(L.ddf_launch_count(1))
 
     # (2) end to end through the public module call: every step copies ITS inputs from pinned host
@@ -347,35 +582,36 @@ def run_ours(args):
 
     def stage_inputs():
         with torch.cuda.stream(copy_stream):
-            pts = [p.to(dev, non_blocking=True) for p in h_pts]
-            feats = h_feats.to(dev, non_blocking=True)
+            t = map_tensors(h_t, lambda x: x.to(dev, non_blocking=True))
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        staged["next"] = (pts, feats, ev)
+        staged["next"] = (t, ev)
 
     def e2e_step():
-        pts, feats, ev = staged.pop("next")
+        t, ev = staged.pop("next")
         torch.cuda.current_stream().wait_event(ev)
-        for t in pts + [feats]:
-            t.record_stream(torch.cuda.current_stream())
+        for x in flat_tensors(t):
+            x.record_stream(torch.cuda.current_stream())
         stage_inputs()                      # next step's host->device copy overlaps this step
-        loss = step(pts, feats)
+        loss = step(t)
         h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     stage_inputs()
     e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e, ranks_e2e = timed(e2e_step, args.steps)
     staged.clear()
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
 
-    # (3) kernel-family rooflines, timed live with CUDA events on the launching stream
+    # (3) kernel-family rooflines, timed live with CUDA events on the launching stream: 5 extra steps, per-launch
+    # medians over them
     ct = KernelTimer()
     ct.install()
-    step(d_pts, d_feats)
-    torch.cuda.synchronize()
+    for _ in range(5):
+        step(d_t)
+        ct.finish_step()
     by_width = {}
     n_launch, conv_ms, conv_flops, conv_bytes = ct.conv_summary("conv", by_width)
     n_wg, wg_ms, wg_flops, _ = ct.conv_summary("wgrad")
@@ -387,31 +623,39 @@ def run_ours(args):
 
     if rank == 0:
         peaks, how = measured_peaks()
-        global_batch = BATCH_PER_GPU * world
+        global_batch = wl.batch * world
         value = global_batch * args.steps / (ms_dev / 1e3)
         e2e = global_batch * args.steps / (ms_e2e / 1e3)
-        h2d = sum(p.numel() * 4 for p in h_pts) + h_feats.numel() * 4
         tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-        traffic = None   # per-launch DRAM bytes of the conv family from the committed ncu capture of this workload
+        # per-launch DRAM bytes of the conv family: STATIC, from the committed ncu capture of the tf workload (a live
+        # bench run cannot read dram__bytes counters)
+        traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and wl.name == "tf":
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 storage/accumulate; sparse convs bf16x3 (hi/lo split operands, 16-bit significand products) on "
                      "tcgen05, wgrad tf32; library GEMMs " + ("f32" if args.fp32_gemm else "tf32"),
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": wl.describe(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "rank_ms_per_step": {"device_resident": [m / args.steps for m in ranks_dev],
+                                 "e2e": [m / args.steps for m in ranks_e2e]},
             "clocks": sampler.summary(),
             "roofline": {
                 "kernel": "sparse-conv implicit GEMM, tcgen05 (forward + dgrad launches of one step)",
                 "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": tf / peak_tf if peak_tf else None, "traffic": traffic,
-                "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); kernel computes in tf32/fp32" % how,
+                "traffic_source": "static: profiles/conv_traffic.json (ncu dram__bytes of this workload's conv launches)"
+                                  if traffic is not None else None,
+                "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); achieved = ALGORITHMIC flops (2 * pairs * "
+                               "Cin * Cout) / median event time: the bf16x3 kernels issue 3 bf16 MMAs per algorithmic "
+                               "MAC (ceiling 1/3 of the bf16 peak), the fp32 narrow layers none" % how,
+                "timing": "CUDA events around every launch, median per launch over 5 steps after the timed region",
                 "launches_per_step": n_launch, "avg_launch_ms": conv_ms / max(n_launch, 1),
                 "share_of_step": conv_ms / (ms_dev / args.steps),
                 "algorithmic_GFLOP_per_step": conv_flops / 1e9, "algorithmic_MB_per_step": conv_bytes / 1e6,
@@ -436,7 +680,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"], _ = cpu_reference_run(1, 0)
+                line["cpu_baseline"], _ = cpu_reference_run(wl, 1, 0, 1)
             except Exception as e:  # the oracle is a checker; its absence must not fake a number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: %r" % (e,)}
