@@ -15,7 +15,11 @@
 // The winner is bit-identical to the reference's: largest distance, ties to the lowest
 // (index mod B) then lowest index, B = the reference's block size (largest power of two <= n,
 // capped at 1024) — that is what its strided per-thread scan + pairwise tree selects.
-// Distances are evaluated as written (no FMA contraction), like the oracle.
+// Squared distances use the contraction the reference kernels get from nvcc (default -fmad=true; read off the SASS
+// of oracle/_ref/furthest_point_sample_ext.so and ball_query_ext.so built from the reference sources for sm_100):
+// d = fma(dz, dz, fma(dx, dx, dy * dy)).  With it the sampled indices are identical to the reference CUDA kernel's
+// on real clouds (tools/bench_reference_kernels.py, tests/test_reference_cuda_gpu.py); an uncontracted sum differs in
+// the last bit often enough to pick another arg-max after a few hundred picks.
 #include "common.cuh"
 
 namespace {
@@ -24,7 +28,7 @@ constexpr int kFpsThreads = 1024;
 
 __device__ __forceinline__ float sqdist(float x1, float y1, float z1, float x2, float y2, float z2) {
   const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
@@ -172,6 +176,99 @@ fps_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* __restr
     }
   }
   cluster_barrier();  // no CTA exits while peers may still address its shared memory
+}
+
+// Rows of at most 8 * 1024 points (every 3D-DF configuration: <= 26000 queries over 6 cameras, 20000 for KITTI's
+// single camera uses the cluster kernel): ONE CTA, points in registers, ONE __syncthreads per pick.  Every warp
+// publishes its best (key, x, y, z) into a double-buffered slot before the barrier; after it every thread reduces the
+// 32 warp keys with shuffles and reads the winner's coordinates from the winning warp's slot.  (The reference pays a
+// 10-level __syncthreads tree and re-reads the cloud from global memory per pick.)
+template <int PPT>
+__global__ void __launch_bounds__(kFpsThreads)
+fps_single_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* __restrict__ idxs, int n, int m,
+                  int ref_block) {
+  __shared__ FpsSlot s_warp[2][kFpsThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = xyz + (long long)blockIdx.x * n * 3;
+  float* trow = temp ? temp + (long long)blockIdx.x * n : nullptr;
+  int* out = idxs + (long long)blockIdx.x * m;
+  float px[PPT], py[PPT], pz[PPT], pd[PPT];
+  unsigned tie[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int k = tid + kFpsThreads * i;
+    if (k < n) {
+      px[i] = row[3 * k];
+      py[i] = row[3 * k + 1];
+      pz[i] = row[3 * k + 2];
+      pd[i] = trow ? trow[k] : 1e10f;
+      // smaller tie value wins: (k mod B) major, k / B minor; +1 keeps every real key non-zero
+      tie[i] = 0x7fffffffu - (((unsigned)(k % ref_block) << 21) | (unsigned)(k / ref_block)) + 1u;
+    } else {
+      px[i] = py[i] = pz[i] = pd[i] = 0.f;
+      tie[i] = 0u;
+    }
+  }
+  float x1 = row[0], y1 = row[1], z1 = row[2];
+  if (tid == 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const int buf = j & 1;
+    unsigned long long best = 0ull;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      if (tie[i]) {
+        const float d = fminf(sqdist(x1, y1, z1, px[i], py[i], pz[i]), pd[i]);
+        pd[i] = d;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | tie[i];
+        if (key > best) {
+          best = key;
+          bx = px[i];
+          by = py[i];
+          bz = pz[i];
+        }
+      }
+    }
+    unsigned long long wbest = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = shfl_xor_u64(wbest, o);
+      wbest = other > wbest ? other : wbest;
+    }
+    // keys are unique per point: exactly one lane owns the warp's best (lane 0 when the warp has no point)
+    if ((wbest != 0ull && best == wbest) || (wbest == 0ull && lane == 0)) {
+      FpsSlot sl;
+      sl.key = wbest;
+      sl.x = bx;
+      sl.y = by;
+      sl.z = bz;
+      sl.pad = 0.f;
+      s_warp[buf][warp] = sl;
+    }
+    __syncthreads();
+    const unsigned long long mine = s_warp[buf][lane].key;
+    unsigned long long g = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = shfl_xor_u64(g, o);
+      g = other > g ? other : g;
+    }
+    const int w = __ffs(__ballot_sync(0xffffffffu, mine == g)) - 1;
+    x1 = s_warp[buf][w].x;
+    y1 = s_warp[buf][w].y;
+    z1 = s_warp[buf][w].z;
+    if (tid == 0) {
+      const unsigned t = 0x7fffffffu - ((unsigned)(g & 0xffffffffu) - 1u);
+      out[j] = (int)((t & 0x1fffffu) * (unsigned)ref_block + (t >> 21));
+    }
+  }
+  if (trow) {
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = tid + kFpsThreads * i;
+      if (k < n) trow[k] = pd[i];
+    }
+  }
 }
 
 template <int PPT>
@@ -334,6 +431,19 @@ extern "C" int ddf_furthest_point_sampling(const float* xyz, float* temp, int* i
   // the reference's block size decides its tie-break (opt_n_threads, furthest_point_sample_cuda.cu:9-13)
   int ref_block = 1;
   while (ref_block * 2 <= N && ref_block < 1024) ref_block *= 2;
+  if (N <= 8 * kFpsThreads) {
+    // one CTA per row, one barrier per pick
+    const unsigned grid = (unsigned)B;
+#define DDF_FPS_SINGLE(PPT) \
+    DDF_LAUNCH(fps_single_kernel<PPT>, grid, kFpsThreads, 0, stream, xyz, temp, idx, (int)N, (int)m, ref_block)
+    if (N <= kFpsThreads) DDF_FPS_SINGLE(1);
+    else if (N <= 2 * kFpsThreads) DDF_FPS_SINGLE(2);
+    else if (N <= 4 * kFpsThreads) DDF_FPS_SINGLE(4);
+    else DDF_FPS_SINGLE(8);
+#undef DDF_FPS_SINGLE
+    DDF_LAUNCH_CHECK();
+    return DDF_OK;
+  }
   // cluster size: up to 4 points per thread first, then grow the per-thread count
   int cs = 1;
   while (cs < kMaxCluster && (long long)cs * 4 * kFpsThreads < N) cs *= 2;

@@ -11,15 +11,25 @@ self-attention. The reference has no CPU implementation of these; each function 
 
 Pinned by the known-answer vectors of TransFusion/tests/test_models/test_common_modules/
 test_pointnet_ops.py:9-24 (FPS), :26-73 (ball query incl. dilated), :126-196 (grouping),
-:198-238 (gather) through tests/golden/pointops_golden.npz. fp32 arithmetic as written (no FMA).
+:198-238 (gather) through tests/golden/pointops_golden.npz, and on the GPU box by the reference CUDA kernels themselves
+(oracle/_ref/*_ext.so, tests/test_reference_cuda_gpu.py). Distances in fp32 with the reference kernels' FMA contraction.
 """
 import numpy as np
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64, one rounding to float32 at the
+    end (the float64 sum can itself round when the exponents are > 29 apart: harmless double rounding)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
 def _sqdist(a, b):
+    """Squared distance with the contraction nvcc gives the reference kernels (SASS of oracle/_ref/
+    furthest_point_sample_ext.so, ball_query_ext.so built from the reference sources, default -fmad=true):
+    d = fma(dz, dz, fma(dx, dx, dy * dy))."""
     d = (b - a).astype(np.float32)
-    return ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32) \
-        + (d[..., 2] * d[..., 2]).astype(np.float32)
+    dx, dy, dz = d[..., 0], d[..., 1], d[..., 2]
+    return _fma32(dz, dz, _fma32(dx, dx, (dy * dy).astype(np.float32)))
 
 
 def furthest_point_sample(xyz, npoint, temp=None):
