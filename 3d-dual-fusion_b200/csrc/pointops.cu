@@ -12,9 +12,12 @@
 // coordinates and min-distances live in registers for the whole kernel, the per-iteration arg-max
 // is one packed 64-bit key (distance bits | inverted tie-break) reduced by warp shuffles and one
 // shared-memory stage: 2 barriers per iteration instead of ~12 and no global traffic in the loop.
-// The winner is bit-identical to the reference's: largest distance, ties to the lowest
-// (index mod B) then lowest index, B = the reference's block size (largest power of two <= n,
-// capped at 1024) — that is what its strided per-thread scan + pairwise tree selects.
+// The winner is bit-identical to the reference's: largest distance; among EQUAL distances (common on voxel-centre
+// lattices) the reference's pairwise tree (stride B/2 ... 1, the lower slot keeps a tie) ends up preferring the
+// thread whose index has the smallest BIT-REVERSED value, and inside a thread the strided scan keeps the lowest
+// index: ties go to the smallest bitrev_log2(B)(index mod B), then the lowest index, B = the reference's block
+// size (largest power of two <= n, capped at 1024).  Checked against the reference CUDA kernel itself
+// (tests/test_reference_cuda_gpu.py).
 // Squared distances use the contraction the reference kernels get from nvcc (default -fmad=true; read off the SASS
 // of oracle/_ref/furthest_point_sample_ext.so and ball_query_ext.so built from the reference sources for sm_100):
 // d = fma(dz, dz, fma(dx, dx, dy * dy)).  With it the sampled indices are identical to the reference CUDA kernel's
@@ -29,6 +32,12 @@ constexpr int kFpsThreads = 1024;
 __device__ __forceinline__ float sqdist(float x1, float y1, float z1, float x2, float y2, float z2) {
   const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// bit reversal of (k mod B) in log2(B) bits (B a power of two); an involution, so it also decodes
+__device__ __forceinline__ unsigned tie_major(unsigned k, int B) {
+  if (B <= 1) return 0u;
+  return __brev(k & (unsigned)(B - 1)) >> (__clz(B) + 1);
 }
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
@@ -109,8 +118,8 @@ fps_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* __restr
       if (k < n) {
         const float d = fminf(sqdist(x1, y1, z1, px[i], py[i], pz[i]), pd[i]);
         pd[i] = d;
-        // smaller tie value wins: (k mod B) major, k / B minor; +1 keeps every real key non-zero
-        const unsigned tie = 0x7fffffffu - (((unsigned)(k % ref_block) << 21) | (unsigned)(k / ref_block));
+        // smaller tie value wins: bitrev(k mod B) major, k / B minor; +1 keeps every real key non-zero
+        const unsigned tie = 0x7fffffffu - ((tie_major(k, ref_block) << 21) | (unsigned)(k / ref_block));
         const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (tie + 1u);
         if (key > best) {
           best = key;
@@ -165,7 +174,7 @@ fps_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* __restr
     z1 = s_slot[buf][gi].z;
     if (rank == 0 && tid == 0) {
       const unsigned t = 0x7fffffffu - ((unsigned)(g & 0xffffffffu) - 1u);
-      out[j] = (int)((t & 0x1fffffu) * (unsigned)ref_block + (t >> 21));
+      out[j] = (int)((t & 0x1fffffu) * (unsigned)ref_block + tie_major(t >> 21, ref_block));
     }
   }
   if (trow) {
@@ -202,8 +211,8 @@ fps_single_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* 
       py[i] = row[3 * k + 1];
       pz[i] = row[3 * k + 2];
       pd[i] = trow ? trow[k] : 1e10f;
-      // smaller tie value wins: (k mod B) major, k / B minor; +1 keeps every real key non-zero
-      tie[i] = 0x7fffffffu - (((unsigned)(k % ref_block) << 21) | (unsigned)(k / ref_block)) + 1u;
+      // smaller tie value wins: bitrev(k mod B) major, k / B minor; +1 keeps every real key non-zero
+      tie[i] = 0x7fffffffu - ((tie_major(k, ref_block) << 21) | (unsigned)(k / ref_block)) + 1u;
     } else {
       px[i] = py[i] = pz[i] = pd[i] = 0.f;
       tie[i] = 0u;
@@ -259,7 +268,7 @@ fps_single_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* 
     z1 = s_warp[buf][w].z;
     if (tid == 0) {
       const unsigned t = 0x7fffffffu - ((unsigned)(g & 0xffffffffu) - 1u);
-      out[j] = (int)((t & 0x1fffffu) * (unsigned)ref_block + (t >> 21));
+      out[j] = (int)((t & 0x1fffffu) * (unsigned)ref_block + tie_major(t >> 21, ref_block));
     }
   }
   if (trow) {

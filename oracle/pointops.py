@@ -2,9 +2,11 @@
 self-attention. The reference has no CPU implementation of these; each function follows the kernel:
 
   furthest_point_sample  <proj>/ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:25-141
-                         (incl. its tie-break: per-thread strided scan keeps the lowest index, the
-                         pairwise tree keeps the lower thread => lowest (k mod B), then lowest k,
-                         B = largest power of two <= n capped at 1024, :9-13)
+                         (incl. its tie-break: the per-thread strided scan keeps the lowest index; the pairwise
+                         tree - strides B/2 ... 1, the LOWER slot keeps a tie - decides equal distances by the
+                         low bits of the thread index first => smallest bit-reversed (k mod B), then lowest k,
+                         B = largest power of two <= n capped at 1024, :9-13; verified against the compiled
+                         reference kernel on lattice clouds, where exact ties are common)
   ball_query             <proj>/ops/ball_query/src/ball_query_cuda.cu:11-54
   grouping_operation     <proj>/ops/group_points/src/group_points_cuda.cu:10-31,56-79
   gather_points          <proj>/ops/gather_points/src/gather_points_cuda.cu:8-26,51-70
@@ -42,7 +44,11 @@ def furthest_point_sample(xyz, npoint, temp=None):
     while block * 2 <= N and block < 1024:
         block *= 2
     k = np.arange(N)
-    tie = (k % block).astype(np.int64) * (1 << 21) + k // block   # smaller wins
+    bits = int(block).bit_length() - 1
+    rev = np.zeros(N, np.int64)
+    for bit in range(bits):                                        # bit reversal of (k mod block) in log2(block) bits
+        rev |= (((k % block) >> bit) & 1) << (bits - 1 - bit)
+    tie = rev * (1 << 21) + k // block   # smaller wins
     for b in range(B):
         dist = np.full((N,), 1e10, np.float32) if temp is None else temp[b]
         old = 0

@@ -40,11 +40,13 @@ def test_group_gather_known_answers_and_grads():
 
 
 def test_fps_tie_break_follows_reference_thread_layout():
-    # 6 identical points + 2 distinct: block size B = 4 -> ties go to the lowest (k mod 4), then lowest k
+    # 6 identical points + 2 distinct: block size B = 8; the reference's pairwise tree resolves ties by the low bits
+    # of the thread index first = smallest bit-reversed (k mod B), then lowest k (checked against the compiled
+    # reference kernel on the GPU box: tests/test_reference_cuda_gpu.py::test_fps_tiny_tie_case)
     xyz = np.zeros((1, 8, 3), np.float32)
     xyz[0, 5] = [1, 0, 0]
     xyz[0, 6] = [1, 0, 0]
     idx = op.furthest_point_sample(xyz, 3)
-    # after picking 0, points 5 and 6 tie at distance 1: k mod 4 = 1 vs 2 -> 5; then everything is at
-    # distance 0 from the picked set -> lowest (k mod 4): 0 (k=0)
-    assert idx.tolist() == [[0, 5, 0]]
+    # after picking 0, points 5 (0b101 -> reversed 0b101) and 6 (0b110 -> reversed 0b011) tie at distance 1 -> 6;
+    # then everything is at distance 0 from the picked set -> reversed index 0 (k = 0)
+    assert idx.tolist() == [[0, 6, 0]]

@@ -51,6 +51,20 @@ def test_fps_indices_identical_to_reference_cuda_kernel(n, m):
     assert torch.equal(ours, out)
 
 
+def test_fps_tiny_tie_case():
+    """The tie case of tests/test_oracle_pointops.py on the compiled reference kernel: pins the oracle's tie rule."""
+    from ddf_b200.ops import pointops
+    from oracle import pointops as opo
+    ext = ref("furthest_point_sample_ext")
+    xyz = np.zeros((1, 8, 3), np.float32)
+    xyz[0, 5] = [1, 0, 0]
+    xyz[0, 6] = [1, 0, 0]
+    t = torch.from_numpy(xyz).cuda()
+    out = torch.zeros(1, 3, dtype=torch.int32, device="cuda")
+    ext.furthest_point_sampling_wrapper(1, 8, 3, t, torch.full((1, 8), 1e10, device="cuda"), out)
+    assert out.cpu().tolist() == opo.furthest_point_sample(xyz, 3).tolist() == pointops.furthest_point_sample(t, 3).cpu().tolist()
+
+
 def test_ball_query_and_group_identical_to_reference_cuda_kernels():
     from ddf_b200.ops import pointops
     bq, gp, ga = ref("ball_query_ext"), ref("group_points_ext"), ref("gather_points_ext")
