@@ -151,9 +151,13 @@ class DeformableTransformerEncoder(nn.Module):
             raise NotImplementedError("image->point direction (IACTR) is not part of the 3D-DF hot path")
         reference_points = q_reference_points[:, :, None] * valid_ratios[:, None]
         plan = self._tile_plan(src, reference_points, spatial_shapes)
+        geom = None
         for idx, layer in enumerate(self.layers):
             if self.model_name == "ACTRv2":
-                q_feat = self.lidar_attns[idx](q_lidar_grid, q_feat.permute(0, 2, 1))
+                lt = self.lidar_attns[idx]
+                if geom is None and lt._token_path_ok(q_feat.permute(0, 2, 1)):
+                    geom = lt.geometry(q_lidar_grid)   # FPS / ball query / scatter table: once for all layers
+                q_feat = lt(q_lidar_grid, q_feat.permute(0, 2, 1), geom)
             q_feat, q_i_feat = layer(src, pos, reference_points, spatial_shapes, level_start_index,
                                      padding_mask, q_pos=q_pos, q_feat=q_feat, q_i_feat=q_i_feat, plan=plan)
         return q_feat

@@ -9,7 +9,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops import fused as _fused
 from ..ops import pointops as _pointops
+from ..ops import sparse_norm as _sparse_norm
 from ..ops.pointops import Points_Sampler, QueryAndGroup, gather_points
 
 
@@ -132,8 +134,69 @@ class LocalTransformer(nn.Module):
         else:
             raise NotImplementedError(self.attn_feat_agg_method)
 
-    def forward(self, xyz, features):
+    # ---- CUDA hot path: everything token-major --------------------------------------------------------------
+    def _token_path_ok(self, features):
+        layer = self.chunk.layers[0]
+        mha = layer.self_attn
+        C = features.shape[1]
+        return (features.is_cuda and features.dtype == torch.float32 and self.attn_feat_agg_method == "unique"
+                and self.feat_agg_method == "replace" and mha._qkv_same_embed_dim and mha.in_proj_bias is not None
+                and (mha.dropout == 0.0 or not self.training)
+                and _pointops.local_attn_supported(mha.num_heads, C // mha.num_heads, self.nsample))
+
+    def geometry(self, xyz):
+        """Everything of the LocalTransformer that depends on the coordinates only: D-FPS centres, ball-query groups,
+        the flattened row index of every grouped token, the grouped (absolute) coordinates and the first-occurrence
+        table of the scatter. The encoder hands the same ``xyz`` to every layer's LocalTransformer, which the reference
+        re-samples and re-groups each time (actr_transformer.py:496-498); here it is computed once per forward."""
+        xyz = xyz.contiguous()
+        B, N, _ = xyz.shape
+        fps_idx = self.sampler(xyz, None)
+        new_xyz = gather_points(xyz.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2).contiguous()
+        idx = _pointops.ball_query(0, self.radius, self.nsample, xyz, new_xyz)         # (B, np, ns) int32
+        flat = (idx.long() + torch.arange(B, device=idx.device)[:, None, None] * N).reshape(-1)
+        gxyz = xyz.reshape(B * N, 3).index_select(0, flat)                            # (T, 3) absolute coordinates
+        first = _pointops.first_occurrence(idx, N).long()                              # (B, N), E where never grouped
+        E = idx.shape[1] * idx.shape[2]
+        hit = first < E
+        src = (first.clamp(max=E - 1) + torch.arange(B, device=idx.device)[:, None] * E).reshape(-1)
+        return dict(flat=flat, gxyz=gxyz, hit=hit.reshape(-1, 1), src=src, xyz=xyz)
+
+    def _layer_tokens(self, layer, x):
+        """TransformerEncoderLayerPreNorm.forward (pointformer.py:33-44) on (T, C) tokens; groups of ``nsample``
+        consecutive rows are the sequences."""
+        mha = layer.self_attn
+        s = layer.norm1(x)
+        qkv = F.linear(s, mha.in_proj_weight, mha.in_proj_bias)
+        o = _pointops.local_attention(qkv, mha.num_heads, self.nsample)
+        s = s + layer.dropout1(F.linear(o, mha.out_proj.weight, mha.out_proj.bias))
+        s = layer.norm2(s)
+        hidden = _fused.ffn_hidden(layer.linear1, layer.dropout, s)
+        return s + layer.dropout2(layer.linear2(hidden))
+
+    def forward_tokens(self, xyz, feats_nc, geom=None):
+        """feats_nc (B, N, C) row-major voxel features -> (B, N, C). No (B, C, np, ns) tensor, no permutes: the grouped
+        tokens are gathered as (T, C) rows, the position MLP (1x1 convs + BN2d = Linear + BatchNorm over the same T
+        samples) and the transformer layers are row-major GEMMs + the fused kernels, the 32-token attention is
+        csrc/local_attn.cu, the write-back is a row gather through the first-occurrence table."""
+        B, N, C = feats_nc.shape
+        if geom is None:
+            geom = self.geometry(xyz)
+        rows = feats_nc.reshape(B * N, C)
+        x = rows.index_select(0, geom["flat"])
+        conv1, bn, conv2 = self.pe[0].conv, self.pe[0].bn, self.pe[1].conv
+        pe = F.linear(geom["gxyz"], conv1.weight.view(conv1.out_channels, 3))
+        pe = _sparse_norm.batch_norm_act(bn, pe, relu=True)        # BatchNorm2d over (B, H, W) == over the T rows
+        x = x + F.linear(pe, conv2.weight.view(conv2.out_channels, conv2.in_channels), conv2.bias)
+        for layer in self.chunk.layers:
+            x = self._layer_tokens(layer, x)
+        out = torch.where(geom["hit"], x.index_select(0, geom["src"]), rows)
+        return out.view(B, N, C)
+
+    def forward(self, xyz, features, geom=None):
         """xyz (B, N, 3), features (B, C, N) -> (B, N, C). Mutates ``features`` like the reference."""
+        if self._token_path_ok(features):
+            return self.forward_tokens(xyz, features.transpose(1, 2).contiguous(), geom)
         xyz = xyz.contiguous()
         fps_idx = self.sampler(xyz, features)
         new_xyz = gather_points(xyz.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2)

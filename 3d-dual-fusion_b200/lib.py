@@ -52,6 +52,9 @@ _SIGNATURES = {
     "ddf_group_points_grad": [c_ptr] * 3 + [c_i64] * 5 + [c_ptr],
     "ddf_gather_points": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
     "ddf_gather_points_grad": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
+    "ddf_local_attn_supported": [c_i64] * 3,
+    "ddf_local_attn_forward": [c_ptr, c_ptr] + [c_i64] * 4 + [c_ptr],
+    "ddf_local_attn_backward": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
     "ddf_first_occurrence": [c_ptr, c_ptr] + [c_i64] * 3 + [c_ptr],
     "ddf_scatter_first": [c_ptr] * 3 + [c_i64] * 4 + [c_ptr],
     "ddf_scatter_first_grad": [c_ptr] * 4 + [c_i64] * 4 + [c_ptr],

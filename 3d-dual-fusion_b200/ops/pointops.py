@@ -169,6 +169,62 @@ class ScatterFirst(Function):
 scatter_first = ScatterFirst.apply
 
 
+def first_occurrence(idx, N):
+    """idx (B, npoint, nsample) int32 -> first (B, N) int32: flattened position of every voxel's first occurrence,
+    npoint * nsample where the voxel is in no group."""
+    _lib.require_cuda(idx)
+    idx = idx.contiguous()
+    B, E = idx.shape[0], idx.shape[1] * idx.shape[2]
+    first = torch.empty((B, N), dtype=torch.int32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        rc = _lib.get_lib().ddf_first_occurrence(_lib.ptr(idx), _lib.ptr(first), B, N, E, _lib.current_stream())
+    _lib.check(rc, "first_occurrence")
+    return first
+
+
+def local_attn_supported(heads, head_dim, group_size):
+    return bool(_lib.get_lib().ddf_local_attn_supported(int(heads), int(head_dim), int(group_size)))
+
+
+class LocalAttention(Function):
+    """softmax(q k^T / sqrt(hd)) v inside every group of 32 tokens, per head, on token-major projections:
+    qkv (T, 3C) -> (T, C), T = groups * 32 (csrc/local_attn.cu)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, group_size):
+        _lib.require_cuda(qkv)
+        qkv = qkv.contiguous()
+        if qkv.dtype != torch.float32:
+            raise RuntimeError("local attention: float32 only")
+        T, C3 = qkv.shape
+        C = C3 // 3
+        out = torch.empty((T, C), dtype=qkv.dtype, device=qkv.device)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.get_lib().ddf_local_attn_forward(_lib.ptr(qkv), _lib.ptr(out), T // group_size, heads, C // heads,
+                                                       group_size, _lib.current_stream())
+        _lib.check(rc, "local_attn_forward")
+        ctx.save_for_backward(qkv)
+        ctx.dims = (heads, group_size)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (qkv,) = ctx.saved_tensors
+        heads, group_size = ctx.dims
+        grad_out = grad_out.contiguous()
+        T, C3 = qkv.shape
+        g = torch.empty_like(qkv)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.get_lib().ddf_local_attn_backward(_lib.ptr(qkv), _lib.ptr(grad_out), _lib.ptr(g), T // group_size,
+                                                        heads, C3 // 3 // heads, group_size, _lib.current_stream())
+        _lib.check(rc, "local_attn_backward")
+        return g, None, None
+
+
+local_attention = LocalAttention.apply
+
+
 class DFPS_Sampler(nn.Module):
     def forward(self, points, features, npoint):
         return furthest_point_sample(points.contiguous(), npoint)

@@ -311,6 +311,17 @@ int ddf_scatter_first(const float* feats, const int* first, float* inout, int64_
 int ddf_scatter_first_grad(const float* grad_out, const int* first, float* grad_feats, float* grad_features,
                            int64_t B, int64_t C, int64_t N, int64_t E, void* stream);
 
+/* 3D local self-attention core (LocalTransformer; <proj>/models/model_utils/pointformer.py:10-44, 349-380): inside
+ * every ball-query group of group_size = 32 tokens, per head: out = softmax(q k^T / sqrt(head_dim)) v.
+ *   qkv [groups*32, 3*heads*head_dim] float32 token-major (q | k | v as nn.MultiheadAttention's in_proj emits them)
+ *   out [groups*32, heads*head_dim];  backward recomputes the probabilities: grad_qkv from grad_out.
+ * head_dim in {16, 32}; ddf_local_attn_supported says whether a shape is taken. */
+int ddf_local_attn_supported(int64_t heads, int64_t head_dim, int64_t group_size);
+int ddf_local_attn_forward(const float* qkv, float* out, int64_t groups, int64_t heads, int64_t head_dim,
+                           int64_t group_size, void* stream);
+int ddf_local_attn_backward(const float* qkv, const float* grad_out, float* grad_qkv, int64_t groups, int64_t heads,
+                            int64_t head_dim, int64_t group_size, void* stream);
+
 /* ---- BatchNorm1d over sparse-voxel features [N, C], fused with the residual add and ReLU -----------
  * Replaces the elementwise chain conv -> BN1d -> [+ identity] -> ReLU of the reference's sparse
  * blocks (TransFusion/mmdet3d/ops/sparse_block.py:102-120,153-185; torch.nn.BatchNorm1d semantics:

@@ -38,6 +38,7 @@ from ref_loader import AttrDict  # noqa: E402
 
 HYB = dict(attn_layer="BiGateSum1D_2", q_method="sum", q_rep_place=["weight"])
 LT = dict(npoint=24, radius=2.0, nsample=8, num_layers=1, attn_feat_agg_method="unique", feat_agg_method="replace")
+LT32 = dict(LT, nsample=32)   # the shipped group size: on CUDA this is the token-major path + csrc/local_attn.cu
 
 # name -> flavour, model_name, ACTR cfg, lt_cfg, hybrid_cfg, (B', Lq, H, W), valid rows per batch row, train too?
 CASES = {
@@ -47,13 +48,13 @@ CASES = {
                                     pos_encode_method="depth", feature_modal="hybrid", hybrid_cfg=HYB),
                            dims=(3, 90, 9, 14), valid=(90, 61, 0)),
     # CenterPoint pfatv2 (nusc_centerpoint_..._pfatv2.py:75-90): lidar + ACTRv2
-    "cp_lidar_actrv2": dict(flavour="CP", model_name="ACTRv2", train=True, lt=LT,
+    "cp_lidar_actrv2": dict(flavour="CP", model_name="ACTRv2", train=True, lt=LT32,
                             cfg=dict(num_channels=[64], query_num_feat=128, num_enc_layers=1, max_num_ne_voxel=26000,
                                      pos_encode_method="depth"),
                             dims=(2, 70, 8, 12), valid=(70, 43)),
     # Voxel-RCNN (voxel_rcnn_car_mm_mvx+actrv2_hybrid_ifat.yaml:53-76): hybrid + ACTRv2, d_model 64, 4 layers,
     # gate BEFORE the FFNs, hybrid_cfg passed separately
-    "vr_hybrid_actrv2": dict(flavour="VR", model_name="ACTRv2", train=True, lt=dict(LT, num_layers=2),
+    "vr_hybrid_actrv2": dict(flavour="VR", model_name="ACTRv2", train=True, lt=dict(LT32, num_layers=2),
                              cfg=dict(num_channels=[48], query_num_feat=64, num_enc_layers=4, max_num_ne_voxel=20000,
                                       pos_encode_method="depth", feature_modal="hybrid"), hybrid=HYB,
                              dims=(2, 80, 7, 16), valid=(80, 55)),
@@ -73,6 +74,11 @@ CASES = {
                                            pos_encode_method="depth", feature_modal="hybrid",
                                            hybrid_cfg=dict(HYB, attn_layer="BiGate1D_2", q_rep_place=["offset"])),
                                   dims=(2, 40, 6, 10), valid=(40, 17)),
+    # the generic LocalTransformer path (group size 8: module graph with nn.MultiheadAttention)
+    "cp_lidar_actrv2_ns8": dict(flavour="CP", model_name="ACTRv2", train=True, lt=LT,
+                                cfg=dict(num_channels=[32], query_num_feat=64, num_enc_layers=2, max_num_ne_voxel=100,
+                                         pos_encode_method="depth"),
+                                dims=(2, 70, 6, 10), valid=(70, 43)),
     # single-stream modes
     "tf_image_actr": dict(flavour="TF", model_name="ACTR",
                           cfg=dict(num_channels=[32], query_num_feat=64, num_enc_layers=1, max_num_ne_voxel=100,

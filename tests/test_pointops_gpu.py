@@ -127,3 +127,53 @@ def test_scatter_first_occurrence_kernel_matches_reference_rule():
     for v, pos in ((5, 0), (3, 1), (7, 3), (9, 6)):
         assert torch.equal(out[0, :, v].cpu(), feats[0, :, 0, pos])
     assert torch.equal(d_base.detach().cpu(), base)   # input not modified
+
+
+@pytest.mark.parametrize("C,heads", [(128, 4), (64, 4)])
+def test_local_attention_kernel_matches_multihead_attention(C, heads):
+    """csrc/local_attn.cu vs nn.MultiheadAttention's own attention (scaled_dot_product) on groups of 32 tokens."""
+    from ddf_b200.ops import pointops
+    torch.manual_seed(0)
+    G, ns = 37, 32
+    qkv = torch.randn(G * ns, 3 * C, device="cuda", dtype=torch.float64)
+    hd = C // heads
+    q, k, v = (t.view(G, ns, heads, hd).transpose(1, 2) for t in qkv.split(C, dim=1))
+    qkv32 = qkv.float().requires_grad_()
+    out = pointops.local_attention(qkv32, heads, ns)
+    g = torch.randn(G * ns, C, device="cuda")
+    out.backward(g)
+    q, k, v = (t.detach().requires_grad_() for t in (q, k, v))
+    ref = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, -1) @ v
+    ref = ref.transpose(1, 2).reshape(G * ns, C)
+    ref.backward(g.double())
+    ref_g = torch.cat([t.grad.transpose(1, 2).reshape(G * ns, C) for t in (q, k, v)], 1)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((qkv32.grad.double() - ref_g).abs().max() / ref_g.abs().max()) < 1e-5
+
+
+def test_local_transformer_token_path_equals_module_graph():
+    """LocalTransformer on CUDA (token-major path, csrc/local_attn.cu, cached geometry) == the same module through
+    the generic module graph (nn.MultiheadAttention on the permuted (32, B*np, C) tensor), forward and backward."""
+    from ddf_b200.fusion.pointformer import LocalTransformer
+    torch.manual_seed(0)
+    lt = LocalTransformer(64, 2.0, 32, 128, 128, num_layers=2).cuda().train()
+    B, N = 3, 900
+    xyz = (torch.rand(B, N, 3, device="cuda") * torch.tensor([20.0, 20.0, 4.0], device="cuda")).contiguous()
+    xyz[:, -100:] = 0        # padded rows at the origin
+    feats = torch.randn(B, N, 128, device="cuda")
+    f1 = feats.clone().requires_grad_()
+    out1 = lt(xyz, f1.permute(0, 2, 1))
+    out1.square().sum().backward()
+    g1 = {n: p.grad.clone() for n, p in lt.named_parameters()}
+    lt.zero_grad()
+    for m in lt.modules():                     # same batch statistics update twice: reset the momentum side effects
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.reset_running_stats()
+    f2 = feats.clone().requires_grad_()
+    lt._token_path_ok = lambda features: False
+    out2 = lt(xyz, f2.permute(0, 2, 1).contiguous())
+    out2.square().sum().backward()
+    assert float((out1 - out2).abs().max() / out2.abs().max()) < 1e-4
+    assert float((f1.grad - f2.grad).abs().max() / f2.grad.abs().max()) < 1e-3
+    for n, p in lt.named_parameters():
+        assert float((g1[n] - p.grad).abs().max() / p.grad.abs().max().clamp_min(1e-12)) < 2e-3, n
