@@ -155,6 +155,8 @@ def test_local_transformer_token_path_equals_module_graph():
     """LocalTransformer on CUDA (token-major path, csrc/local_attn.cu, cached geometry) == the same module through
     the generic module graph (nn.MultiheadAttention on the permuted (32, B*np, C) tensor), forward and backward."""
     from ddf_b200.fusion.pointformer import LocalTransformer
+    torch.backends.cudnn.allow_tf32 = False      # the module graph runs its 1x1 position convs through cuDNN
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     lt = LocalTransformer(64, 2.0, 32, 128, 128, num_layers=2).cuda().train()
     B, N = 3, 900
