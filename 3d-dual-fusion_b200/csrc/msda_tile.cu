@@ -56,12 +56,11 @@ struct PlanLayout {
   long long counts, tile_start, q_tile, q_rank, perm, work, total;
   int NT, NWmax, TX, TY;
 };
-__host__ __device__ inline PlanLayout plan_layout(long long N, long long Lq, int H, int W) {
+__host__ __device__ inline PlanLayout plan_layout(long long N, long long NQ, int H, int W) {
   PlanLayout p;
   p.TX = (W + kTile - 1) / kTile;
   p.TY = (H + kTile - 1) / kTile;
   p.NT = (int)(N * p.TX * p.TY);
-  const long long NQ = N * Lq;
   p.NWmax = (int)(p.NT + NQ / kQC + 1);
   p.counts = 1;
   p.tile_start = p.counts + p.NT;
@@ -74,8 +73,8 @@ __host__ __device__ inline PlanLayout plan_layout(long long N, long long Lq, int
 }
 
 __global__ void __launch_bounds__(kThreads)
-msda_plan_count_kernel(const float* __restrict__ ref, int* __restrict__ plan, PlanLayout pl, long long NQ, int Lq,
-                       int H, int W) {
+msda_plan_count_kernel(const float* __restrict__ ref, const int* __restrict__ qbatch, int* __restrict__ plan,
+                       PlanLayout pl, long long NQ, int Lq, int H, int W) {
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= NQ) return;
   const float2 r = __ldg(reinterpret_cast<const float2*>(ref) + i);
@@ -83,7 +82,7 @@ msda_plan_count_kernel(const float* __restrict__ ref, int* __restrict__ plan, Pl
   int px = (int)floorf(r.x * (float)W), py = (int)floorf(r.y * (float)H);
   px = min(max(px, 0), W - 1);
   py = min(max(py, 0), H - 1);
-  const int b = (int)(i / Lq);
+  const int b = qbatch ? qbatch[i] : (int)(i / Lq);     // ragged query list: the image of every query is given
   const int t = (b * pl.TY + py / kTile) * pl.TX + px / kTile;
   plan[pl.q_tile + i] = t;
   plan[pl.q_rank + i] = atomicAdd(plan + pl.counts + t, 1);
@@ -584,12 +583,12 @@ bool stage_with_tma() {
   return tma;
 }
 
-int check_shapes(int64_t N, int64_t H, int64_t W, int64_t M, int64_t D, int64_t Lq, const char* what) {
-  DDF_CHECK_ARG(N >= 0 && H > 0 && W > 0 && M > 0 && Lq >= 0, "%s: bad sizes", what);
+int check_shapes(int64_t N, int64_t H, int64_t W, int64_t M, int64_t D, int64_t NQ, const char* what) {
+  DDF_CHECK_ARG(N >= 0 && H > 0 && W > 0 && M > 0 && NQ >= 0, "%s: bad sizes", what);
   DDF_CHECK_ARG((D == 8 || D == 16) && (M * D) % 32 == 0,
                 "%s: the tile-staged kernel takes D in {8, 16} with M * D a multiple of 32 (D=%lld M=%lld)", what,
                 (long long)D, (long long)M);
-  DDF_CHECK_ARG(H < 32768 && W < 32768 && N * H * W * M * D < (1ll << 40) && N * Lq < (1ll << 31),
+  DDF_CHECK_ARG(H < 32768 && W < 32768 && N * H * W * M * D < (1ll << 40) && NQ < (1ll << 31),
                 "%s: problem too large", what);
   return DDF_OK;
 }
@@ -601,40 +600,43 @@ extern "C" int ddf_msda_tile_supported(int64_t M, int64_t D, int64_t L, int64_t 
   return L == 1 && P == kP && (D == 8 || D == 16) && (M * D) % 32 == 0;
 }
 
-extern "C" int64_t ddf_msda_plan_bytes(int64_t N, int64_t Lq, int64_t H, int64_t W) {
-  if (N < 0 || Lq < 0 || H <= 0 || W <= 0) return -1;
-  return plan_layout(N, Lq, (int)H, (int)W).total * 4;
+extern "C" int64_t ddf_msda_plan_bytes(int64_t N, int64_t NQ, int64_t H, int64_t W) {
+  if (N < 0 || NQ < 0 || H <= 0 || W <= 0) return -1;
+  return plan_layout(N, NQ, (int)H, (int)W).total * 4;
 }
 
-// reference_points [N, Lq, 2] (x, y in [0, 1]) -> plan (ddf_msda_plan_bytes bytes, int32 aligned)
-extern "C" int ddf_msda_plan(const float* reference_points, void* plan_, int64_t N, int64_t Lq, int64_t H, int64_t W,
-                             void* stream_) {
+// reference_points [NQ, 2] (x, y in [0, 1]) -> plan (ddf_msda_plan_bytes bytes, int32 aligned).  Regular layout:
+// query_batch = NULL and query i belongs to image i / Lq (NQ = N * Lq).  Ragged layout (only the real queries of a
+// zero-padded per-camera layout): query_batch [NQ] int32 gives the image of every query, Lq is ignored.
+extern "C" int ddf_msda_plan(const float* reference_points, const int* query_batch, void* plan_, int64_t N, int64_t NQ,
+                             int64_t Lq, int64_t H, int64_t W, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DDF_CHECK_ARG(N >= 0 && Lq >= 0 && H > 0 && W > 0 && N * Lq < (1ll << 31), "msda_plan: bad sizes");
+  DDF_CHECK_ARG(N >= 0 && NQ >= 0 && H > 0 && W > 0 && NQ < (1ll << 31), "msda_plan: bad sizes");
+  DDF_CHECK_ARG(query_batch || (Lq > 0 && NQ == N * Lq) || NQ == 0, "msda_plan: NQ must be N * Lq without query_batch");
   DDF_CHECK_ARG(plan_ != nullptr, "msda_plan: null plan");
   int* plan = reinterpret_cast<int*>(plan_);
-  const PlanLayout pl = plan_layout(N, Lq, (int)H, (int)W);
+  const PlanLayout pl = plan_layout(N, NQ, (int)H, (int)W);
   DDF_CUDA(cudaMemsetAsync(plan, 0, sizeof(int) * (size_t)(pl.tile_start), stream));   // n_work + counts
-  const long long NQ = N * Lq;
   if (NQ == 0) return DDF_OK;
   DDF_CHECK_ARG(reference_points != nullptr, "msda_plan: null reference_points");
   const unsigned grid = (unsigned)ddf::cdiv(NQ, kThreads);
-  DDF_LAUNCH(msda_plan_count_kernel, grid, kThreads, 0, stream, reference_points, plan, pl, NQ, (int)Lq, (int)H, (int)W);
+  DDF_LAUNCH(msda_plan_count_kernel, grid, kThreads, 0, stream, reference_points, query_batch, plan, pl, NQ,
+             (int)(Lq > 0 ? Lq : 1), (int)H, (int)W);
   DDF_LAUNCH(msda_plan_scan_kernel, 1, 1024, 0, stream, plan, pl);
   DDF_LAUNCH(msda_plan_scatter_kernel, grid, kThreads, 0, stream, plan, pl, NQ);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
 
-// out [N, Lq, M*D] = MSDA(value [N, H*W, M, D]; loc = ref + offsets / (W, H); weights = softmax(logits))
-// offsets [N, Lq, M, 1, 4, 2] raw (pixels), logits [N, Lq, M, 4].
+// out [NQ, M*D] = MSDA(value [N, H*W, M, D]; loc = ref + offsets / (W, H); weights = softmax(logits))
+// offsets [NQ, M, 1, 4, 2] raw (pixels), logits [NQ, M, 4]; NQ and the query -> image map are those of the plan.
 extern "C" int ddf_msda_tile_forward(const float* value, const float* reference_points, const float* offsets,
                                      const float* logits, const void* plan_, float* out, int64_t N, int64_t H,
-                                     int64_t W, int64_t M, int64_t D, int64_t Lq, void* stream_) {
+                                     int64_t W, int64_t M, int64_t D, int64_t NQ, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = check_shapes(N, H, W, M, D, Lq, "msda_tile_forward");
+  int rc = check_shapes(N, H, W, M, D, NQ, "msda_tile_forward");
   if (rc) return rc;
-  if (N * Lq == 0) return DDF_OK;
+  if (N * NQ == 0) return DDF_OK;
   DDF_CHECK_ARG(value && reference_points && offsets && logits && plan_ && out, "msda_tile_forward: null pointer");
   CUtensorMap map;
   const bool tma = stage_with_tma();
@@ -642,7 +644,7 @@ extern "C" int ddf_msda_tile_forward(const float* value, const float* reference_
     ddf::set_error("msda_tile_forward: cuTensorMapEncodeTiled failed");
     return DDF_ERR_CUDA;
   }
-  const PlanLayout pl = plan_layout(N, Lq, (int)H, (int)W);
+  const PlanLayout pl = plan_layout(N, NQ, (int)H, (int)W);
   const int* plan = reinterpret_cast<const int*>(plan_);
   const int smem = kStageBytes + 128;
   const dim3 grid((unsigned)pl.NWmax, (unsigned)(M * D / 32));
@@ -650,7 +652,7 @@ extern "C" int ddf_msda_tile_forward(const float* value, const float* reference_
   do {                                                                                                            \
     DDF_SET_SMEM_ONCE((msda_tile_fwd_kernel<TPH, TMA>), smem);                                                    \
     DDF_LAUNCH((msda_tile_fwd_kernel<TPH, TMA>), grid, kThreads, smem, stream, map, value, reference_points,      \
-               offsets, logits, plan, pl.perm, pl.work, out, (int)H, (int)W, (int)M, (int)Lq, pl.TX, pl.TY);      \
+               offsets, logits, plan, pl.perm, pl.work, out, (int)H, (int)W, (int)M, (int)NQ, pl.TX, pl.TY);      \
   } while (0)
   if (D == 16) {
     if (tma) DDF_TILE_FWD(4, true); else DDF_TILE_FWD(4, false);
@@ -666,15 +668,15 @@ extern "C" int ddf_msda_tile_forward(const float* value, const float* reference_
 extern "C" int ddf_msda_tile_backward(const float* value, const float* reference_points, const float* offsets,
                                       const float* logits, const float* grad_out, const void* plan_,
                                       float* grad_value, float* grad_offsets, float* grad_logits, int64_t N,
-                                      int64_t H, int64_t W, int64_t M, int64_t D, int64_t Lq, void* stream_) {
+                                      int64_t H, int64_t W, int64_t M, int64_t D, int64_t NQ, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = check_shapes(N, H, W, M, D, Lq, "msda_tile_backward");
+  int rc = check_shapes(N, H, W, M, D, NQ, "msda_tile_backward");
   if (rc) return rc;
   if (N > 0) {
     DDF_CHECK_ARG(grad_value != nullptr, "msda_tile_backward: null grad_value");
     DDF_CUDA(cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)(N * H * W * M * D), stream));
   }
-  if (N * Lq == 0) return DDF_OK;
+  if (N * NQ == 0) return DDF_OK;
   DDF_CHECK_ARG(value && reference_points && offsets && logits && grad_out && plan_ && grad_offsets && grad_logits,
                 "msda_tile_backward: null pointer");
   CUtensorMap map;
@@ -683,7 +685,7 @@ extern "C" int ddf_msda_tile_backward(const float* value, const float* reference
     ddf::set_error("msda_tile_backward: cuTensorMapEncodeTiled failed");
     return DDF_ERR_CUDA;
   }
-  const PlanLayout pl = plan_layout(N, Lq, (int)H, (int)W);
+  const PlanLayout pl = plan_layout(N, NQ, (int)H, (int)W);
   const int* plan = reinterpret_cast<const int*>(plan_);
   const int smem = kStageBytes + 128;
   const dim3 grid((unsigned)pl.NWmax, (unsigned)(M * D / 32));
@@ -692,7 +694,7 @@ extern "C" int ddf_msda_tile_backward(const float* value, const float* reference
     DDF_SET_SMEM_ONCE((msda_tile_bwd_kernel<TPH, TMA>), smem);                                                    \
     DDF_LAUNCH((msda_tile_bwd_kernel<TPH, TMA>), grid, kThreads, smem, stream, map, value, reference_points,      \
                offsets, logits, grad_out, plan, pl.perm, pl.work, grad_value, grad_offsets, grad_logits, (int)H,  \
-               (int)W, (int)M, (int)Lq, pl.TX, pl.TY);                                                            \
+               (int)W, (int)M, (int)NQ, pl.TX, pl.TY);                                                            \
   } while (0)
   if (D == 16) {
     if (tma) DDF_TILE_BWD(4, true); else DDF_TILE_BWD(4, false);

@@ -61,10 +61,13 @@ class ACTR(nn.Module):
         # kept for attribute parity; its output never reaches the encoder layers (see transformer)
         self.v_position_embedding = PositionEmbeddingSine(num_pos_feats=hidden_dim // 2, normalize=True)
 
-    def forward(self, v_feat, grid, i_feats, v_i_feat=None, lidar_grid=None):
+    def forward(self, v_feat, grid, i_feats, v_i_feat=None, lidar_grid=None, valid_index=None):
         """v_feat (B', Lq, C) voxel-query features (zero-padded rows included), grid (B', Lq, 2)
         reference points in [0,1], i_feats list of (B', Cimg, H, W), v_i_feat (B', Lq, Cimg) the
-        camera feature under each query, lidar_grid (B', Lq, 3) xyz.  Returns (B', Lq, C)."""
+        camera feature under each query, lidar_grid (B', Lq, 3) xyz.  Returns (B', Lq, C).
+        ``valid_index`` (ours, optional): flat positions of the real queries in the padded layout; the encoder layers
+        then skip the padding (see DeformableTransformerEncoder.forward). The input projections / GroupNorm above the
+        encoder always see the padded layout, whose statistics include the padded rows."""
         q_feat = v_feat
         q_i_feat = None
         if self.feature_modal in ["image", "hybrid"]:
@@ -81,7 +84,7 @@ class ACTR(nn.Module):
             q_pos = self.q_position_embedding(lidar_grid[..., 0].clone()).transpose(1, 2)
         srcs = [self.input_proj[l](src) for l, src in enumerate(i_feats)]
         return self.transformer(srcs, None, None, q_feat, q_pos, grid, q_lidar_grid=lidar_grid,
-                                q_i_feat_flatten=q_i_feat)
+                                q_i_feat_flatten=q_i_feat, valid_index=valid_index)
 
 
 def _cfg_get(cfg, key, default=None):

@@ -146,10 +146,20 @@ class DeformableTransformerEncoder(nn.Module):
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None,
                 padding_mask=None, q_feat=None, q_pos=None, q_reference_points=None,
-                q_lidar_grid=None, q_i_feat=None):
+                q_lidar_grid=None, q_i_feat=None, valid_index=None):
+        """``valid_index`` (optional, 1-D long): flat positions (row * Lq + col) of the REAL queries inside the
+        zero-padded (B', Lq) layout. Everything the encoder layers do is row-wise (Linear, LayerNorm, FFN, the gate,
+        MSDA per query), so with it the layers run on the real rows only and the padded rows of the returned tensor
+        are zero - the fusion wrappers drop them anyway (agg_param). Without it (or with the 3D local self-attention,
+        whose FPS / ball query see the padding) the padded layout is processed as in the reference."""
         if q_reference_points is None:
             raise NotImplementedError("image->point direction (IACTR) is not part of the 3D-DF hot path")
         reference_points = q_reference_points[:, :, None] * valid_ratios[:, None]
+        if valid_index is not None and self.model_name != "ACTRv2":
+            out = self._forward_compact(src, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                                        q_feat, q_pos, q_i_feat, valid_index)
+            if out is not None:
+                return out
         plan = self._tile_plan(src, reference_points, spatial_shapes)
         geom = None
         for idx, layer in enumerate(self.layers):
@@ -161,6 +171,22 @@ class DeformableTransformerEncoder(nn.Module):
             q_feat, q_i_feat = layer(src, pos, reference_points, spatial_shapes, level_start_index,
                                      padding_mask, q_pos=q_pos, q_feat=q_feat, q_i_feat=q_i_feat, plan=plan)
         return q_feat
+
+    def _forward_compact(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask, q_feat,
+                         q_pos, q_i_feat, valid_index):
+        if self._tile_plan(src, reference_points[:1, :1], spatial_shapes) is None:
+            return None       # the generic MSDA op needs the regular (N, Lq) layout
+        Bp, Lq, C = q_feat.shape
+        pick = lambda t: None if t is None else t.reshape(Bp * Lq, -1).index_select(0, valid_index)[None]
+        qf, qi, qp = pick(q_feat), pick(q_i_feat), pick(q_pos)
+        ref = reference_points.reshape(Bp * Lq, -1, 2).index_select(0, valid_index)
+        plan = _msda.TilePlan(ref[:, 0], *self.spatial_hw, query_batch=valid_index // Lq, n_images=Bp)
+        ref = ref[None]
+        for layer in self.layers:
+            qf, qi = layer(src, pos, ref, spatial_shapes, level_start_index, padding_mask, q_pos=qp, q_feat=qf,
+                           q_i_feat=qi, plan=plan)
+        out = q_feat.new_zeros((Bp * Lq, C)).index_copy(0, valid_index, qf[0])
+        return out.view(Bp, Lq, C)
 
     def _tile_plan(self, src, reference_points, spatial_shapes):
         """One tile binning of the queries for all layers (and their backward): the reference points do not change
@@ -216,7 +242,7 @@ class DeformableTransformerACTR(nn.Module):
         return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
 
     def forward(self, srcs, masks, pos_embeds, q_feat_flatten, q_pos, q_ref_coors, q_lidar_grid=None,
-                q_i_feat_flatten=None):
+                q_i_feat_flatten=None, valid_index=None):
         """srcs: per-level (B', C, H, W) projected camera maps. ``masks`` may be None (= no padding,
         which is what ACTR always passes: all-False masks, actr.py:172-176) — then valid ratios are 1
         and no masked_fill is issued. ``pos_embeds`` is accepted for signature parity; the encoder
@@ -243,7 +269,7 @@ class DeformableTransformerACTR(nn.Module):
         return self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, None,
                             mask_flatten, q_pos=q_pos, q_feat=q_feat_flatten,
                             q_reference_points=q_ref_coors, q_lidar_grid=q_lidar_grid,
-                            q_i_feat=q_i_feat_flatten)
+                            q_i_feat=q_i_feat_flatten, valid_index=valid_index)
 
 
 def build_deformable_transformer(args, model_name="ACTR", lt_cfg=None):

@@ -93,14 +93,15 @@ class MSDeformAttn(nn.Module):
             if "weight" in self.q_rep_place:
                 weight_query = new_query
 
-        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
-        attention_weights = self.attention_weights(weight_query).view(N, Len_q, M, L * P)
+        Nq = query.shape[0]     # == N, or 1 for a ragged query list (plan.qbatch names the image of every query)
+        sampling_offsets = self.sampling_offsets(query).view(Nq, Len_q, M, L, P, 2)
+        attention_weights = self.attention_weights(weight_query).view(Nq, Len_q, M, L * P)
         if plan is not None:
             # hot path: softmax, the location arithmetic and the sampling run as ONE tile-staged kernel
             # (csrc/msda_tile.cu); ``plan`` (ops.msda.TilePlan) carries the reference points binned by image tile
             output = _msda.MSDeformAttnTileFunction.apply(value, sampling_offsets, attention_weights, plan)
             return self.output_proj(output)
-        attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
+        attention_weights = F.softmax(attention_weights, -1).view(Nq, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.stack(
                 [input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)

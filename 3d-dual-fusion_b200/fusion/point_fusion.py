@@ -177,9 +177,11 @@ class ACTR(nn.Module):
             sids.append(torch.full_like(cam, b))
         cam, grid, grid_o, sid = (torch.cat(x) for x in (cams, grids, grids_o, sids))
         xyz = torch.cat([p[:, :3] for p in pts])
-        feats_n, img_n, grid_n, xyz_n, row, col, _ = self.split_param(
+        feats_n, img_n, grid_n, xyz_n, row, col, max_points = self.split_param(
             pts_feats, cam, grid, grid_o, img_feats, xyz, sid, n_cam)
-        enh_n = self.actr(v_feat=feats_n, grid=grid_n, i_feats=img_feats, lidar_grid=xyz_n, v_i_feat=img_n)
+        # the encoder layers only have to visit the real queries (row, col) of the padded layout
+        enh_n = self.actr(v_feat=feats_n, grid=grid_n, i_feats=img_feats, lidar_grid=xyz_n, v_i_feat=img_n,
+                          valid_index=row * max_points + col)
         enh = enh_n[row, col]                                                  # agg_param + concat
         if self.fusion_method == "replace":
             fuse_out = enh

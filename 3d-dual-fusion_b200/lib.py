@@ -25,7 +25,7 @@ _SIGNATURES = {
     "ddf_ms_deform_attn_backward": [c_ptr] * 9 + [c_i64] * 8 + [c_int, c_ptr],
     "ddf_msda_tile_supported": [c_i64] * 4,
     "ddf_msda_plan_bytes": [c_i64] * 4,
-    "ddf_msda_plan": [c_ptr, c_ptr] + [c_i64] * 4 + [c_ptr],
+    "ddf_msda_plan": [c_ptr, c_ptr, c_ptr] + [c_i64] * 5 + [c_ptr],
     "ddf_msda_tile_forward": [c_ptr] * 6 + [c_i64] * 6 + [c_ptr],
     "ddf_msda_tile_backward": [c_ptr] * 9 + [c_i64] * 6 + [c_ptr],
     "ddf_hard_voxelize_workspace_bytes": [c_i64] * 3,

@@ -97,32 +97,44 @@ def tile_supported(M, D, L, P, dtype=torch.float32):
 
 class TilePlan(object):
     """Queries binned by feature-map tile (ddf_msda_plan). Built once per encoder forward from the reference
-    points; shared by every layer's forward and backward."""
+    points; shared by every layer's forward and backward.
 
-    def __init__(self, reference_points, H, W):
+    Regular layout: ``reference_points`` (N, Lq, [1,] 2), query (b, q) samples image b.  Ragged layout
+    (``query_batch`` given): ``reference_points`` (NQ, 2) are only the real queries of the padded per-camera layout and
+    ``query_batch`` (NQ,) int32 names the image each one samples; the per-query tensors handed to the kernels are then
+    (1, NQ, ...)."""
+
+    def __init__(self, reference_points, H, W, query_batch=None, n_images=None):
         ref = reference_points
-        if ref.dim() == 4:           # (N, Lq, L=1, 2)
-            ref = ref[:, :, 0]
         _lib.require_cuda(ref)
+        if query_batch is None:
+            if ref.dim() == 4:           # (N, Lq, L=1, 2)
+                ref = ref[:, :, 0]
+            self.N, self.Lq = ref.shape[0], ref.shape[1]
+            self.NQ = self.N * self.Lq
+            self.qbatch = None
+        else:
+            ref = ref.reshape(-1, 2)
+            self.N, self.Lq, self.NQ = int(n_images), 0, ref.shape[0]
+            self.qbatch = query_batch.to(torch.int32).contiguous()
         self.ref = ref.detach().contiguous().float()
-        self.N, self.Lq = self.ref.shape[0], self.ref.shape[1]
         self.H, self.W = int(H), int(W)
         L = _lib.get_lib()
-        nbytes = int(L.ddf_msda_plan_bytes(self.N, self.Lq, self.H, self.W))
+        nbytes = int(L.ddf_msda_plan_bytes(self.N, self.NQ, self.H, self.W))
         self.buf = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=ref.device)
         with torch.cuda.device(ref.device):
-            rc = L.ddf_msda_plan(_lib.ptr(self.ref), _lib.ptr(self.buf), self.N, self.Lq, self.H, self.W,
-                                 _lib.current_stream())
+            rc = L.ddf_msda_plan(_lib.ptr(self.ref), _lib.ptr(self.qbatch), _lib.ptr(self.buf), self.N, self.NQ, self.Lq,
+                                 self.H, self.W, _lib.current_stream())
         _lib.check(rc, "msda_plan")
 
 
 def msda_tile_forward(value, plan, offsets, logits):
     N, S, M, D = value.shape
-    out = torch.empty((N, plan.Lq, M * D), dtype=value.dtype, device=value.device)
+    out = torch.empty(tuple(offsets.shape[:2]) + (M * D,), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
         rc = _lib.get_lib().ddf_msda_tile_forward(
             _lib.ptr(value), _lib.ptr(plan.ref), _lib.ptr(offsets), _lib.ptr(logits), _lib.ptr(plan.buf),
-            _lib.ptr(out), N, plan.H, plan.W, M, D, plan.Lq, _lib.current_stream())
+            _lib.ptr(out), N, plan.H, plan.W, M, D, plan.NQ, _lib.current_stream())
     _lib.check(rc, "msda_tile_forward")
     return out
 
@@ -136,7 +148,7 @@ def msda_tile_backward(value, plan, offsets, logits, grad_out):
         rc = _lib.get_lib().ddf_msda_tile_backward(
             _lib.ptr(value), _lib.ptr(plan.ref), _lib.ptr(offsets), _lib.ptr(logits), _lib.ptr(grad_out),
             _lib.ptr(plan.buf), _lib.ptr(grad_value), _lib.ptr(grad_off), _lib.ptr(grad_logit), N, plan.H, plan.W,
-            M, D, plan.Lq, _lib.current_stream())
+            M, D, plan.NQ, _lib.current_stream())
     _lib.check(rc, "msda_tile_backward")
     return grad_value, grad_off, grad_logit
 
@@ -144,7 +156,8 @@ def msda_tile_backward(value, plan, offsets, logits, grad_out):
 class MSDeformAttnTileFunction(Function):
     """out = MSDA(value, loc = ref + offsets / (W, H), softmax(logits)): the module arithmetic of
     ops/modules/ms_deform_attn.py:149-188 as one op. value (N, H*W, M, D), offsets (N, Lq, M, 1, 4, 2) raw,
-    logits (N, Lq, M, 4); reference points live in ``plan`` (no gradient flows to them)."""
+    logits (N, Lq, M, 4) - or (1, NQ, ...) for a ragged plan; reference points live in ``plan`` (no gradient flows
+    to them)."""
 
     @staticmethod
     def forward(ctx, value, offsets, logits, plan):
@@ -152,7 +165,8 @@ class MSDeformAttnTileFunction(Function):
             if t.dtype != torch.float32 or not t.is_cuda:
                 raise RuntimeError("msda tile kernels: CUDA float32 tensors only")
         value, offsets, logits = value.contiguous(), offsets.contiguous(), logits.contiguous()
-        if value.shape[0] != plan.N or value.shape[1] != plan.H * plan.W or offsets.shape[1] != plan.Lq:
+        if (value.shape[0] != plan.N or value.shape[1] != plan.H * plan.W
+                or offsets.shape[0] * offsets.shape[1] != plan.NQ or logits.shape[0] * logits.shape[1] != plan.NQ):
             raise RuntimeError("msda tile kernels: plan was built for another problem size")
         ctx.plan = plan
         ctx.save_for_backward(value, offsets, logits)

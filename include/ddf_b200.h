@@ -81,16 +81,23 @@ int ddf_ms_deform_attn_backward(const void* value, const int64_t* spatial_shapes
  * (ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299) and its backward (:301-403).  Queries are binned by image
  * tile once per encoder forward (ddf_msda_plan; reference points are shared by all layers and by backward),
  * every CTA stages its tile + halo of `value` in shared memory with one 4-D TMA box load.
- *   value [N, H*W, M, D]; reference_points [N, Lq, 2]; offsets [N, Lq, M, 1, 4, 2] (raw Linear output, pixels);
- *   logits [N, Lq, M, 4]; out [N, Lq, M*D].  Backward returns grads wrt value, offsets and logits.
+ *   value [N, H*W, M, D]; reference_points [NQ, 2]; offsets [NQ, M, 1, 4, 2] (raw Linear output, pixels);
+ *   logits [NQ, M, 4]; out [NQ, M*D].  Backward returns grads wrt value, offsets and logits.
+ * Queries: either the regular layout NQ = N * Lq (query i samples image i / Lq; query_batch = NULL), or a ragged list
+ * of only the REAL queries of the zero-padded per-camera layout with query_batch [NQ] int32 = image of each query
+ * (the row-wise work of the encoder then skips the padding).
  * ddf_msda_tile_supported: 1 when (M, D, L, P) is handled here (else use ddf_ms_deform_attn_*). */
 int ddf_msda_tile_supported(int64_t M, int64_t D, int64_t L, int64_t P);
-int64_t ddf_msda_plan_bytes(int64_t N, int64_t Lq, int64_t H, int64_t W);
-int ddf_msda_plan(const float* reference_points, void* plan, int64_t N, int64_t Lq, int64_t H, int64_t W,
-                  void* stream);
+int64_t ddf_msda_plan_bytes(int64_t N, int64_t NQ, int64_t H, int64_t W);
+int ddf_msda_plan(const float* reference_points, const int* query_batch, void* plan, int64_t N, int64_t NQ,
+                  int64_t Lq, int64_t H, int64_t W, void* stream);
 int ddf_msda_tile_forward(const float* value, const float* reference_points, const float* offsets,
                           const float* logits, const void* plan, float* out, int64_t N, int64_t H, int64_t W,
-                          int64_t M, int64_t D, int64_t Lq, void* stream);
+                          int64_t M, int64_t D, int64_t NQ, void* stream);
+int ddf_msda_tile_backward(const float* value, const float* reference_points, const float* offsets,
+                           const float* logits, const float* grad_out, const void* plan, float* grad_value,
+                           float* grad_offsets, float* grad_logits, int64_t N, int64_t H, int64_t W, int64_t M,
+                           int64_t D, int64_t NQ, void* stream);
 int ddf_msda_tile_backward(const float* value, const float* reference_points, const float* offsets,
                            const float* logits, const float* grad_out, const void* plan, float* grad_value,
                            float* grad_offsets, float* grad_logits, int64_t N, int64_t H, int64_t W, int64_t M,

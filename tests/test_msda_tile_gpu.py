@@ -121,3 +121,48 @@ def test_tile_msda_cp_async_staging_variant():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(root, "tests", "test_msda_tile_gpu.py"),
                         "-k", "matches_module_arithmetic", "-m", "gpu"], env=env, capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_compact_encoder_equals_padded_encoder_on_real_rows():
+    """The encoder with ``valid_index`` (layers visit only the real queries; ragged MSDA plan) returns, on those rows,
+    what the padded pass returns - forward and parameter gradients (loss over the real rows only, as the wrappers use it)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden"))
+    import detfill
+    from ddf_b200.fusion import actr
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = dict(num_channels=[64], query_num_feat=128, num_enc_layers=2, max_num_ne_voxel=26000, pos_encode_method="depth",
+               feature_modal="hybrid", hybrid_cfg=dict(attn_layer="BiGateSum1D_2", q_method="sum", q_rep_place=["weight"]))
+    net = actr.build(cfg).cuda().train()
+    detfill.fill_state_dict(net)
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    Bp, Lq, H, W = 6, 300, 28, 50
+    g = torch.Generator().manual_seed(3)
+    counts = [300, 120, 0, 77, 250, 1]
+    valid = torch.cat([b * Lq + torch.arange(c) for b, c in enumerate(counts)]).cuda()
+    mask = torch.zeros(Bp * Lq, 1, device="cuda")
+    mask[valid] = 1
+    pad = lambda t: (t.reshape(Bp * Lq, -1) * mask).reshape(t.shape)
+    v_feat = pad(torch.randn(Bp, Lq, 128, generator=g).cuda())
+    grid = pad(torch.rand(Bp, Lq, 2, generator=g).cuda())
+    v_i = pad(torch.randn(Bp, Lq, 64, generator=g).cuda())
+    lidar = pad((torch.rand(Bp, Lq, 3, generator=g) * 50).cuda())
+    img = torch.randn(Bp, 64, H, W, generator=g).cuda()
+    outs, grads = [], []
+    for vi in (None, valid):
+        net.zero_grad()
+        out = net(v_feat, grid, [img], v_i, lidar, valid_index=vi)
+        sel = out.reshape(Bp * Lq, -1)[valid]
+        sel.square().sum().backward()
+        outs.append(sel.detach())
+        grads.append({n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None})
+    assert rel(outs[1], outs[0]) < 1e-5
+    assert grads[0].keys() == grads[1].keys()
+    for n in grads[0]:
+        assert rel(grads[1][n], grads[0][n]) < 1e-4, n
+    # padded rows of the compact result are zero
+    full = net(v_feat, grid, [img], v_i, lidar, valid_index=valid).reshape(Bp * Lq, -1)
+    assert float(full[mask[:, 0] == 0].abs().max()) == 0.0

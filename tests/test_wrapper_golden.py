@@ -42,9 +42,9 @@ def check(name, device, tol):
     seen = {}
     inner = layer.actr.forward
 
-    def spy(v_feat, grid, i_feats, v_i_feat=None, lidar_grid=None):
+    def spy(v_feat, grid, i_feats, v_i_feat=None, lidar_grid=None, valid_index=None):
         seen.update(v_feat=v_feat, grid=grid, lidar_grid=lidar_grid, v_i_feat=v_i_feat)
-        return inner(v_feat, grid, i_feats, v_i_feat=v_i_feat, lidar_grid=lidar_grid)
+        return inner(v_feat, grid, i_feats, v_i_feat=v_i_feat, lidar_grid=lidar_grid, valid_index=valid_index)
     layer.actr.forward = spy
     with torch.no_grad():
         out = layer([t.to(device) for t in data["img_feats"]], [p.to(device) for p in data["pts"]],

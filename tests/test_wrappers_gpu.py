@@ -18,7 +18,7 @@ class Recorder(torch.nn.Module):
     num_backbone_outs = 1
     max_num_ne_voxel = 0
 
-    def forward(self, v_feat, grid, i_feats, v_i_feat=None, lidar_grid=None):
+    def forward(self, v_feat, grid, i_feats, v_i_feat=None, lidar_grid=None, valid_index=None):
         self.seen = dict(v_feat=v_feat, grid=grid, v_i_feat=v_i_feat, lidar_grid=lidar_grid)
         return v_feat * 2 + grid.sum(-1, keepdim=True) + lidar_grid[..., :1]
 
