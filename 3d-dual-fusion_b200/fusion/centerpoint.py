@@ -315,6 +315,7 @@ class VoxelWithPointProjection(nn.Module):
 
         ref = torch.stack([qx, qy], -1).float() / torch.tensor([Wf, Hf], dtype=torch.float32, device=feats.device)
         enh = self.pfat(v_feat=pad(feats[vox]), grid=pad(ref), i_feats=[img], lidar_grid=pad(pts[vox]),
-                        v_i_feat=pad(v_i), valid_index=group * max_ne + col)
+                        v_i_feat=pad(v_i),
+                        valid_index=(group * max_ne + col) if group.numel() < 0.75 * n_groups * max_ne else None)
         new = feats.index_add(0, vox, enh[group, col])       # one additive update per (voxel, camera)
         return encoded_voxel.replace_feature(new)

@@ -179,9 +179,12 @@ class ACTR(nn.Module):
         xyz = torch.cat([p[:, :3] for p in pts])
         feats_n, img_n, grid_n, xyz_n, row, col, max_points = self.split_param(
             pts_feats, cam, grid, grid_o, img_feats, xyz, sid, n_cam)
-        # the encoder layers only have to visit the real queries (row, col) of the padded layout
+        # when the per-camera counts are unbalanced (real data: voxels no camera sees all become camera-0 queries) the
+        # encoder layers only visit the real queries (row, col) of the padded layout; with balanced counts the
+        # gather / scatter around them costs more than the padding
+        ragged = pts_feats.shape[0] < 0.75 * feats_n.shape[0] * max_points
         enh_n = self.actr(v_feat=feats_n, grid=grid_n, i_feats=img_feats, lidar_grid=xyz_n, v_i_feat=img_n,
-                          valid_index=row * max_points + col)
+                          valid_index=(row * max_points + col) if ragged else None)
         enh = enh_n[row, col]                                                  # agg_param + concat
         if self.fusion_method == "replace":
             fuse_out = enh
