@@ -97,6 +97,33 @@ relu_dropout_bwd_bias_kernel(const float* __restrict__ gy, const float* __restri
   }
 }
 
+// ---- column sums of a tall [rows, C] matrix: the bias gradient of a Linear over all tokens -------------------
+// autograd's grad.sum(0) on a [146 k, 128] tensor runs 14x below the HBM rate in ATen (168 us for 75 MB, torch
+// profiler, B200); here a thread owns 4 columns and walks the rows grid-stride, one shared-memory fold and one
+// atomicAdd per column and CTA.  out must be zeroed by the caller.  C / 4 <= 256 and 256 % (C / 4) == 0.
+__global__ void __launch_bounds__(kThreads)
+col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int c4) {
+  const int col = threadIdx.x % c4, rl = threadIdx.x / c4, rpb = kThreads / c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+    const float4 v = ldg4(x + (r * c4 + col) * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __shared__ float4 sh[kThreads];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 1; j < rpb; ++j) {
+      const float4 t = sh[j * c4 + col];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomicAdd(out + col * 4, acc.x);
+    atomicAdd(out + col * 4 + 1, acc.y);
+    atomicAdd(out + col * 4 + 2, acc.z);
+    atomicAdd(out + col * 4 + 3, acc.w);
+  }
+}
+
 // ---- s = a + dropout(b);  y = LayerNorm(s) * gamma + beta.  One warp per row, C = 32 * VPL * 4 ---------
 template <int VPL>   // float4 vectors per lane: C = 128 * VPL
 __global__ void __launch_bounds__(kThreads)
@@ -321,6 +348,23 @@ extern "C" int ddf_add_dropout_layer_norm_backward(const float* grad_y, const fl
   DDF_LN_DISPATCH(C, DDF_LAUNCH(add_dropout_ln_bwd_kernel<VPL>, (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_y,
                                 s, gamma, mean, rstd, grad_a, grad_b, grad_gamma, grad_beta, (long long)rows,
                                 (unsigned long long)seed, threshold(p), 1.f / (1.f - p)));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// out [C] = sum over the rows of x [rows, C] (zeroed inside).  C % 4 == 0, C / 4 <= 256, 256 % (C / 4) == 0.
+extern "C" int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0 && C / 4 <= kThreads && kThreads % (C / 4) == 0,
+                "col_sum: C / 4 must divide %d (C=%lld)", kThreads, (long long)C);
+  DDF_CHECK_ARG(out != nullptr, "col_sum: null out");
+  DDF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, stream));
+  if (rows == 0) return DDF_OK;
+  DDF_CHECK_ARG(x != nullptr && aligned16(x), "col_sum: null / misaligned x");
+  const int c4 = (int)(C / 4), rpb = kThreads / c4;
+  long long grid = ddf::cdiv(rows, rpb);
+  if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;
+  DDF_LAUNCH(col_sum_kernel, (unsigned)grid, kThreads, 0, stream, x, out, (long long)rows, c4);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }

@@ -58,7 +58,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
             hidden = fused.ffn_hidden(self.linear1, self.dropout2, src)
         else:
             hidden = self.dropout2(self.activation(self.linear1(src)))
-        return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, self.linear2(hidden))
+        return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, fused.linear(self.linear2, hidden))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
                 padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None, plan=None):
@@ -108,11 +108,11 @@ class DeformableTransformerFusionEncoderLayer(nn.Module):
         return dropout(self.activation(linear(src)))
 
     def forward_i_ffn(self, src):
-        src2 = self.linear2(self._hidden(self.linear1, self.dropout2, src))
+        src2 = fused.linear(self.linear2, self._hidden(self.linear1, self.dropout2, src))
         return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, src2)
 
     def forward_p_ffn(self, src):
-        src2 = self.linear4(self._hidden(self.linear3, self.dropout4, src))
+        src2 = fused.linear(self.linear4, self._hidden(self.linear3, self.dropout4, src))
         return fused.add_dropout_layer_norm(self.norm3, self.dropout5, src, src2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,

@@ -10,6 +10,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
+from ..ops import fused as _fused
 from ..ops import msda as _msda
 from ..ops.msda import MSDeformAttnFunction
 from .attentions import attn_dict
@@ -70,7 +71,7 @@ class MSDeformAttn(nn.Module):
         assert input_spatial_shapes.shape[0] == self.n_levels
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
-        value = self.value_proj(input_flatten)
+        value = _fused.linear(self.value_proj, input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, M, self.d_model // M)
@@ -94,13 +95,13 @@ class MSDeformAttn(nn.Module):
                 weight_query = new_query
 
         Nq = query.shape[0]     # == N, or 1 for a ragged query list (plan.qbatch names the image of every query)
-        sampling_offsets = self.sampling_offsets(query).view(Nq, Len_q, M, L, P, 2)
-        attention_weights = self.attention_weights(weight_query).view(Nq, Len_q, M, L * P)
+        sampling_offsets = _fused.linear(self.sampling_offsets, query).view(Nq, Len_q, M, L, P, 2)
+        attention_weights = _fused.linear(self.attention_weights, weight_query).view(Nq, Len_q, M, L * P)
         if plan is not None:
             # hot path: softmax, the location arithmetic and the sampling run as ONE tile-staged kernel
             # (csrc/msda_tile.cu); ``plan`` (ops.msda.TilePlan) carries the reference points binned by image tile
             output = _msda.MSDeformAttnTileFunction.apply(value, sampling_offsets, attention_weights, plan)
-            return self.output_proj(output)
+            return _fused.linear(self.output_proj, output)
         attention_weights = F.softmax(attention_weights, -1).view(Nq, Len_q, M, L, P)
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.stack(
@@ -116,4 +117,4 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                             sampling_locations.contiguous(), attention_weights,
                                             self.im2col_step)
-        return self.output_proj(output)
+        return _fused.linear(self.output_proj, output)

@@ -57,6 +57,55 @@ class _BiasReluDropout(Function):
         return gh, gb, None
 
 
+def col_sum(x2d):
+    """Column sums of a contiguous fp32 (rows, C) CUDA matrix (ddf_col_sum)."""
+    out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.get_lib().ddf_col_sum(_lib.ptr(x2d), _lib.ptr(out), x2d.shape[0], x2d.shape[1], _lib.current_stream())
+    _lib.check(rc, "col_sum")
+    return out
+
+
+def _col_sum_ok(C):
+    return C % 4 == 0 and C // 4 <= 256 and 256 % (C // 4) == 0
+
+
+class _Linear(Function):
+    """F.linear over (..., Cin) tokens whose bias gradient is one pass at the HBM rate (ddf_col_sum) instead of
+    ATen's grad.sum(0) (168 us for a [146 k, 128] gradient on B200 = 14x below the copy rate); the GEMMs stay in the
+    library."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x.reshape(-1, x.shape[-1])
+        if ctx.needs_input_grad[2]:
+            gb = col_sum(g2)
+        return gx, gw, gb
+
+
+def linear(module, x):
+    """``module(x)`` for an ``nn.Linear`` applied to many tokens (same parameters, same forward GEMM)."""
+    if (module.bias is None or not x.is_cuda or x.dtype != torch.float32 or module.weight.dtype != torch.float32
+            or not _col_sum_ok(module.out_features) or not torch.is_grad_enabled()
+            or x.numel() // max(x.shape[-1], 1) < 4096):
+        return module(x)
+    return _Linear.apply(x, module.weight, module.bias)
+
+
 def ffn_hidden(linear, dropout, x):
     """``dropout(relu(linear(x)))``: the GEMM without bias, then bias + ReLU + dropout in one in-place pass."""
     C = linear.out_features

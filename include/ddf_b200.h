@@ -374,6 +374,10 @@ int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, con
                                         float* grad_gamma, float* grad_beta, int64_t rows, int64_t C,
                                         float p, uint64_t seed, void* stream);
 
+/* out [C] = column sums of x [rows, C] (the bias gradient of a Linear over all tokens; zeroed inside).
+ * C % 4 == 0 and C / 4 must divide 256. */
+int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,3 +111,23 @@ def test_unsupported_shapes_use_library_ops_and_cpu_is_refused():
     assert torch.allclose(add_dropout_layer_norm(norm, drop, x, x), norm(x + x))
     with pytest.raises(RuntimeError):
         ffn_hidden(nn.Linear(128, 256), drop, torch.randn(4, 128))
+
+
+def test_linear_with_fast_bias_gradient_equals_nn_linear():
+    from ddf_b200.ops import fused
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(128, 64).cuda()
+    x = torch.randn(3, 4000, 128, device="cuda", requires_grad=True)
+    y = fused.linear(lin, x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    got = (x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None
+    lin.zero_grad()
+    y2 = lin(x)
+    y2.backward(g)
+    assert torch.equal(y, y2)
+    for a, b in zip(got, (x.grad, lin.weight.grad, lin.bias.grad)):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    big = torch.randn(146016, 128, device="cuda")
+    assert float((fused.col_sum(big) - big.double().sum(0).float()).abs().max()) < 1e-2
