@@ -5,6 +5,7 @@ defaults of ``ActrArgs`` here."""
 import torch
 from torch import nn
 
+from ..ops import fused as _fused
 from .actr_transformer import build_deformable_transformer
 from .position_encoding import (PositionEmbeddingLearnedDepth, PositionEmbeddingSine,
                                 PositionEmbeddingSineSparse, PositionEmbeddingSineSparseDepth)
@@ -74,7 +75,7 @@ class ACTR(nn.Module):
             assert v_i_feat is not None
             # Conv1d(k=1) on (B', C, Lq) == Linear on (B', Lq, C): skip the two transposes around it
             conv, gn = self.i_input_proj[0], self.i_input_proj[1]
-            q_i_feat = torch.nn.functional.linear(v_i_feat, conv.weight.squeeze(-1), conv.bias)
+            q_i_feat = _fused.linear_wb(v_i_feat, conv.weight.squeeze(-1), conv.bias)
             q_i_feat = gn(q_i_feat.transpose(1, 2)).transpose(1, 2)
             if self.feature_modal == "image":
                 q_feat = q_i_feat

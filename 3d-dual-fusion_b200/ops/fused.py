@@ -106,6 +106,15 @@ def linear(module, x):
     return _Linear.apply(x, module.weight, module.bias)
 
 
+def linear_wb(x, weight, bias):
+    """``F.linear(x, weight, bias)`` with the fast bias gradient (weight / bias given directly)."""
+    if (bias is None or not x.is_cuda or x.dtype != torch.float32 or weight.dtype != torch.float32
+            or not _col_sum_ok(weight.shape[0]) or not torch.is_grad_enabled()
+            or x.numel() // max(x.shape[-1], 1) < 4096):
+        return F.linear(x, weight, bias)
+    return _Linear.apply(x, weight, bias)
+
+
 def ffn_hidden(linear, dropout, x):
     """``dropout(relu(linear(x)))``: the GEMM without bias, then bias + ReLU + dropout in one in-place pass."""
     C = linear.out_features
