@@ -139,3 +139,47 @@ def tf_wrapper_case(name, n_pts=(260, 340), ori_hw=(180, 320), scale=0.5, pad_hw
     feats = torch.from_numpy(detfill.uniform(name + "/pts_feats", (sum(n_pts), c_pts)))
     img = torch.from_numpy(detfill.uniform(name + "/img", (B * len(CAMS), c_img, pad_hw[0] // 4, pad_hw[1] // 4)))
     return dict(pts=pts, pts_feats=feats, img_feats=[img], img_metas=metas, tables=tables)
+
+
+# ---- CenterPoint wrapper: Det3D batch pieces ---------------------------------------------------------------
+CP_CAMS = ["CAM_FRONT", "CAM_FRONT_LEFT", "CAM_FRONT_RIGHT", "CAM_BACK", "CAM_BACK_LEFT", "CAM_BACK_RIGHT"]
+CP_YAW_DEG = [0.0, 55.0, -55.0, 180.0, 110.0, -110.0]
+CP_VOXEL = [0.075, 0.075, 0.2]
+CP_RANGE = [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+
+
+def cp_wrapper_case(name, batch=2, n_vox=(220, 160, 120), chans=(8, 16, 64), c_img=32, img_hw=(60, 107), feat_hw=(15, 27),
+                    ori_hw=(90, 160)):
+    """Inputs of ``FUSION['VoxelWithPointProjection'].forward`` (fuse_mode 'pfat'): three sparse tensors (x_conv2..4,
+    d_factor 2/4/8) as (indices, features) pairs, per-camera calibration / image shapes / feature maps."""
+    focal = 0.8 * ori_hw[1]
+    K = np.array([[focal, 0, ori_hw[1] / 2.0], [0, focal, ori_hw[0] / 2.0], [0, 0, 1]], np.float64)
+    calib, image_shape, img_feat = {}, {}, {}
+    for cam, yaw in zip(CP_CAMS, CP_YAW_DEG):
+        key = cam.lower()[4:]
+        th = np.deg2rad(yaw)
+        R = np.stack([[np.sin(th), -np.cos(th), 0.0], [0.0, 0.0, -1.0], [np.cos(th), np.sin(th), 0.0]])
+        ext = np.eye(4)
+        ext[:3, :3] = R @ _small_rot(name + cam)
+        ext[:3, 3] = -ext[:3, :3] @ np.array([0.3 * np.cos(th), 0.3 * np.sin(th), -0.3])
+        calib["lidar2cam_" + key] = torch.from_numpy(np.repeat(ext[None], batch, 0).astype(np.float32))
+        calib["cam_intrinsic_" + key] = torch.from_numpy(np.repeat(K[None], batch, 0).astype(np.float32))
+        image_shape[cam.lower()] = torch.tensor([list(img_hw)] * batch)
+        img_feat[cam.lower()] = torch.from_numpy(detfill.uniform(name + "/img/" + cam, (batch, c_img, *feat_hw)))
+    tensors = []
+    for s, (n, c, d) in enumerate(zip(n_vox, chans, (2, 4, 8))):
+        dims = (40 // d + 1, 1440 // d, 1440 // d)
+        idx = []
+        for b in range(batch):
+            nb = n - 17 * b
+            z = (detfill.uniform("%s/z%d%d" % (name, s, b), (nb,), 0, 1) * dims[0] * 0.6).astype(np.int64)
+            ang = detfill.uniform("%s/a%d%d" % (name, s, b), (nb,), -np.pi, np.pi)
+            rad = detfill.uniform("%s/r%d%d" % (name, s, b), (nb,), 2.0, 50.0)
+            x = ((rad * np.cos(ang) - CP_RANGE[0]) / (CP_VOXEL[0] * d)).astype(np.int64)
+            y = ((rad * np.sin(ang) - CP_RANGE[1]) / (CP_VOXEL[1] * d)).astype(np.int64)
+            cells = np.unique(np.stack([np.full(nb, b), z, y, x], 1), axis=0)      # sorted by (b, z, y, x), no duplicates
+            idx.append(cells)
+        idx = np.concatenate(idx)
+        feat = detfill.uniform("%s/feat%d" % (name, s), (len(idx), c))
+        tensors.append((torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(feat)))
+    return dict(tensors=tensors, calib=calib, image_shape=image_shape, img_feat={"layer1_ori_feat2d": img_feat})
