@@ -62,10 +62,55 @@ def reverse_3d_transformation(points, img_meta):
     return pts
 
 
+def _project_params(img_meta):
+    scale = img_meta.get("scale_factor", None)
+    sx, sy = (float(scale[0]), float(scale[1])) if scale is not None else (1.0, 1.0)
+    crop = img_meta.get("img_crop_offset", None)
+    cx, cy = (float(crop[0]), float(crop[1])) if crop is not None else (0.0, 0.0)
+    flip_w = float(img_meta["img_shape"][1]) if img_meta.get("flip", False) else -1.0
+    pad_h, pad_w = img_meta["input_shape"][:2]
+    ori_h, ori_w = img_meta["ori_shape"][:2]
+    return float(ori_h), float(ori_w), sx, sy, cx, cy, flip_w, float(pad_h), float(pad_w)
+
+
+def project_to_cameras_cuda(points, img_meta, group_base=0):
+    """``project_to_cameras`` as ONE kernel (csrc/projection.cu: ddf_project_assign). Returns group = group_base +
+    camera (int32), grid, grid_o."""
+    import ctypes
+    import numpy as np
+    from .. import lib as _lib
+    pts = reverse_3d_transformation(points, img_meta).contiguous().float()
+    n = pts.shape[0]
+    l2i = np.ascontiguousarray(np.asarray(img_meta["lidar2img"], dtype=np.float32).reshape(-1, 4, 4))
+    group = torch.empty(n, dtype=torch.int32, device=pts.device)
+    grid = torch.empty((n, 2), dtype=torch.float32, device=pts.device)
+    grid_o = torch.empty((n, 2), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        rc = _lib.get_lib().ddf_project_assign(
+            _lib.ptr(pts), n, pts.shape[1], l2i.ctypes.data_as(ctypes.c_void_p), l2i.shape[0], *_project_params(img_meta),
+            int(group_base), _lib.ptr(group), _lib.ptr(grid), _lib.ptr(grid_o), _lib.current_stream())
+    _lib.check(rc, "project_assign")
+    return group, grid, grid_o
+
+
+def group_ranks(group, n_groups):
+    """Stable rank of every query inside its (sample, camera) group + the group sizes (ddf_group_ranks)."""
+    from .. import lib as _lib
+    n = group.shape[0]
+    col = torch.empty(n, dtype=torch.int32, device=group.device)
+    counts = torch.empty(n_groups, dtype=torch.int32, device=group.device)
+    with torch.cuda.device(group.device):
+        rc = _lib.get_lib().ddf_group_ranks(_lib.ptr(group), n, n_groups, _lib.ptr(col), _lib.ptr(counts),
+                                            _lib.current_stream())
+    _lib.check(rc, "group_ranks")
+    return col, counts
+
+
 def project_to_cameras(points, img_meta):
     """points (n, 3) LiDAR xyz.  Returns cam (n,) int64 in [0, n_cam) (0 for unseen voxels),
     grid (n, 2) normalised (x / W_pad, y / H_pad), grid_o (n, 2) padded-image pixels; rows of unseen
-    voxels are zero.  Follows get_2d_coor_multi (point_fusion.py:509-549) + projection (:551-643)."""
+    voxels are zero.  Follows get_2d_coor_multi (point_fusion.py:509-549) + projection (:551-643).
+    (Host-tensor form, used by the oracle-driven CPU path; CUDA tensors take project_to_cameras_cuda.)"""
     n = points.shape[0]
     dev, dtype = points.device, points.dtype
     pts = reverse_3d_transformation(points, img_meta)
@@ -134,8 +179,14 @@ class ACTR(nn.Module):
     def split_param(self, pts_feats, cam, grid, grid_o, img_feats, pts_xyz, sample_id, n_cam):
         """Group the concatenated voxel queries by (sample, camera) and zero-pad to the largest
         group. Returns the padded tensors and (row, col) of every query inside them."""
-        group = sample_id * n_cam + cam
         n_groups = img_feats[0].shape[0]
+        if pts_feats.is_cuda and cam.dtype == torch.int32:
+            # ``cam`` already is the (sample, camera) group id from ddf_project_assign; ranks by ddf_group_ranks
+            col32, counts = group_ranks(cam, n_groups)
+            max_points = int(counts.max().item())
+            row, col = cam.long(), col32.long()
+            return self._pad_all(pts_feats, grid, grid_o, img_feats, pts_xyz, row, col, n_groups, max_points)
+        group = sample_id * n_cam + cam
         order = torch.sort(group, stable=True)[1]
         g_sorted = group[order]
         counts = torch.bincount(group, minlength=n_groups)
@@ -149,7 +200,9 @@ class ACTR(nn.Module):
         col = torch.empty_like(group)
         row[order] = g_sorted
         col[order] = col_sorted
+        return self._pad_all(pts_feats, grid, grid_o, img_feats, pts_xyz, row, col, n_groups, max_points)
 
+    def _pad_all(self, pts_feats, grid, grid_o, img_feats, pts_xyz, row, col, n_groups, max_points):
         def pad(x):
             out = x.new_zeros((n_groups, max_points) + tuple(x.shape[1:]))
             out[row, col] = x
@@ -158,7 +211,7 @@ class ACTR(nn.Module):
         stride = self.img_stride
         ix = grid_o[:, 0].to(torch.long) // stride
         iy = grid_o[:, 1].to(torch.long) // stride
-        img_at_query = img_feats[0][group, :, iy, ix]                        # (n, C_img)
+        img_at_query = img_feats[0][row, :, iy, ix]                          # (n, C_img)
         return (pad(pts_feats), pad(img_at_query), pad(grid), pad(pts_xyz), row, col, max_points)
 
     def forward(self, img_feats, pts, pts_feats, img_metas, imgs=None):
@@ -170,7 +223,11 @@ class ACTR(nn.Module):
         self.actr.max_num_ne_voxel = max(p.shape[0] for p in pts)
         cams, grids, grids_o, sids = [], [], [], []
         for b in range(batch_size):
-            cam, grid, grid_o = project_to_cameras(pts[b][:, :3], img_metas[b])
+            if pts_feats.is_cuda:
+                # one kernel per sample: projection to every camera + assignment; cam = (sample, camera) group id
+                cam, grid, grid_o = project_to_cameras_cuda(pts[b][:, :3], img_metas[b], group_base=b * n_cam)
+            else:
+                cam, grid, grid_o = project_to_cameras(pts[b][:, :3], img_metas[b])
             cams.append(cam)
             grids.append(grid)
             grids_o.append(grid_o)

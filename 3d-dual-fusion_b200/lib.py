@@ -67,6 +67,8 @@ _SIGNATURES = {
     "ddf_bias_relu_dropout_backward": [c_ptr] * 4 + [c_i64, c_i64, c_f32, c_ptr],
     "ddf_add_dropout_layer_norm_forward": [c_ptr] * 8 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_f32, c_ptr],
     "ddf_add_dropout_layer_norm_backward": [c_ptr] * 9 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_ptr],
+    "ddf_project_assign": [c_ptr, c_i64, c_i64, c_ptr, c_i64] + [c_f32] * 9 + [c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "ddf_group_ranks": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "ddf_col_sum": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_dense_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],

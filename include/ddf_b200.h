@@ -378,6 +378,20 @@ int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, con
  * C % 4 == 0 and C / 4 must divide 256. */
 int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream);
 
+/* ---- fusion wrapper geometry (TransFusion/mmdet3d/models/fusion_layers/point_fusion.py:342-382, 509-643) ----------
+ * ddf_project_assign: voxel centres -> camera assignment ("last camera that sees the voxel", unseen -> camera 0 at
+ *   (0, 0)) + reference points; visibility in ORIGINAL image pixels (depth > 1, 1 < u < ori_w - 1, 1 < v < ori_h - 1),
+ *   then scale -> crop -> flip (flip_w = un-padded image width, < 0 when not flipped) -> / padded size.
+ *   points [n, stride] device fp32; lidar2img_host [n_cam, 4, 4] HOST floats (composed lidar -> pixel matrices);
+ *   group [n] int32 = group_base + camera; grid [n, 2] normalised; grid_o [n, 2] padded-image pixels.
+ * ddf_group_ranks: col [n] = stable rank of every element inside its group (= its column in the zero-padded
+ *   (n_groups, max_count) layout, input order preserved), counts [n_groups]. */
+int ddf_project_assign(const float* points, int64_t n, int64_t stride, const float* lidar2img_host, int64_t n_cam,
+                       float ori_h, float ori_w, float scale_x, float scale_y, float crop_x, float crop_y, float flip_w,
+                       float pad_h, float pad_w, int64_t group_base, int* group, float* grid, float* grid_o,
+                       void* stream);
+int ddf_group_ranks(const int* group, int64_t n, int64_t n_groups, int* col, int* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,3 +278,28 @@ def test_voxelrcnn_actrv2_hybrid_path_fwd_bwd():
     out.features.square().mean().backward()
     grads = [p.grad for p in m.parameters() if p.grad is not None]
     assert len(grads) > 100 and all(bool(torch.isfinite(g).all()) for g in grads)
+
+
+def test_projection_and_group_rank_kernels_match_the_tensor_implementation():
+    """ddf_project_assign / ddf_group_ranks (csrc/projection.cu) == project_to_cameras + stable sort of the host-tensor
+    implementation (which tests/test_wrapper_golden.py pins to the reference class), incl. flip / crop / scale."""
+    from ddf_b200.fusion.point_fusion import group_ranks, project_to_cameras, project_to_cameras_cuda
+    pts = torch.from_numpy(synth.lidar_points(20000, seed=3)[:, :3]).cuda()
+    for flip, crop in ((False, None), (True, None), (False, (3.0, 2.0))):
+        meta = synth.nusc_img_meta(6)
+        meta["flip"] = flip
+        if crop is not None:
+            meta["img_crop_offset"] = list(crop)
+        cam, grid, grid_o = project_to_cameras(pts, meta)
+        g2, grid2, grid_o2 = project_to_cameras_cuda(pts, meta, group_base=12)
+        same = (g2.long() - 12) == cam
+        assert float(same.float().mean()) > 0.9999          # a last-ulp difference can flip a border voxel
+        assert float((grid2 - grid)[same].abs().max()) < 1e-5 and float((grid_o2 - grid_o)[same].abs().max()) < 2e-3
+    group = torch.randint(0, 12, (50000,), device="cuda", dtype=torch.int32)
+    col, counts = group_ranks(group, 12)
+    assert torch.equal(counts.long(), torch.bincount(group.long(), minlength=12))
+    order = torch.sort(group.long(), stable=True)[1]
+    starts = torch.cumsum(counts.long(), 0) - counts.long()
+    expect = torch.empty_like(order)
+    expect[order] = torch.arange(50000, device="cuda") - starts[group.long()[order]]
+    assert torch.equal(col.long(), expect)
