@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="tf", choices=sorted(WORKLOADS),
-                    help="tf = BASELINE configs[2] (the headline: what N=1 and the scaling run measure); cp / cp_pfatv2 = "
+                    help="tf = BASELINE configs[2] (the headline: what N=1 and the scaling run measure); tf_cam = the same "
+                         "with the camera branch on the device; cp / cp_pfatv2 = "
                          "configs[1] (CenterPoint hybrid+IFAT / its ACTRv2 variant); kitti = configs[3]; dense200k = configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp32-gemm", action="store_true",
@@ -109,6 +110,48 @@ class TransFusionWorkload(Workload):
 
     def forward(self, model, t, metas):
         return model(t["pts"], [t["feats"].float()], metas)
+
+
+class TransFusionCameraWorkload(TransFusionWorkload):
+    """configs[2] including the camera branch: the step starts from uint8 camera images, a frozen
+    bf16 ResNet-50 + FPN level 0 under a CUDA graph produces the 256 x 112 x 200 maps on the device."""
+    name = "tf_cam"
+
+    def describe(self, n_gpus):
+        d = super().describe(n_gpus)
+        d["workload"] = "TransFusion-L+3D-DF: frozen bf16 ResNet50+FPN(level 0) camera branch (CUDA graph) + " + d["workload"]
+        d["cam_input"] = "uint8 images 6 x 3 x 448 x 800 per sample"
+        d.pop("cam_feat_transfer_dtype", None)
+        return d
+
+    def build(self, device):
+        from ddf_b200.fusion.camera import CameraBranch
+        m = torch.nn.ModuleDict(dict(pts=super().build(device)))
+        if str(device) != "cpu":
+            m["cam"] = CameraBranch().to(device)
+        else:    # the CPU reference arm: same network in fp32 through the library
+            from ddf_b200.fusion.camera import ResNet50FPN0
+            torch.manual_seed(0)
+            m["cam"] = ResNet50FPN0().eval()
+            for p in m["cam"].parameters():
+                p.requires_grad_(False)
+        return m
+
+    def host_batch(self, rank, batch=None):
+        t, metas = super().host_batch(rank, batch)
+        del t["feats"]
+        g = torch.Generator().manual_seed(rank)
+        t["images"] = torch.randint(0, 256, ((batch or self.batch) * N_CAM, 3, 448, 800), dtype=torch.uint8, generator=g)
+        return t, metas
+
+    def forward(self, model, t, metas):
+        if t["images"].is_cuda:
+            feats = model["cam"](t["images"]).float()
+        else:
+            with torch.no_grad():
+                mean = torch.tensor((103.530, 116.280, 123.675)).view(1, 3, 1, 1)
+                feats = model["cam"](t["images"].float() - mean)
+        return model["pts"](t["pts"], [feats], metas)
 
 
 class Dense200kWorkload(TransFusionWorkload):
@@ -256,7 +299,7 @@ class KittiWorkload(Workload):
         return m["backbone"](bd)["encoded_spconv_tensor"].features
 
 
-WORKLOADS = {w.name: w for w in (TransFusionWorkload, Dense200kWorkload, CenterPointWorkload, CenterPointV2Workload,
+WORKLOADS = {w.name: w for w in (TransFusionWorkload, TransFusionCameraWorkload, Dense200kWorkload, CenterPointWorkload, CenterPointV2Workload,
                                  KittiWorkload)}
 
 
