@@ -25,7 +25,7 @@ class Recorder(torch.nn.Module):
 
 def test_transfusion_split_matches_reference_loops():
     """split_param / agg_param (point_fusion.py:342-394) restated with the reference's own loops."""
-    from ddf_b200.fusion.point_fusion import ACTR, project_to_cameras
+    from ddf_b200.fusion.point_fusion import ACTR, project_to_cameras, project_to_cameras_cuda
     import sys, os
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import configs
@@ -41,7 +41,15 @@ def test_transfusion_split_matches_reference_loops():
     out = layer([img], pts, feats, metas)
     # ---- reference-style loops ----
     N = 6
-    cams, grids, grids_o = zip(*[project_to_cameras(p, m) for p, m in zip(pts, metas)])
+    # geometry from the projection kernel the wrapper runs (ddf_project_assign), checked against the eager tensor form
+    # (the reduction order of a 4-term torch sum is not specified: 1-ulp differences are allowed, flips at the
+    # visibility border are not expected on this cloud)
+    cams, grids, grids_o = zip(*[project_to_cameras_cuda(p, m) for p, m in zip(pts, metas)])
+    cams = [c.long() for c in cams]
+    for (c_k, g_k, go_k), p, m in zip(zip(cams, grids, grids_o), pts, metas):
+        c_e, g_e, go_e = project_to_cameras(p, m)
+        assert torch.equal(c_k, c_e)
+        assert torch.allclose(g_k, g_e, rtol=1e-5, atol=1e-6) and torch.allclose(go_k, go_e, rtol=1e-5, atol=1e-3)
     max_points = max(int((c == n).sum()) for c in cams for n in range(N))
     pts_feats_n = torch.zeros(B * N, max_points, 128, device="cuda")
     img_feats_n = torch.zeros(B * N, max_points, 256, device="cuda")

@@ -30,3 +30,10 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=45,
                                                           max_shapes_column_width=70))
+if os.environ.get("DDF_PROFILE_STACKS"):
+    # second pass: attribute the ATen kernels to source lines of this package
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof2:
+        step()
+        torch.cuda.synchronize()
+    print(prof2.key_averages(group_by_stack_n=6).table(sort_by="self_cuda_time_total", row_limit=70, max_name_column_width=40,
+                                                       max_src_column_width=110))
