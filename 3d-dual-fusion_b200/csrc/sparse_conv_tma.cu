@@ -36,8 +36,33 @@
 //                 build; four issuers run in parallel.  Warp 8 also owns the TMEM allocation.
 //   warp 12     : B producer (one tiled TMA per filter slice)
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+
+#ifdef DDF_PHASES
+// instrumented builds only (tools/build_trace.py -DDDF_PHASES): per-CTA phase clocks of the conv kernel
+__device__ unsigned long long g_ph[16384][10];
+__device__ unsigned int g_ph_n;
+extern "C" int ddf_phase_dump(const char* path) {
+  static unsigned long long h[16384][10];
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_ph_n, sizeof(n));
+  cudaMemcpyFromSymbol(h, g_ph, sizeof(h));
+  FILE* f = fopen(path, "w");
+  if (!f) return 1;
+  if (n > 16384) n = 16384;
+  for (unsigned i = 0; i < n; ++i) {
+    for (int j = 0; j < 10; ++j) fprintf(f, "%llu%c", h[i][j], j == 9 ? '\n' : ',');
+  }
+  fclose(f);
+  n = 0;
+  cudaMemcpyToSymbol(g_ph_n, &n, sizeof(n));
+  return 0;
+}
+#endif
 
 namespace {
 constexpr int TM = 128;            // rows per tile = UMMA M
@@ -50,6 +75,7 @@ constexpr int kThreads = (kProducerWarps + kMaxT + 1) * 32;   // + one MMA issue
 constexpr int kStagesA = 8;         // at most; split into per-tile rings of n_slots / T slots (see below)
 constexpr int kMaxStagesB = 4;
 constexpr int kABytes = TM * KCH * 4;  // 16 KB
+constexpr int kDefaultRowsTma = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -76,6 +102,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   } while (!done);
+}
+// Whole-warp wait.  Every lane polls: electing one lane to poll and parking the others at a warp barrier was
+// measured 1.5-2x SLOWER on every conv kernel (B200, tools/bench_ops.py spconv; DDF_POLL_ONE keeps that variant);
+// a suspend-time hint on try_wait and nanosleep back-off of the non-critical waiters changed nothing
+// (profiles/r2_conv_analysis.md).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#ifdef DDF_POLL_ONE
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -197,7 +235,7 @@ struct Cfg {
 // boxes and the stage bookkeeping are unchanged).  Per stage the issuer runs hi.hi + hi.lo + lo.hi as six
 // kind::f16 MMAs (K = 16): products carry a 16-bit significand (error about 2^-17 per product instead of 2^-11
 // for tf32) at 1.5x the tensor-pipe time of the tf32 stage, fp32 accumulation in TMEM either way.
-template <int CO, bool GATHER4, int PREC>
+template <int CO, bool GATHER4, int PREC, int RT>
 __global__ void __launch_bounds__(kThreads)
 spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_constant__ CUtensorMap map_w,
                   const float* __restrict__ feat, const int* __restrict__ table, const float* __restrict__ bias, float* __restrict__ out,
@@ -214,18 +252,30 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
   uint64_t* b_full = a_empty + kStagesA;
   uint64_t* b_empty = b_full + kMaxStagesB;
   uint64_t* accum_bar = b_empty + kMaxStagesB;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tbl_bar = accum_bar + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tbl_bar + 1);
   uint32_t* s_mask = s_tmem + 1;   // [kMaxT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef DDF_TRACE
-  __shared__ long long s_tr[6][64];
+  __shared__ long long s_tr[11][64];
+  int tr_b = 0;
 #define TR(ev, i) do { if (blockIdx.x == 3 && (i) < 64) s_tr[ev][i] = clock64(); } while (0)
 #else
 #define TR(ev, i) do {} while (0)
 #endif
+#ifdef DDF_PHASES
+  unsigned long long ph[8];
+#define PH(i) do { if (tid == 0) ph[i] = clock64(); } while (0)
+#else
+#define PH(i) do {} while (0)
+#endif
+  PH(0);
   const int tile0 = blockIdx.x * T;
   const int rows = T * TM;         // rows of this CTA (padded)
+  const int vrows = (int)min((long long)rows, (long long)n_out - (long long)tile0 * TM);   // rows that exist
+  const int* tbl_src = table + (long long)tile0 * TM * kvol;
+  const uint32_t tbl_bulk = ((uint32_t)vrows * (uint32_t)kvol * 4u) & ~15u;   // bytes the bulk copy brings
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(T * C::kCols)) tmem_cols <<= 1;
 
@@ -233,7 +283,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
     for (int s = 0; s < kStagesA; ++s) {
       // gather4: one arrive.expect_tx per warp of the owning group; cp.async: one arrival per thread
       // of the owning 2-warp group
-      mbar_init(a_full + s, GATHER4 ? kProducerWarps / kGroups : 64);
+      mbar_init(a_full + s, GATHER4 ? kProducerWarps / kGroups : 64 + (RT > 0 ? 1 : 0));
       mbar_init(a_empty + s, 1);
     }
     for (int s = 0; s < n_sb; ++s) {
@@ -241,8 +291,21 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
       mbar_init(b_empty + s, T);   // every issuer releases every filter slice
     }
     mbar_init(accum_bar, T);
+    mbar_init(tbl_bar, 1);
     for (int t = 0; t < kMaxT; ++t) s_mask[t] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // rulebook rows of the T tiles: the slice [vrows x kvol] of the table is contiguous in global memory -> ONE bulk
+    // copy (16-byte granules) into the still unused A-slot area; the producers transpose it into s_idx from there.
+    // The strided per-thread global table walk this replaces was a fifth of a CTA's life.
+    if (tbl_bulk) {
+      mbar_expect_tx(tbl_bar, tbl_bulk);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(a_base)),
+          "l"(tbl_src), "r"(tbl_bulk), "r"(smem_u32(tbl_bar))
+          : "memory");
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tbl_bar)) : "memory");
+    }
   }
   if (warp == kProducerWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
@@ -251,13 +314,18 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   __syncthreads();
+  PH(1);
   if (warp < kProducerWarps) {
-    // rulebook rows of the T tiles -> smem, transposed to [k][row]; per-tile mask of the offsets in use
+    // staged table slice [row][k] -> s_idx [k][row] (what the producers read with 16-byte loads); per-tile mask of
+    // the offsets in use.  Row stride kvol = 27 is odd: the staged reads are conflict-free.
+    mbar_wait(tbl_bar, 0);
+    const int* staged = reinterpret_cast<const int*>(a_base);
     for (int r = tid; r < rows; r += kProducerWarps * 32) {
-      const long long o = (long long)tile0 * TM + r;
       uint32_t m = 0;
       for (int k = 0; k < kvol; ++k) {
-        const int j = o < n_out ? __ldg(table + o * kvol + k) : -1;
+        const uint32_t e = (uint32_t)(r * kvol + k);
+        // the at most 3 trailing ints of a ragged last CTA come straight from global memory
+        const int j = r < vrows ? (e * 4u < tbl_bulk ? staged[e] : __ldg(tbl_src + e)) : -1;
         s_idx[k * rows + r] = j >= 0 ? j : n_in;   // n_in = out of bounds = zero row
         if (j >= 0) m |= 1u << k;
       }
@@ -269,6 +337,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  PH(2);
   const uint32_t tmem_base = *s_tmem;
   uint32_t tmask[kMaxT];
   uint32_t any = 0;
@@ -318,14 +387,21 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
       // being issued at any time (a thread spends about 500 cycles per stage between the barrier
       // poll and 16 dependent address computations; with every thread on every stage that latency
       // was the stage period).  Thread -> 16-byte chunk ch of 16 consecutive rows.
+      // Hybrid gather (RT > 0, DDF_CONV_ROWS_TMA=32|64; off by default): the last RT rows of every stage go through
+      // the TMA unit (RT / 4 gather4 instructions per stage) in parallel with the LDGSTS of the first TM - RT rows;
+      // both land on the same a_full barrier (64 cp.async arrivals + one expect_tx arrival).  Measured: no gain
+      // (32 rows: +-1%, 64 rows: 3-15% slower) - the kernels are bound by the gathered bytes themselves, not by the
+      // unit that moves them (profiles/r2_conv_analysis.md).
       constexpr int kCpGroups = kProducerWarps / 2;
+      constexpr int NR = (TM - RT) / 8;                // LDGSTS rows per thread: 16, 12 or 8
+      constexpr int LPW = RT / 8;                      // lanes per warp that issue one gather4 each
       const int grp = warp >> 1, gt = tid & 63;
-      const int rb = (gt >> 3) * 16, ch = gt & 7;      // first row, chunk
-      const uint32_t a0 = smem_u32(a_base) + (uint32_t)(rb * 128);
+      const int rb = (gt >> 3) * NR, ch = gt & 7;      // first row, chunk
+      const uint32_t a0 = smem_u32(a_base);
       const float* col0 = feat + ch * 4;
       for (int k = 0; k < kvol; ++k) {
         if (!((any >> k) & 1u)) continue;
-        const int* ik = s_idx + k * rows + rb;
+        const int* ik = s_idx + k * rows;
         for (int c = 0; c < n_chunks; ++c) {
           const float* col = col0 + c * KCH;
 #pragma unroll
@@ -337,19 +413,30 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
             // a slot always belongs to the same group: one producer and one consumer per slot, both
             // in order, so a parity wait can never be two phases off
             if ((slot & (kCpGroups - 1)) != grp) continue;
-            int4 j4[4];
+            int4 j4[NR / 4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) j4[i] = *reinterpret_cast<const int4*>(ik + t * TM + 4 * i);
+            for (int i = 0; i < NR / 4; ++i) j4[i] = *reinterpret_cast<const int4*>(ik + t * TM + rb + 4 * i);
             const int* j = reinterpret_cast<const int*>(j4);
+            int4 jt = make_int4(0, 0, 0, 0);
+            int rt0 = 0;
+            if constexpr (RT > 0) {
+              rt0 = TM - RT + ((warp & 1) * LPW + lane) * 4;
+              if (lane < LPW) jt = *reinterpret_cast<const int4*>(ik + t * TM + rt0);
+            }
             const uint32_t dst = a0 + (uint32_t)(slot * kABytes);
             if (t == 0 && tid == 0) TR(0, cnt[0] - 1);
-            mbar_wait(a_empty + slot, par ^ 1u);
+            mbar_wait_warp(a_empty + slot, par ^ 1u);
             if (t == 0 && tid == 0) TR(1, cnt[0] - 1);
+            if constexpr (RT > 0) {
+              if (gt == 0) mbar_expect_tx(a_full + slot, RT * 128);
+              if (lane < LPW)
+                tma_gather4(dst + (uint32_t)(rt0 * 128), &map_feat, a_full + slot, c * KCH, jt.x, jt.y, jt.z, jt.w);
+            }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < NR; ++i) {
               const bool v = (unsigned)j[i] < (unsigned)n_in;
-              // rows rb + i: rb is a multiple of 16, so (row & 7) == (i & 7)
-              cp_async16(dst + (uint32_t)(i * 128 + ((ch ^ (i & 7)) << 4)),
+              const int row = rb + i;
+              cp_async16(dst + (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4)),
                          col + (v ? (size_t)(unsigned)j[i] * (unsigned)cin : 0), v ? 16u : 0u);
             }
             cp_async_arrive_noinc(a_full + slot);
@@ -361,10 +448,12 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;     // TMEM lane quadrant this warp may read
     const int part = warp >> 2; // the quadrant's (tile, 16-column) items are split over its 2 warps
+    PH(3);
     if (any) {
-      mbar_wait(accum_bar, 0);
+      mbar_wait_warp(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    PH(4);
     constexpr int kBlocks = CO / 16;
     for (int item = part; item < T * kBlocks; item += kProducerWarps / 4) {
       const int t = item / kBlocks, cb = (item % kBlocks) * 16;
@@ -406,6 +495,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    PH(5);
   } else if (warp < kProducerWarps + kMaxT) {
     // ===================== MMA issuers: warp 8 + t drives tile t =====================
     const int t = warp - kProducerWarps;
@@ -423,15 +513,17 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
         if (!((any_u >> k) & 1u)) continue;
         const bool mine = (mt >> k) & 1u;
         for (int c = 0; c < n_chunks; ++c) {
-          mbar_wait(b_full + sb, pb);
+          if (t == 0 && lane == 0 && mine) TR(3, cnt);
+          mbar_wait_warp(b_full + sb, pb);
           if (mine) {
             const int slot = cnt & (ring - 1);
-            if (t == 0 && lane == 0) TR(3, cnt);
-            mbar_wait(a_full + t * ring + slot, (uint32_t)(cnt >> ring_shift) & 1u);
+            if (t == 0 && lane == 0) TR(6, cnt);
+            mbar_wait_warp(a_full + t * ring + slot, (uint32_t)(cnt >> ring_shift) & 1u);
             if (t == 0 && lane == 0) TR(4, cnt);
             ++cnt;
             if constexpr (!GATHER4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (t == 0 && lane == 0) TR(7, cnt - 1);
             const uint64_t a_desc = make_desc_sw128(a_ring + (uint32_t)(slot * kABytes));
             const uint64_t b_desc = make_desc_sw128(smem_u32(b_base) + (uint32_t)(sb * C::kBBytes));
             if constexpr (PREC == 0) {
@@ -454,6 +546,7 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
                 }
               }
             }
+            if (t == 0 && lane == 0) TR(8, cnt - 1);
             umma_commit_elect(a_empty + t * ring + slot);
             umma_commit_elect(b_empty + sb);
             if (t == 0 && lane == 0) TR(5, cnt - 1);
@@ -476,7 +569,12 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
       for (int k = 0; k < kvol; ++k) {
         if (!((any >> k) & 1u)) continue;
         for (int c = 0; c < n_chunks; ++c) {
+          TR(9, tr_b);
           mbar_wait(b_empty + sb, pb ^ 1u);
+          TR(10, tr_b);
+#ifdef DDF_TRACE
+          ++tr_b;
+#endif
           mbar_expect_tx(b_full + sb, (uint32_t)(cout * KCH * 4));
           tma_tile_2d(smem_u32(b_base + sb * C::kBBytes), &map_w, b_full + sb, c * KCH, k * cout);
           if (++sb == n_sb) { sb = 0; pb ^= 1u; }
@@ -486,12 +584,27 @@ spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_con
     __syncwarp();
   }
   __syncthreads();
+#ifdef DDF_PHASES
+  if (tid == 0) {
+    ph[6] = clock64();
+    const unsigned slot = atomicAdd(&g_ph_n, 1u);
+    if (slot < 16384) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_ph[slot][0] = smid;
+      g_ph[slot][1] = blockIdx.x;
+      for (int i = 0; i < 7; ++i) g_ph[slot][2 + i] = ph[i];
+      g_ph[slot][9] = (unsigned long long)T;
+    }
+  }
+#endif
 #ifdef DDF_TRACE
   if (blockIdx.x == 3 && tid == 0) {
     const long long t0 = s_tr[0][0];
-    for (int i = 0; i < 40; ++i)
-      printf("stage %2d: prod wait_start %6lld got_slot %6lld issued %6lld | issuer wait_start %6lld full %6lld committed %6lld\n", i,
-             s_tr[0][i] - t0, s_tr[1][i] - t0, s_tr[2][i] - t0, s_tr[3][i] - t0, s_tr[4][i] - t0, s_tr[5][i] - t0);
+    for (int i = 0; i < 30; ++i)
+      printf("stage %2d: prod wait %6lld slot %6lld issued %6lld | issuer start %6lld b_full %6lld a_full %6lld fenced %6lld mma %6lld committed %6lld | B wait %6lld empty %6lld\n", i,
+             s_tr[0][i] - t0, s_tr[1][i] - t0, s_tr[2][i] - t0, s_tr[3][i] - t0, s_tr[6][i] - t0, s_tr[4][i] - t0,
+             s_tr[7][i] - t0, s_tr[8][i] - t0, s_tr[5][i] - t0, s_tr[9][i] - t0, s_tr[10][i] - t0);
   }
 #endif
   if (warp == kProducerWarps) {
@@ -623,7 +736,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
           const int sl = j * 2 + (c & 1);
           if ((sl & 3) != grp) continue;
           if (!have_tbl) {
-            mbar_wait(b_full + sb, pb);     // table slice (and gout rows) of this sub-tile landed
+            mbar_wait_warp(b_full + sb, pb);     // table slice (and gout rows) of this sub-tile landed
             have_tbl = true;
           }
           const int k = k0 + kk;
@@ -633,7 +746,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 #ifdef DDF_TRACE
           if (tid == 0) WTR(0, tr_p);
 #endif
-          mbar_wait(a_empty + sl, (uint32_t)((c >> 1) & 1) ^ 1u);
+          mbar_wait_warp(a_empty + sl, (uint32_t)((c >> 1) & 1) ^ 1u);
 #ifdef DDF_TRACE
           if (tid == 0) WTR(1, tr_p);
 #endif
@@ -656,7 +769,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
     }
     // ===================== epilogue: accumulators -> gW (red.global.add) =====================
     if (work) {
-      mbar_wait(accum_bar, 0);
+      mbar_wait_warp(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3, half = warp >> 2;
       const int ci = q * 32 + lane;
@@ -693,7 +806,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
       int cnt = 0, sb = 0;
       uint32_t pb = 0;
       for (int st = st_begin; st < st_end; ++st) {
-        mbar_wait(b_full + sb, pb);
+        mbar_wait_warp(b_full + sb, pb);
         const uint32_t b_smem = smem_u32(b_base) + (uint32_t)(sb * b_bytes);
         bool issued = false;
         for (int kk = j; kk < nk; kk += kMaxT) {
@@ -701,7 +814,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 #ifdef DDF_TRACE
           if (j == 0 && lane == 0) WTR(3, tr_i);
 #endif
-          mbar_wait(a_full + j * 2 + sl, (uint32_t)(cnt >> 1) & 1u);
+          mbar_wait_warp(a_full + j * 2 + sl, (uint32_t)(cnt >> 1) & 1u);
 #ifdef DDF_TRACE
           if (j == 0 && lane == 0) WTR(4, tr_i);
 #endif
@@ -741,7 +854,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 #ifdef DDF_TRACE
         if (bt == 0) WTR(6, tr_b);
 #endif
-        mbar_wait(b_empty + sb, pb ^ 1u);
+        mbar_wait_warp(b_empty + sb, pb ^ 1u);
         const uint32_t tdst = smem_u32(t_base + sb * kTblBytes);
         const long long tsrc = (long long)st * SR * kvol * 4;
 #pragma unroll 4
@@ -837,11 +950,11 @@ bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CO, bool GATHER4, int PREC>
+template <int CO, bool GATHER4, int PREC, int RT>
 int launch_tma(const float* feat, const float* wt, const int* table, const float* bias, float* out,
                int64_t n_out, int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
   using C = Cfg<CO>;
-  DDF_SET_SMEM_ONCE((spconv_tma_kernel<CO, GATHER4, PREC>), C::kSmemBytes);
+  DDF_SET_SMEM_ONCE((spconv_tma_kernel<CO, GATHER4, PREC, RT>), C::kSmemBytes);
   CUtensorMap map_feat, map_w;
   if (!make_map(&map_feat, feat, n_in, cin, 1) || !make_map(&map_w, wt, (int64_t)kvol * cout, cin, cout)) {
     ddf::set_error("sparse conv: cuTensorMapEncodeTiled failed (n_in=%lld cin=%d cout=%d)", (long long)n_in, cin, cout);
@@ -861,9 +974,15 @@ int launch_tma(const float* feat, const float* wt, const int* table, const float
     n_slots = 4;
     n_sb = 2;
   }
+#if defined(DDF_TRACE) || defined(DDF_TUNE)
+  // instrumented builds only: schedule overrides for A/B timing
+  if (const char* e = getenv("DDF_TMA_T")) { T = atoi(e); if (T > tmax) T = tmax; }
+  if (const char* e = getenv("DDF_TMA_SLOTS")) n_slots = atoi(e);
+  if (const char* e = getenv("DDF_TMA_SB")) n_sb = atoi(e);
+#endif
   const int smem = n_slots * kABytes + n_sb * C::kBBytes + T * TM * kMaxKvol * 4 + 512 + 1024;
   const unsigned grid = (unsigned)ddf::cdiv(ntiles, T);
-  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4, PREC>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
+  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4, PREC, RT>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
              bias, out, (int)n_out, (int)n_in, kvol, cin, cout, T, n_slots, n_sb);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -884,15 +1003,29 @@ bool spconv_tma_supported(int kvol, int cin, int cout) {
 int spconv_tma_launch(const float* feat, const float* wt, const int* table, const float* bias, float* out,
                       int64_t n_out, int64_t n_in, int kvol, int cin, int cout, bool gather4, bool split,
                       cudaStream_t stream) {
-#define DDF_TMA_CASE(CO)                                                                                         \
-  if (split) return launch_tma<CO, false, 1>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream); \
-  return gather4 ? launch_tma<CO, true, 0>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream)    \
-                 : launch_tma<CO, false, 0>(feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream)
+  // rows of every A stage that go through TMA gather4 instead of LDGSTS (hybrid gather; 0 = LDGSTS only)
+  static const int rows_tma = [] {
+    const char* e = getenv("DDF_CONV_ROWS_TMA");
+    const int v = e ? atoi(e) : kDefaultRowsTma;
+    return v >= 64 ? 64 : v >= 32 ? 32 : 0;
+  }();
+#define DDF_TMA_ARGS feat, wt, table, bias, out, n_out, n_in, kvol, cin, cout, stream
+#define DDF_TMA_CASE(CO)                                                                   \
+  if (gather4 && !split) return launch_tma<CO, true, 0, 0>(DDF_TMA_ARGS);                  \
+  if (split) {                                                                             \
+    if (rows_tma == 64) return launch_tma<CO, false, 1, 64>(DDF_TMA_ARGS);                 \
+    if (rows_tma == 32) return launch_tma<CO, false, 1, 32>(DDF_TMA_ARGS);                 \
+    return launch_tma<CO, false, 1, 0>(DDF_TMA_ARGS);                                      \
+  }                                                                                        \
+  if (rows_tma == 64) return launch_tma<CO, false, 0, 64>(DDF_TMA_ARGS);                   \
+  if (rows_tma == 32) return launch_tma<CO, false, 0, 32>(DDF_TMA_ARGS);                   \
+  return launch_tma<CO, false, 0, 0>(DDF_TMA_ARGS)
   if (cout <= 16) { DDF_TMA_CASE(16); }
   if (cout <= 32) { DDF_TMA_CASE(32); }
   if (cout <= 64) { DDF_TMA_CASE(64); }
   DDF_TMA_CASE(128);
 #undef DDF_TMA_CASE
+#undef DDF_TMA_ARGS
 }
 
 // table-driven wgrad: SubM layers with Cin == Cout in {32, 64, 128} (the sub-tile of the gather table

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libddf_b200.so")
+# DDF_LIB_PATH: an instrumented build of the same library (tools/build_trace.py), for kernel timeline traces only
+LIB_PATH = os.environ.get("DDF_LIB_PATH") or os.path.join(_PKG_DIR, "libddf_b200.so")
 
 _lib = None
 
