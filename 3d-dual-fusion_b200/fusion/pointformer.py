@@ -167,12 +167,12 @@ class LocalTransformer(nn.Module):
         consecutive rows are the sequences."""
         mha = layer.self_attn
         s = layer.norm1(x)
-        qkv = F.linear(s, mha.in_proj_weight, mha.in_proj_bias)
+        qkv = _fused.linear_wb(s, mha.in_proj_weight, mha.in_proj_bias)
         o = _pointops.local_attention(qkv, mha.num_heads, self.nsample)
-        s = s + layer.dropout1(F.linear(o, mha.out_proj.weight, mha.out_proj.bias))
+        s = s + layer.dropout1(_fused.linear_wb(o, mha.out_proj.weight, mha.out_proj.bias))
         s = layer.norm2(s)
         hidden = _fused.ffn_hidden(layer.linear1, layer.dropout, s)
-        return s + layer.dropout2(layer.linear2(hidden))
+        return s + layer.dropout2(_fused.linear(layer.linear2, hidden))
 
     def forward_tokens(self, xyz, feats_nc, geom=None):
         """feats_nc (B, N, C) row-major voxel features -> (B, N, C). No (B, C, np, ns) tensor, no permutes: the grouped
@@ -187,7 +187,7 @@ class LocalTransformer(nn.Module):
         conv1, bn, conv2 = self.pe[0].conv, self.pe[0].bn, self.pe[1].conv
         pe = F.linear(geom["gxyz"], conv1.weight.view(conv1.out_channels, 3))
         pe = _sparse_norm.batch_norm_act(bn, pe, relu=True)        # BatchNorm2d over (B, H, W) == over the T rows
-        x = x + F.linear(pe, conv2.weight.view(conv2.out_channels, conv2.in_channels), conv2.bias)
+        x = x + _fused.linear_wb(pe, conv2.weight.view(conv2.out_channels, conv2.in_channels), conv2.bias)
         for layer in self.chunk.layers:
             x = self._layer_tokens(layer, x)
         out = torch.where(geom["hit"], x.index_select(0, geom["src"]), rows)

@@ -70,10 +70,28 @@ def _col_sum_ok(C):
     return C % 4 == 0 and C // 4 <= 256 and 256 % (C // 4) == 0
 
 
+def xty(a2d, b2d):
+    """a2d (K, M)^T @ b2d (K, N) -> (M, N): the weight gradient of a Linear over K tokens.  tf32 arithmetic allowed
+    (``torch.backends.cuda.matmul.allow_tf32``) and widths that are multiples of 32: one split-K tcgen05 pass that
+    streams both operands once (ddf_xty_tf32); otherwise the library product."""
+    K, M = a2d.shape
+    N = b2d.shape[1]
+    if (torch.backends.cuda.matmul.allow_tf32 and K >= 4096 and a2d.is_cuda and a2d.dtype == torch.float32
+            and b2d.dtype == torch.float32 and a2d.is_contiguous() and b2d.is_contiguous()
+            and a2d.data_ptr() % 16 == 0 and b2d.data_ptr() % 16 == 0
+            and _lib.get_lib().ddf_xty_supported(K, M, N)):
+        out = torch.empty((M, N), dtype=torch.float32, device=a2d.device)
+        with torch.cuda.device(a2d.device):
+            rc = _lib.get_lib().ddf_xty_tf32(_lib.ptr(a2d), _lib.ptr(b2d), _lib.ptr(out), K, M, N, _lib.current_stream())
+        _lib.check(rc, "xty_tf32")
+        return out
+    return a2d.t() @ b2d
+
+
 class _Linear(Function):
     """F.linear over (..., Cin) tokens whose bias gradient is one pass at the HBM rate (ddf_col_sum) instead of
-    ATen's grad.sum(0) (168 us for a [146 k, 128] gradient on B200 = 14x below the copy rate); the GEMMs stay in the
-    library."""
+    ATen's grad.sum(0) (168 us for a [146 k, 128] gradient on B200 = 14x below the copy rate) and whose weight
+    gradient is the split-K tcgen05 pass ``xty``; the forward and input-gradient GEMMs stay in the library."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -91,27 +109,47 @@ class _Linear(Function):
         if ctx.needs_input_grad[0]:
             gx = (g2 @ weight).view(x.shape)
         if ctx.needs_input_grad[1]:
-            gw = g2.t() @ x.reshape(-1, x.shape[-1])
+            gw = xty(g2, x.reshape(-1, x.shape[-1]))
         if ctx.needs_input_grad[2]:
-            gb = col_sum(g2)
+            gb = col_sum(g2) if _col_sum_ok(g2.shape[1]) else g2.sum(0)
         return gx, gw, gb
+
+
+class _LinearNoBias(Function):
+    """x @ weight.T over (..., Cin) tokens; the weight gradient through ``xty``."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        gx = (g2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        gw = xty(g2, x.reshape(-1, x.shape[-1]).contiguous()) if ctx.needs_input_grad[1] else None
+        return gx, gw
 
 
 def linear(module, x):
     """``module(x)`` for an ``nn.Linear`` applied to many tokens (same parameters, same forward GEMM)."""
     if (module.bias is None or not x.is_cuda or x.dtype != torch.float32 or module.weight.dtype != torch.float32
-            or not _col_sum_ok(module.out_features) or not torch.is_grad_enabled()
-            or x.numel() // max(x.shape[-1], 1) < 4096):
+            or not torch.is_grad_enabled() or x.numel() // max(x.shape[-1], 1) < 4096):
         return module(x)
     return _Linear.apply(x, module.weight, module.bias)
 
 
 def linear_wb(x, weight, bias):
     """``F.linear(x, weight, bias)`` with the fast bias gradient (weight / bias given directly)."""
-    if (bias is None or not x.is_cuda or x.dtype != torch.float32 or weight.dtype != torch.float32
-            or not _col_sum_ok(weight.shape[0]) or not torch.is_grad_enabled()
-            or x.numel() // max(x.shape[-1], 1) < 4096):
+    if (not x.is_cuda or x.dtype != torch.float32 or weight.dtype != torch.float32
+            or not torch.is_grad_enabled() or x.numel() // max(x.shape[-1], 1) < 4096):
         return F.linear(x, weight, bias)
+    if bias is None:
+        return _LinearNoBias.apply(x, weight)
     return _Linear.apply(x, weight, bias)
 
 
@@ -121,7 +159,8 @@ def ffn_hidden(linear, dropout, x):
     if x.dtype != torch.float32 or C % 4:
         _lib.require_cuda(x)
         return dropout(F.relu(linear(x)))
-    h = F.linear(x, linear.weight)           # fresh tensor: safe to overwrite in place
+    big = x.is_cuda and torch.is_grad_enabled() and x.numel() // max(x.shape[-1], 1) >= 4096
+    h = _LinearNoBias.apply(x, linear.weight) if big else F.linear(x, linear.weight)   # fresh tensor: overwritten in place
     if h.dtype != torch.float32 or (linear.bias is not None and linear.bias.dtype != torch.float32):
         # e.g. under torch.autocast the GEMM returns half precision: the fp32 kernels must not see it
         h = h if linear.bias is None else h + linear.bias.to(h.dtype)

@@ -378,6 +378,13 @@ int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, con
  * C % 4 == 0 and C / 4 must divide 256. */
 int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream);
 
+/* c [M, N] = a [K, M]^T . b [K, N]: the weight gradient of an nn.Linear over K tokens, W.grad [out, in] =
+ * grad_out [K, out]^T . x [K, in] (autograd of F.linear in <proj>/models/model_utils/actr_transformer.py:383-397,
+ * ops/modules/ms_deform_attn.py:124-147).  fp32 row-major operands read as tf32 (top 19 bits) by tcgen05, fp32
+ * accumulation, split-K partial sums reduced in c (overwritten).  M, N multiples of 32 (ddf_xty_supported). */
+int ddf_xty_supported(int64_t K, int64_t M, int64_t N);
+int ddf_xty_tf32(const float* a, const float* b, float* c, int64_t K, int64_t M, int64_t N, void* stream);
+
 /* ---- fusion wrapper geometry (TransFusion/mmdet3d/models/fusion_layers/point_fusion.py:342-382, 509-643) ----------
  * ddf_project_assign: voxel centres -> camera assignment ("last camera that sees the voxel", unseen -> camera 0 at
  *   (0, 0)) + reference points; visibility in ORIGINAL image pixels (depth > 1, 1 < u < ori_w - 1, 1 < v < ori_h - 1),

@@ -131,3 +131,55 @@ def test_linear_with_fast_bias_gradient_equals_nn_linear():
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
     big = torch.randn(146016, 128, device="cuda")
     assert float((fused.col_sum(big) - big.double().sum(0).float()).abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("K,M,N", [(146016, 128, 1024), (146016, 1024, 128), (20000, 128, 128), (5000, 32, 64),
+                                   (4097, 96, 288), (30011, 256, 128), (12345, 64, 32)])
+def test_xty_matches_matmul(K, M, N):
+    """ddf_xty_tf32 (weight gradient of a Linear over K tokens, split-K tcgen05) against the fp64 product: exact on
+    integer-valued operands (every tf32 product and fp32 partial sum is exact, so any layout / swizzle / split-K
+    mistake shows), tf32-class on normal data (operands are truncated to tf32 by the hardware)."""
+    from ddf_b200.ops import fused
+    from ddf_b200 import lib as _lib
+    assert _lib.get_lib().ddf_xty_supported(K, M, N)
+    g = torch.Generator(device="cuda").manual_seed(K + M + N)
+    a = torch.randint(-3, 4, (K, M), device="cuda", generator=g).float()
+    b = torch.randint(-3, 4, (K, N), device="cuda", generator=g).float()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = fused.xty(a, b)
+        ref = (a.double().t() @ b.double())
+        assert torch.equal(out.double(), ref)
+        a = torch.randn(K, M, device="cuda", generator=g)
+        b = torch.randn(K, N, device="cuda", generator=g)
+        out = fused.xty(a, b)
+        ref = a.double().t() @ b.double()
+        err = float((out.double() - ref).abs().max() / ref.abs().max())
+        assert err < 4e-3, err
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_linear_weight_grad_through_xty():
+    """fused.linear / ffn_hidden route W.grad through ddf_xty_tf32 when tf32 is allowed: gradients against the stock
+    modules in fp64."""
+    from ddf_b200.ops import fused
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(128, 256).cuda()
+    x = torch.randn(3, 5000, 128, device="cuda", requires_grad=True)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        y = fused.linear(lin, x)
+        go = torch.randn_like(y)
+        y.backward(go)
+        gw, gb, gx = lin.weight.grad.clone(), lin.bias.grad.clone(), x.grad.clone()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    lin64 = torch.nn.Linear(128, 256).cuda().double()
+    lin64.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
+    x64 = x.detach().double().requires_grad_()
+    lin64(x64).backward(go.double())
+    for got, ref in ((gw, lin64.weight.grad), (gb, lin64.bias.grad), (gx, x64.grad)):
+        assert float((got.double() - ref).abs().max() / ref.abs().max()) < 4e-3
