@@ -651,7 +651,11 @@ __device__ __forceinline__ uint32_t mn_chunk_offset(int p, int mb, int ch, int n
 
 constexpr int kWgThreads = kThreads + 32;   // two staging warps instead of one
 
-template <int CO, int SR>
+// PK = kernel offsets packed into the M dimension of one MMA (PK * Cin = 128 TMEM lanes): with 32 or 64 channels an
+// unpacked accumulator uses a quarter / half of the lanes and the issuers spend their time issuing 4x / 2x the MMAs
+// (about 100 cycles each: in-kernel trace, profiles/r2_conv_analysis.md).  A packed A stage is laid out like the A
+// stage of a 128-channel layer whose 32-channel blocks come from PK different gathered rows.
+template <int CO, int SR, int PK>
 __global__ void __launch_bounds__(kWgThreads)
 spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
                           const int* __restrict__ table, float* __restrict__ gw, int n_out, int n_in,
@@ -659,8 +663,8 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
-  const int a_nb = cin >> 5, b_nb = CO >> 5;           // 32-channel blocks per row
-  const int a_bytes = SR * cin * 4, b_bytes = SR * CO * 4;
+  const int a_nb = (PK * cin) >> 5, b_nb = CO >> 5;    // 32-channel blocks per row (cin == CO when PK > 1)
+  const int a_bytes = SR * PK * cin * 4, b_bytes = SR * CO * 4;
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + kWgSlotsA * a_bytes;
   uint8_t* t_base = b_base + kWgSlotsB * b_bytes;
@@ -682,7 +686,8 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 #endif
   const int g = blockIdx.x % G, split = blockIdx.x / G, S = gridDim.x / G;
   const int k0 = g * KG;
-  const int nk = min(KG, kvol - k0);
+  const int nko = min(KG, kvol - k0);          // kernel offsets of this CTA
+  const int nk = (nko + PK - 1) / PK;          // packed units (accumulators) of this CTA
   const int NS = (n_out + SR - 1) / SR;
   const int st_begin = (int)((long long)NS * split / S), st_end = (int)((long long)NS * (split + 1) / S);
   constexpr uint32_t kCols = CO;     // CO >= 32 here
@@ -717,10 +722,12 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
     // ===================== A producers =====================
     if (work) {
       const int grp = warp >> 1, gt = tid & 63;
-      constexpr int kChunks = CO / 4;                    // 16-byte chunks per row (Cin == Cout == CO)
+      constexpr int kChunksO = CO / 4;                   // 16-byte chunks per gathered row (Cin == Cout == CO)
+      constexpr int kChunks = PK * kChunksO;             // ... per row of the packed stage
       constexpr int kRowsPerPass = 64 / kChunks;         // rows covered by the 64 threads of a group
       constexpr int kIters = SR / kRowsPerPass;          // chunks per thread and stage
-      const int cc = gt % kChunks, pr = gt / kChunks;    // this thread's chunk and first row
+      const int c32 = gt % kChunks, pr = gt / kChunks;   // this thread's chunk of the packed row and first row
+      const int jo = c32 / kChunksO, cc = c32 % kChunksO;   // offset inside the unit, chunk of the gathered row
       int cnt[kMaxT] = {0, 0, 0, 0};
       int sb = 0;
       uint32_t pb = 0;
@@ -739,10 +746,11 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
             mbar_wait_warp(b_full + sb, pb);     // table slice (and gout rows) of this sub-tile landed
             have_tbl = true;
           }
-          const int k = k0 + kk;
+          const int k = k0 + kk * PK + jo;
+          const bool kv = kk * PK + jo < nko;            // the last unit of a CTA may be partly empty: zero rows
           int rowidx[kIters];
 #pragma unroll
-          for (int i = 0; i < kIters; ++i) rowidx[i] = tbl[(pr + i * kRowsPerPass) * kvol + k];
+          for (int i = 0; i < kIters; ++i) rowidx[i] = kv ? tbl[(pr + i * kRowsPerPass) * kvol + k] : -1;
 #ifdef DDF_TRACE
           if (tid == 0) WTR(0, tr_p);
 #endif
@@ -756,7 +764,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
           for (int i = 0; i < kIters; ++i) {
             const int p = pr + i * kRowsPerPass;
             const bool v = rowidx[i] >= 0 && p < rows_left;
-            cp_async16(dst + mn_chunk_offset(p, cc >> 3, cc & 7, a_nb),
+            cp_async16(dst + mn_chunk_offset(p, c32 >> 3, c32 & 7, a_nb),
                        src0 + (v ? (size_t)(unsigned)rowidx[i] * (unsigned)CO : 0), v ? 16u : 0u);
           }
           cp_async_arrive_noinc(a_full + sl);
@@ -772,8 +780,10 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
       mbar_wait_warp(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3, half = warp >> 2;
-      const int ci = q * 32 + lane;
+      const int lrow = q * 32 + lane;                    // TMEM lane = (offset inside the unit, input channel)
+      const int jl = PK > 1 ? lrow / CO : 0, ci = PK > 1 ? lrow % CO : lrow;
       for (int kk = half; kk < nk; kk += kProducerWarps / 4) {
+        const bool lane_live = ci < cin && kk * PK + jl < nko;
         for (int cb = 0; cb < cout; cb += 16) {
           uint32_t v[16];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kk * kCols + cb);
@@ -785,8 +795,8 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
                 "=r"(v[14]), "=r"(v[15])
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ci < cin) {
-            float* dst = gw + ((long long)(k0 + kk) * cin + ci) * cout + cb;
+          if (lane_live) {
+            float* dst = gw + ((long long)(k0 + kk * PK + jl) * cin + ci) * cout + cb;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               red_add_v4(dst + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
@@ -900,22 +910,23 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
 template <int CO>
 int launch_wgrad_table(const float* feat, const float* gout, const int* table, float* gw, int64_t n_out,
                        int64_t n_in, int kvol, int cin, int cout, cudaStream_t stream) {
-  // rows per stage: 32 (64 and 128 channels; measured better than 64-row stages), 128 at 32 channels so
-  // that a stage is 16 KB and the per-stage fixed costs are amortised
-  constexpr int SR = CO == 32 ? 128 : 32;
+  // 32 output rows per stage; 128 / CO kernel offsets share one MMA (M = 128 lanes), so an A stage is always
+  // 32 rows x 512 bytes = 16 KB
+  constexpr int SR = 32;
+  constexpr int PK = 128 / CO;
   constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
-  const int smem = kWgSlotsA * SR * cin * 4 + kWgSlotsB * SR * CO * 4 + kWgSlotsB * kTblBytes + 2048 + 512 + 1024;
-  DDF_SET_SMEM_ONCE((spconv_wgrad_table_kernel<CO, SR>), smem);
+  const int smem = kWgSlotsA * SR * PK * cin * 4 + kWgSlotsB * SR * CO * 4 + kWgSlotsB * kTblBytes + 2048 + 512 + 1024;
+  DDF_SET_SMEM_ONCE((spconv_wgrad_table_kernel<CO, SR, PK>), smem);
   // two CTAs per SM when the rings are small; they then share the 512 TMEM columns
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-  int KG = (512 / per_sm) / CO;
+  int KG = (512 / per_sm) / CO * PK;    // kernel offsets per CTA = accumulators x offsets per accumulator
   if (KG > kvol) KG = kvol;
   const int G = (kvol + KG - 1) / KG;
   const long long NS = ddf::cdiv(n_out, SR);
   long long S = (ddf::kNumSM * per_sm) / G;
   if (S > NS) S = NS;
   if (S < 1) S = 1;
-  DDF_LAUNCH((spconv_wgrad_table_kernel<CO, SR>), (unsigned)(G * S), kWgThreads, smem, stream, feat, gout, table, gw,
+  DDF_LAUNCH((spconv_wgrad_table_kernel<CO, SR, PK>), (unsigned)(G * S), kWgThreads, smem, stream, feat, gout, table, gw,
              (int)n_out, (int)n_in, kvol, cin, cout, KG, G);
   DDF_LAUNCH_CHECK();
   return DDF_OK;

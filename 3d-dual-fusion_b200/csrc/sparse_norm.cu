@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxGrid = 2 * ddf::kNumSM;
+constexpr int kMaxGrid = 4 * ddf::kNumSM;
 
 struct Acc8 {
   double v[8];
@@ -61,22 +61,37 @@ __device__ __forceinline__ bool fold_and_publish(Acc8& a, int tpr, int cg, int r
   return s_last;
 }
 
-// Last CTA: totals of the 2*C columns over all CTAs' partials, in a fixed order -> tot[2*C] (shared).
+// Last CTA: totals of the 2*C columns over all CTAs' partials, in a fixed order -> tot[2*C] (shared).  The partials
+// of a column are read with 16 independent loads in flight per thread: a serial chain of up to 296 dependent L2 reads
+// (about 50 us) WAS the tail of every statistics launch.
+__device__ __forceinline__ double fold_column(const double* __restrict__ p, int first, int stride, int G, int cols) {
+  constexpr int U = 16;
+  double s[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) s[u] = 0.0;
+  int g = first;
+  for (; g + (U - 1) * stride < G; g += U * stride) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] += __ldcg(p + (long long)(g + u * stride) * cols);
+  }
+  for (; g < G; g += stride) s[0] += __ldcg(p + (long long)g * cols);   // fewer than U left
+#pragma unroll
+  for (int w = U / 2; w > 0; w >>= 1) {
+#pragma unroll
+    for (int u = 0; u < w; ++u) s[u] += s[u + w];
+  }
+  return s[0];
+}
 __device__ __forceinline__ void fold_partials(const double* __restrict__ part, int C, double* tot) {
   __shared__ double sm[kThreads];
   const int cols = 2 * C;
   const int G = gridDim.x;
   if (cols >= kThreads) {
-    for (int col = threadIdx.x; col < cols; col += kThreads) {
-      double s = 0.0;
-      for (int g = 0; g < G; ++g) s += __ldcg(part + (long long)g * cols + col);
-      tot[col] = s;
-    }
+    for (int col = threadIdx.x; col < cols; col += kThreads) tot[col] = fold_column(part + col, 0, 1, G, cols);
   } else {
     const int nsl = kThreads / cols;  // cols is a power of two >= 8
     const int col = threadIdx.x % cols, sl = threadIdx.x / cols;
-    double s = 0.0;
-    for (int g = sl; g < G; g += nsl) s += __ldcg(part + (long long)g * cols + col);
+    double s = fold_column(part + col, sl, nsl, G, cols);
     sm[threadIdx.x] = s;
     __syncthreads();
     if (sl == 0) {
@@ -105,10 +120,21 @@ bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ 
   const long long step = (long long)gridDim.x * rpb;
   long long r = (long long)blockIdx.x * rpb + rl;
   const float* px = x + cg * 4;
-  for (; r + 3 * step < n; r += 4 * step) {   // four independent 16-byte loads in flight per thread
-    const float4 v0 = ldg4(px + r * C), v1 = ldg4(px + (r + step) * C), v2 = ldg4(px + (r + 2 * step) * C),
-                 v3 = ldg4(px + (r + 3 * step) * C);
-    add(v0); add(v1); add(v2); add(v3);
+  for (; r + 7 * step < n; r += 8 * step) {   // eight independent 16-byte loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = ldg4(px + (r + u * step) * C);
+    // the eight rows are folded in fp32 first (relative error 1e-7 per group), one fp64 update per group: the
+    // fp32 -> fp64 conversions, not the loads, were the inner-loop cost
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s1.x += v[u].x; s1.y += v[u].y; s1.z += v[u].z; s1.w += v[u].w;
+      s2.x = fmaf(v[u].x, v[u].x, s2.x); s2.y = fmaf(v[u].y, v[u].y, s2.y);
+      s2.z = fmaf(v[u].z, v[u].z, s2.z); s2.w = fmaf(v[u].w, v[u].w, s2.w);
+    }
+    a.v[0] += s1.x; a.v[1] += s1.y; a.v[2] += s1.z; a.v[3] += s1.w;
+    a.v[4] += s2.x; a.v[5] += s2.y; a.v[6] += s2.z; a.v[7] += s2.w;
   }
   for (; r < n; r += step) add(ldg4(px + r * C));
   if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
@@ -186,13 +212,17 @@ bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
   const long long step = (long long)gridDim.x * rpb;
   long long r = (long long)blockIdx.x * rpb + rl;
   const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
-  for (; r + step < n; r += 2 * step) {       // two rows (six 16-byte loads) in flight per thread
-    const long long o0 = r * C + cg * 4, o1 = (r + step) * C + cg * 4;
-    const float4 g0 = ldg4(gy + o0), g1 = ldg4(gy + o1);
-    const float4 y0 = relu ? ldg4(y + o0) : one, y1 = relu ? ldg4(y + o1) : one;
-    const float4 v0 = ldg4(x + o0), v1 = ldg4(x + o1);
-    add(g0, y0, v0);
-    add(g1, y1, v1);
+  for (; r + 3 * step < n; r += 4 * step) {   // four rows (twelve 16-byte loads) in flight per thread
+    float4 g[4], yy[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long o = (r + u * step) * C + cg * 4;
+      g[u] = ldg4(gy + o);
+      yy[u] = relu ? ldg4(y + o) : one;
+      v[u] = ldg4(x + o);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(g[u], yy[u], v[u]);
   }
   for (; r < n; r += step) {
     const long long o = r * C + cg * 4;
