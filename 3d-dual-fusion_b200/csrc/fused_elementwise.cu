@@ -368,3 +368,218 @@ extern "C" int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, 
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
+
+// ---- bi-directional gated fusion of the two query streams (<proj>/models/model_utils/attentions.py:89-117) -------
+//   u = fuse_in ? f1 + f2 : (f1 for s1, f2 for s2);  s1 = sigmoid(wb . u + bb), s2 = sigmoid(wa . u + ba)
+//   o1 = f1 + f2 * s1,  o2 = f2 + f1 * s2                      (BiGateSum1D / BiGateSum1D_2)
+// The module chain is nine elementwise / reduction launches over [tokens, C] forward and about twice that backward;
+// here one pass each way: a warp owns a row (C = 128 * VPL), the two dot products are shuffle reductions, the
+// gates [rows, 2] are kept for backward.
+namespace {
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(kThreads)
+bigate_sum_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ wb,
+                      const float* __restrict__ bb, const float* __restrict__ wa, const float* __restrict__ ba,
+                      float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ gates, long long rows,
+                      int fuse_in) {
+  constexpr int C = 128 * VPL;
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  float4 a[VPL], b[VPL];
+  float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int c = (v * 32 + lane) * 4;
+    a[v] = ldg4(f1 + row * C + c);
+    b[v] = ldg4(f2 + row * C + c);
+    const float4 w1 = ldg4(wb + c), w2 = ldg4(wa + c);
+    if (fuse_in) {
+      const float4 u = make_float4(a[v].x + b[v].x, a[v].y + b[v].y, a[v].z + b[v].z, a[v].w + b[v].w);
+      d1 += dot4(w1, u);
+      d2 += dot4(w2, u);
+    } else {
+      d1 += dot4(w1, a[v]);
+      d2 += dot4(w2, b[v]);
+    }
+  }
+  const float s1 = 1.f / (1.f + expf(-(warp_sum(d1) + (bb ? __ldg(bb) : 0.f))));
+  const float s2 = 1.f / (1.f + expf(-(warp_sum(d2) + (ba ? __ldg(ba) : 0.f))));
+  if (lane == 0) *reinterpret_cast<float2*>(gates + row * 2) = make_float2(s1, s2);
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int c = (v * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(o1 + row * C + c) =
+        make_float4(fmaf(b[v].x, s1, a[v].x), fmaf(b[v].y, s1, a[v].y), fmaf(b[v].z, s1, a[v].z), fmaf(b[v].w, s1, a[v].w));
+    *reinterpret_cast<float4*>(o2 + row * C + c) =
+        make_float4(fmaf(a[v].x, s2, b[v].x), fmaf(a[v].y, s2, b[v].y), fmaf(a[v].z, s2, b[v].z), fmaf(a[v].w, s2, b[v].w));
+  }
+}
+
+// go1 / go2 may be NULL (an output that never reaches the loss).  gwb / gwa [C], gbb / gba [1] are accumulated
+// (zeroed by the caller): per-lane partial sums over the warp's rows, one shared-memory fold per CTA, atomics.
+template <int VPL>
+__global__ void __launch_bounds__(kThreads)
+bigate_sum_bwd_kernel(const float* __restrict__ go1, const float* __restrict__ go2, const float* __restrict__ f1,
+                      const float* __restrict__ f2, const float* __restrict__ gates, const float* __restrict__ wb,
+                      const float* __restrict__ wa, float* __restrict__ gf1, float* __restrict__ gf2,
+                      float* __restrict__ gwb, float* __restrict__ gbb, float* __restrict__ gwa,
+                      float* __restrict__ gba, long long rows, int fuse_in) {
+  constexpr int C = 128 * VPL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 w1[VPL], w2[VPL], aw1[VPL], aw2[VPL];
+  float ab1 = 0.f, ab2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int c = (v * 32 + lane) * 4;
+    w1[v] = ldg4(wb + c);
+    w2[v] = ldg4(wa + c);
+    aw1[v] = aw2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long wstride = (long long)gridDim.x * (kThreads / 32);
+  for (long long row = (long long)blockIdx.x * (kThreads / 32) + warp; row < rows; row += wstride) {
+    float4 a[VPL], b[VPL], g1[VPL], g2[VPL];
+    float e1 = 0.f, e2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const long long o = row * C + (v * 32 + lane) * 4;
+      a[v] = ldg4(f1 + o);
+      b[v] = ldg4(f2 + o);
+      g1[v] = go1 ? ldg4(go1 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g2[v] = go2 ? ldg4(go2 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      e1 += dot4(g1[v], b[v]);     // d o1 / d s1 = f2
+      e2 += dot4(g2[v], a[v]);     // d o2 / d s2 = f1
+    }
+    const float2 s = __ldg(reinterpret_cast<const float2*>(gates) + row);
+    const float z1 = warp_sum(e1) * s.x * (1.f - s.x), z2 = warp_sum(e2) * s.y * (1.f - s.y);
+    ab1 += z1;
+    ab2 += z2;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const long long o = row * C + (v * 32 + lane) * 4;
+      // gradient through the gate inputs
+      const float4 u1 = make_float4(z1 * w1[v].x, z1 * w1[v].y, z1 * w1[v].z, z1 * w1[v].w);
+      const float4 u2 = make_float4(z2 * w2[v].x, z2 * w2[v].y, z2 * w2[v].z, z2 * w2[v].w);
+      float4 r1, r2;
+      r1.x = fmaf(g2[v].x, s.y, g1[v].x); r1.y = fmaf(g2[v].y, s.y, g1[v].y);
+      r1.z = fmaf(g2[v].z, s.y, g1[v].z); r1.w = fmaf(g2[v].w, s.y, g1[v].w);
+      r2.x = fmaf(g1[v].x, s.x, g2[v].x); r2.y = fmaf(g1[v].y, s.x, g2[v].y);
+      r2.z = fmaf(g1[v].z, s.x, g2[v].z); r2.w = fmaf(g1[v].w, s.x, g2[v].w);
+      float4 in1, in2;           // the vectors the two gates were computed from
+      if (fuse_in) {
+        const float4 t = make_float4(u1.x + u2.x, u1.y + u2.y, u1.z + u2.z, u1.w + u2.w);
+        r1.x += t.x; r1.y += t.y; r1.z += t.z; r1.w += t.w;
+        r2.x += t.x; r2.y += t.y; r2.z += t.z; r2.w += t.w;
+        in1 = in2 = make_float4(a[v].x + b[v].x, a[v].y + b[v].y, a[v].z + b[v].z, a[v].w + b[v].w);
+      } else {
+        r1.x += u1.x; r1.y += u1.y; r1.z += u1.z; r1.w += u1.w;
+        r2.x += u2.x; r2.y += u2.y; r2.z += u2.z; r2.w += u2.w;
+        in1 = a[v];
+        in2 = b[v];
+      }
+      if (gf1) *reinterpret_cast<float4*>(gf1 + o) = r1;
+      if (gf2) *reinterpret_cast<float4*>(gf2 + o) = r2;
+      aw1[v].x = fmaf(z1, in1.x, aw1[v].x); aw1[v].y = fmaf(z1, in1.y, aw1[v].y);
+      aw1[v].z = fmaf(z1, in1.z, aw1[v].z); aw1[v].w = fmaf(z1, in1.w, aw1[v].w);
+      aw2[v].x = fmaf(z2, in2.x, aw2[v].x); aw2[v].y = fmaf(z2, in2.y, aw2[v].y);
+      aw2[v].z = fmaf(z2, in2.z, aw2[v].z); aw2[v].w = fmaf(z2, in2.w, aw2[v].w);
+    }
+  }
+  // fold the 8 warps of the CTA, then one atomic per column and CTA
+  __shared__ float4 sh[2][kThreads / 32][32 * VPL];
+  __shared__ float shb[2][kThreads / 32];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    sh[0][warp][v * 32 + lane] = aw1[v];
+    sh[1][warp][v * 32 + lane] = aw2[v];
+  }
+  if (lane == 0) {
+    shb[0][warp] = ab1;
+    shb[1][warp] = ab2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 32 * VPL; i += kThreads) {
+    const int which = i / (32 * VPL), col = i % (32 * VPL);
+    float4 t = sh[which][0][col];
+    for (int w = 1; w < kThreads / 32; ++w) {
+      const float4 x = sh[which][w][col];
+      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+    }
+    float* dst = (which ? gwa : gwb);
+    if (dst) {
+      atomicAdd(dst + col * 4, t.x);
+      atomicAdd(dst + col * 4 + 1, t.y);
+      atomicAdd(dst + col * 4 + 2, t.z);
+      atomicAdd(dst + col * 4 + 3, t.w);
+    }
+  }
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += shb[threadIdx.x][w];
+    float* dst = threadIdx.x ? gba : gbb;
+    if (dst) atomicAdd(dst, t);
+  }
+}
+}  // namespace
+
+#define DDF_GATE_DISPATCH(C, CALL)                    \
+  switch (C) {                                        \
+    case 128: { constexpr int VPL = 1; CALL; } break; \
+    case 256: { constexpr int VPL = 2; CALL; } break; \
+    default:                                          \
+      ddf::set_error("bigate_sum: C must be 128 or 256, got %lld", (long long)(C)); \
+      return DDF_ERR_ARG;                             \
+  }
+
+// o1 = f1 + f2 * s1, o2 = f2 + f1 * s2 with s1 = sigmoid(wb . u1 + bb), s2 = sigmoid(wa . u2 + ba); u1 = u2 = f1 + f2
+// when fuse_in (BiGateSum1D_2) else u1 = f1, u2 = f2 (BiGateSum1D).  gates [rows, 2] = (s1, s2) for backward.
+extern "C" int ddf_bigate_sum_forward(const float* f1, const float* f2, const float* wb, const float* bb,
+                                      const float* wa, const float* ba, float* o1, float* o2, float* gates,
+                                      int64_t rows, int64_t C, int fuse_in, void* stream_) {
+  DDF_CHECK_ARG(rows >= 0, "bigate_sum_forward: bad rows");
+  if (rows == 0) return DDF_OK;
+  DDF_CHECK_ARG(f1 && f2 && wb && wa && o1 && o2 && gates, "bigate_sum_forward: null pointer");
+  DDF_CHECK_ARG(aligned16(f1) && aligned16(f2) && aligned16(wb) && aligned16(wa) && aligned16(o1) && aligned16(o2) &&
+                    (reinterpret_cast<uintptr_t>(gates) & 7u) == 0,
+                "bigate_sum_forward: misaligned pointer");
+  const unsigned grid = (unsigned)ddf::cdiv(rows * 32, kThreads);
+  DDF_GATE_DISPATCH(C, DDF_LAUNCH(bigate_sum_fwd_kernel<VPL>, grid, kThreads, 0, (cudaStream_t)stream_, f1, f2, wb, bb,
+                                  wa, ba, o1, o2, gates, (long long)rows, fuse_in));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
+// grad_o1 / grad_o2 may be NULL (treated as zero); grad_f1 / grad_f2 may be NULL; grad_wb / grad_wa [C] and
+// grad_bb / grad_ba [1] are overwritten (NULL = not wanted).
+extern "C" int ddf_bigate_sum_backward(const float* grad_o1, const float* grad_o2, const float* f1, const float* f2,
+                                       const float* gates, const float* wb, const float* wa, float* grad_f1,
+                                       float* grad_f2, float* grad_wb, float* grad_bb, float* grad_wa,
+                                       float* grad_ba, int64_t rows, int64_t C, int fuse_in, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DDF_CHECK_ARG(rows >= 0 && (C == 128 || C == 256), "bigate_sum_backward: C must be 128 or 256");
+  if (grad_wb) DDF_CUDA(cudaMemsetAsync(grad_wb, 0, sizeof(float) * (size_t)C, stream));
+  if (grad_wa) DDF_CUDA(cudaMemsetAsync(grad_wa, 0, sizeof(float) * (size_t)C, stream));
+  if (grad_bb) DDF_CUDA(cudaMemsetAsync(grad_bb, 0, sizeof(float), stream));
+  if (grad_ba) DDF_CUDA(cudaMemsetAsync(grad_ba, 0, sizeof(float), stream));
+  if (rows == 0) return DDF_OK;
+  DDF_CHECK_ARG(f1 && f2 && gates && wb && wa, "bigate_sum_backward: null pointer");
+  DDF_CHECK_ARG(aligned16(grad_o1) && aligned16(grad_o2) && aligned16(f1) && aligned16(f2) && aligned16(grad_f1) &&
+                    aligned16(grad_f2) && aligned16(wb) && aligned16(wa),
+                "bigate_sum_backward: misaligned pointer");
+  long long grid = ddf::cdiv(rows * 32, kThreads);
+  if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;
+  DDF_GATE_DISPATCH(C, DDF_LAUNCH(bigate_sum_bwd_kernel<VPL>, (unsigned)grid, kThreads, 0, stream, grad_o1, grad_o2, f1,
+                                  f2, gates, wb, wa, grad_f1, grad_f2, grad_wb, grad_bb, grad_wa, grad_ba,
+                                  (long long)rows, fuse_in));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}

@@ -649,7 +649,11 @@ __device__ __forceinline__ uint32_t mn_chunk_offset(int p, int mb, int ch, int n
   return (uint32_t)((((p >> 2) * nblk + mb) << 9) + (r << 7) + ((((ch >> 1) ^ r)) << 5) + ((ch & 1) << 4));
 }
 
-constexpr int kWgThreads = kThreads + 32;   // two staging warps instead of one
+// 16 producer warps = 8 groups, one per A slot: what bounds the kernel is how many producer groups issue gathers
+// concurrently on an SM (in-kernel trace: a group needs about 2000 cycles per 16 KB stage, the MMA issuers wait for
+// data), and the rings of this kernel only leave room for one CTA per SM.
+constexpr int kWgProducerWarps = 16;
+constexpr int kWgThreads = (kWgProducerWarps + kMaxT + 2) * 32;   // + 4 MMA issuer warps + 2 staging warps
 
 // PK = kernel offsets packed into the M dimension of one MMA (PK * Cin = 128 TMEM lanes): with 32 or 64 channels an
 // unpacked accumulator uses a quarter / half of the lanes and the issuers spend their time issuing 4x / 2x the MMAs
@@ -706,7 +710,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
     mbar_init(accum_bar, kMaxT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kProducerWarps) {
+  if (warp == kWgProducerWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                  "r"(tmem_cols)
                  : "memory");
@@ -718,7 +722,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
   const uint32_t tmem_base = *s_tmem;
   const bool work = st_begin < st_end;
 
-  if (warp < kProducerWarps) {
+  if (warp < kWgProducerWarps) {
     // ===================== A producers =====================
     if (work) {
       const int grp = warp >> 1, gt = tid & 63;
@@ -741,7 +745,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
           int c;
           if (j == 0) c = cnt[0]++; else if (j == 1) c = cnt[1]++; else if (j == 2) c = cnt[2]++; else c = cnt[3]++;
           const int sl = j * 2 + (c & 1);
-          if ((sl & 3) != grp) continue;
+          if (sl != grp) continue;
           if (!have_tbl) {
             mbar_wait_warp(b_full + sb, pb);     // table slice (and gout rows) of this sub-tile landed
             have_tbl = true;
@@ -782,7 +786,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
       const int q = warp & 3, half = warp >> 2;
       const int lrow = q * 32 + lane;                    // TMEM lane = (offset inside the unit, input channel)
       const int jl = PK > 1 ? lrow / CO : 0, ci = PK > 1 ? lrow % CO : lrow;
-      for (int kk = half; kk < nk; kk += kProducerWarps / 4) {
+      for (int kk = half; kk < nk; kk += kWgProducerWarps / 4) {
         const bool lane_live = ci < cin && kk * PK + jl < nko;
         for (int cb = 0; cb < cout; cb += 16) {
           uint32_t v[16];
@@ -806,9 +810,9 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-  } else if (warp < kProducerWarps + kMaxT) {
+  } else if (warp < kWgProducerWarps + kMaxT) {
     // ===================== MMA issuers: offsets kk = j (mod 4) =====================
-    const int j = warp - kProducerWarps;
+    const int j = warp - kWgProducerWarps;
     if (work) {
       constexpr uint32_t idesc = make_idesc_tf32(CO) | (1u << 15) | (1u << 16);   // A, B MN-major
       const uint32_t tm = __reduce_or_sync(0xffffffffu, tmem_base);
@@ -855,7 +859,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
     // ===================== gout rows + table slice of each sub-tile (cp.async, 2 warps) =====================
     if (work) {
       constexpr int kChunks = CO / 4;
-      const int bt = tid - (kProducerWarps + kMaxT) * 32;     // 0..63
+      const int bt = tid - (kWgProducerWarps + kMaxT) * 32;     // 0..63
       int sb = 0;
       uint32_t pb = 0;
       const long long tbl_bytes_total = (long long)n_out * kvol * 4;
@@ -900,7 +904,7 @@ spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restric
              w_tr[0][i] - t0, w_tr[1][i] - t0, w_tr[2][i] - t0, w_tr[3][i] - t0, w_tr[4][i] - t0, w_tr[5][i] - t0, w_tr[6][i] - t0, w_tr[7][i] - t0);
   }
 #endif
-  if (warp == kProducerWarps) {
+  if (warp == kWgProducerWarps) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
                  : "memory");

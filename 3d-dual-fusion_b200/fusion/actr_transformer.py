@@ -254,7 +254,9 @@ class DeformableTransformerACTR(nn.Module):
             src_flatten.append(src.flatten(2).transpose(1, 2))
             if masks is not None:
                 mask_flatten.append(masks[lvl].flatten(1))
-        src_flatten = torch.cat(src_flatten, 1) if len(src_flatten) > 1 else src_flatten[0]
+        # ONE token-major copy of the projected camera maps for all encoder layers (value_proj of every layer reads
+        # it; each layer used to make its own copy of the transposed view, forward and backward)
+        src_flatten = torch.cat(src_flatten, 1) if len(src_flatten) > 1 else src_flatten[0].contiguous()
         self.encoder.spatial_hw = spatial_shapes[0] if len(spatial_shapes) == 1 else None   # python ints: no sync
         device = src_flatten.device
         spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=device)

@@ -4,6 +4,8 @@
 import torch
 from torch import nn
 
+from ..ops import fused as _fused
+
 
 class _BiGateBase(nn.Module):
     def __init__(self, g_channel, g_channel_):
@@ -45,6 +47,9 @@ class BiGateSum1D(_BiGateBase):
     (attentions.py:89-94)."""
 
     def forward(self, feat1, feat2):
+        out = _fused.bigate_sum(self.b_conv1d, self.a_conv1d, feat1, feat2, False)   # one kernel each way on CUDA
+        if out is not None:
+            return out
         s1 = self._gate(self.b_conv1d, feat1)
         s2 = self._gate(self.a_conv1d, feat2)
         return feat1 + feat2 * s1, feat2 + feat1 * s2
@@ -54,6 +59,9 @@ class BiGateSum1D_2(_BiGateBase):
     """out1 = f1 + f2 * sigmoid(b(f1+f2)); out2 = f2 + f1 * sigmoid(a(f1+f2)) (attentions.py:111-117)."""
 
     def forward(self, feat1, feat2):
+        out = _fused.bigate_sum(self.b_conv1d, self.a_conv1d, feat1, feat2, True)    # one kernel each way on CUDA
+        if out is not None:
+            return out
         fuse = feat1 + feat2
         s1 = self._gate(self.b_conv1d, fuse)
         s2 = self._gate(self.a_conv1d, fuse)

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "ddf_project_assign": [c_ptr, c_i64, c_i64, c_ptr, c_i64] + [c_f32] * 9 + [c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "ddf_group_ranks": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "ddf_col_sum": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
+    "ddf_bigate_sum_forward": [c_ptr] * 9 + [c_i64, c_i64, c_int, c_ptr],
+    "ddf_bigate_sum_backward": [c_ptr] * 13 + [c_i64, c_i64, c_int, c_ptr],
     "ddf_xty_supported": [c_i64] * 3,
     "ddf_xty_tf32": [c_ptr] * 3 + [c_i64] * 3 + [c_ptr],
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],

@@ -223,3 +223,68 @@ def add_dropout_layer_norm(norm, dropout, a, b):
         return norm(a + dropout(b))
     p = dropout.p if (dropout is not None and dropout.training) else 0.0
     return _AddDropoutLayerNorm.apply(a, b, norm.weight, norm.bias, p, norm.eps)
+
+
+class _BiGateSum(Function):
+    """o1 = f1 + f2 * sigmoid(wb . u1 + bb), o2 = f2 + f1 * sigmoid(wa . u2 + ba) in one pass each way
+    (ddf_bigate_sum_forward / _backward); u1 = u2 = f1 + f2 when ``fuse_in`` else u1 = f1, u2 = f2."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, wb, bb, wa, ba, fuse_in):
+        _lib.require_cuda(f1, f2, wb, wa)
+        f1, f2 = f1.contiguous(), f2.contiguous()
+        C = f1.shape[-1]
+        rows = f1.numel() // C
+        wbv, wav = wb.reshape(-1).contiguous(), wa.reshape(-1).contiguous()
+        o1, o2 = torch.empty_like(f1), torch.empty_like(f2)
+        gates = torch.empty((rows, 2), dtype=torch.float32, device=f1.device)
+        with torch.cuda.device(f1.device):
+            rc = _lib.get_lib().ddf_bigate_sum_forward(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(wbv), _lib.ptr(bb),
+                                                       _lib.ptr(wav), _lib.ptr(ba), _lib.ptr(o1), _lib.ptr(o2),
+                                                       _lib.ptr(gates), rows, C, int(fuse_in), _lib.current_stream())
+        _lib.check(rc, "bigate_sum_forward")
+        ctx.fuse_in = bool(fuse_in)
+        ctx.wshape = (wb.shape, wa.shape)
+        ctx.has_bias = (bb is not None, ba is not None)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(f1, f2, gates, wbv, wav)
+        return o1, o2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go1, go2):
+        f1, f2, gates, wbv, wav = ctx.saved_tensors
+        C = f1.shape[-1]
+        rows = f1.numel() // C
+        go1 = go1.contiguous() if go1 is not None else None
+        go2 = go2.contiguous() if go2 is not None else None
+        need = ctx.needs_input_grad
+        new = lambda n: torch.empty(n, dtype=torch.float32, device=f1.device)
+        gf1 = torch.empty_like(f1) if need[0] else None
+        gf2 = torch.empty_like(f2) if need[1] else None
+        # a gate only feeds its own output: with that output unused its parameters get no gradient at all (None, as
+        # autograd leaves them in the module chain - the last layer's a_conv1d is structurally unused)
+        gwb = new(C) if (need[2] and go1 is not None) else None
+        gbb = new(1) if (need[3] and ctx.has_bias[0] and go1 is not None) else None
+        gwa = new(C) if (need[4] and go2 is not None) else None
+        gba = new(1) if (need[5] and ctx.has_bias[1] and go2 is not None) else None
+        with torch.cuda.device(f1.device):
+            rc = _lib.get_lib().ddf_bigate_sum_backward(
+                _lib.ptr(go1), _lib.ptr(go2), _lib.ptr(f1), _lib.ptr(f2), _lib.ptr(gates), _lib.ptr(wbv), _lib.ptr(wav),
+                _lib.ptr(gf1), _lib.ptr(gf2), _lib.ptr(gwb), _lib.ptr(gbb), _lib.ptr(gwa), _lib.ptr(gba), rows, C,
+                int(ctx.fuse_in), _lib.current_stream())
+        _lib.check(rc, "bigate_sum_backward")
+        return (gf1, gf2, gwb.view(ctx.wshape[0]) if gwb is not None else None, gbb,
+                gwa.view(ctx.wshape[1]) if gwa is not None else None, gba, None)
+
+
+def bigate_sum(b_conv, a_conv, feat1, feat2, fuse_in):
+    """BiGateSum1D (``fuse_in=False``) / BiGateSum1D_2 (``True``) on (..., C) token rows with the module's own
+    ``Conv1d(C, 1, 1)`` gates; ``None`` when the shape / dtype is not the fused kernel's (the caller then runs the
+    module chain)."""
+    C = feat1.shape[-1]
+    if (not feat1.is_cuda or feat1.dtype != torch.float32 or feat2.dtype != torch.float32 or feat1.shape != feat2.shape
+            or C not in (128, 256) or b_conv.weight.dtype != torch.float32 or a_conv.weight.dtype != torch.float32
+            or b_conv.weight.numel() != C or a_conv.weight.numel() != C):
+        return None
+    return _BiGateSum.apply(feat1, feat2, b_conv.weight, b_conv.bias, a_conv.weight, a_conv.bias, fuse_in)

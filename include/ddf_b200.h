@@ -378,6 +378,19 @@ int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, con
  * C % 4 == 0 and C / 4 must divide 256. */
 int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream);
 
+/* Bi-directional gated fusion of the LiDAR / image query streams (<proj>/models/model_utils/attentions.py:89-117,
+ * BiGateSum1D and BiGateSum1D_2): o1 = f1 + f2 * s1, o2 = f2 + f1 * s2 with s1 = sigmoid(wb . u1 + bb),
+ * s2 = sigmoid(wa . u2 + ba); fuse_in: u1 = u2 = f1 + f2 (BiGateSum1D_2), else u1 = f1, u2 = f2.  f*, o* [rows, C]
+ * fp32 (C = 128 or 256), wb / wa [C] = the Conv1d(C, 1, 1) weights, bb / ba [1] (may be NULL), gates [rows, 2] is
+ * kept for backward.  Backward: grad_o1 / grad_o2 / grad_f1 / grad_f2 / the parameter gradients may be NULL. */
+int ddf_bigate_sum_forward(const float* f1, const float* f2, const float* wb, const float* bb, const float* wa,
+                           const float* ba, float* o1, float* o2, float* gates, int64_t rows, int64_t C,
+                           int fuse_in, void* stream);
+int ddf_bigate_sum_backward(const float* grad_o1, const float* grad_o2, const float* f1, const float* f2,
+                            const float* gates, const float* wb, const float* wa, float* grad_f1, float* grad_f2,
+                            float* grad_wb, float* grad_bb, float* grad_wa, float* grad_ba, int64_t rows, int64_t C,
+                            int fuse_in, void* stream);
+
 /* c [M, N] = a [K, M]^T . b [K, N]: the weight gradient of an nn.Linear over K tokens, W.grad [out, in] =
  * grad_out [K, out]^T . x [K, in] (autograd of F.linear in <proj>/models/model_utils/actr_transformer.py:383-397,
  * ops/modules/ms_deform_attn.py:124-147).  fp32 row-major operands read as tf32 (top 19 bits) by tcgen05, fp32

@@ -183,3 +183,39 @@ def test_linear_weight_grad_through_xty():
     lin64(x64).backward(go.double())
     for got, ref in ((gw, lin64.weight.grad), (gb, lin64.bias.grad), (gx, x64.grad)):
         assert float((got.double() - ref).abs().max() / ref.abs().max()) < 4e-3
+
+
+@pytest.mark.parametrize("cls_name", ["BiGateSum1D", "BiGateSum1D_2"])
+@pytest.mark.parametrize("C,drop_second", [(128, False), (256, False), (128, True)])
+def test_bigate_sum_kernel_matches_module_chain(cls_name, C, drop_second):
+    """The fused gate (ddf_bigate_sum_*) against the module chain of attentions.py:89-117 in fp64: outputs and every
+    gradient; ``drop_second``: the second output never reaches the loss (the last encoder layer)."""
+    from ddf_b200.fusion import attentions
+    torch.manual_seed(5)
+    gate = getattr(attentions, cls_name)(C, C).cuda()
+    f1 = torch.randn(3, 2500, C, device="cuda", requires_grad=True)
+    f2 = torch.randn(3, 2500, C, device="cuda", requires_grad=True)
+    o1, o2 = gate(f1, f2)
+    g1, g2 = torch.randn_like(o1), torch.randn_like(o2)
+    loss = (o1 * g1).sum() if drop_second else (o1 * g1).sum() + (o2 * g2).sum()
+    loss.backward()
+    ref = getattr(attentions, cls_name)(C, C).cuda().double()
+    ref.load_state_dict({k: v.double() for k, v in gate.state_dict().items()})
+    r1, r2 = f1.detach().double().requires_grad_(), f2.detach().double().requires_grad_()
+    s1 = torch.sigmoid(torch.nn.functional.linear(r1 + r2 if cls_name.endswith("_2") else r1,
+                                                  ref.b_conv1d.weight.squeeze(-1), ref.b_conv1d.bias))
+    s2 = torch.sigmoid(torch.nn.functional.linear(r1 + r2 if cls_name.endswith("_2") else r2,
+                                                  ref.a_conv1d.weight.squeeze(-1), ref.a_conv1d.bias))
+    q1, q2 = r1 + r2 * s1, r2 + r1 * s2
+    rl = (q1 * g1.double()).sum() if drop_second else (q1 * g1.double()).sum() + (q2 * g2.double()).sum()
+    rl.backward()
+    rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert rel(o1, q1) < 1e-5 and rel(o2, q2) < 1e-5
+    assert rel(f1.grad, r1.grad) < 1e-4 and rel(f2.grad, r2.grad) < 1e-4
+    assert rel(gate.b_conv1d.weight.grad, ref.b_conv1d.weight.grad) < 1e-3
+    assert rel(gate.b_conv1d.bias.grad, ref.b_conv1d.bias.grad) < 1e-3
+    if drop_second:
+        assert gate.a_conv1d.weight.grad is None and gate.a_conv1d.bias.grad is None
+    else:
+        assert rel(gate.a_conv1d.weight.grad, ref.a_conv1d.weight.grad) < 1e-3
+        assert rel(gate.a_conv1d.bias.grad, ref.a_conv1d.bias.grad) < 1e-3
