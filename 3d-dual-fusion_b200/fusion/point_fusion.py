@@ -203,10 +203,12 @@ class ACTR(nn.Module):
         return self._pad_all(pts_feats, grid, grid_o, img_feats, pts_xyz, row, col, n_groups, max_points)
 
     def _pad_all(self, pts_feats, grid, grid_o, img_feats, pts_xyz, row, col, n_groups, max_points):
+        flat = row * max_points + col         # every query has its own slot: a row copy, not an index_put
+
         def pad(x):
-            out = x.new_zeros((n_groups, max_points) + tuple(x.shape[1:]))
-            out[row, col] = x
-            return out
+            out = x.new_zeros((n_groups * max_points,) + tuple(x.shape[1:]))
+            out.index_copy_(0, flat, x)
+            return out.view((n_groups, max_points) + tuple(x.shape[1:]))
 
         stride = self.img_stride
         ix = grid_o[:, 0].to(torch.long) // stride
@@ -242,7 +244,7 @@ class ACTR(nn.Module):
         ragged = pts_feats.shape[0] < 0.75 * feats_n.shape[0] * max_points
         enh_n = self.actr(v_feat=feats_n, grid=grid_n, i_feats=img_feats, lidar_grid=xyz_n, v_i_feat=img_n,
                           valid_index=(row * max_points + col) if ragged else None)
-        enh = enh_n[row, col]                                                  # agg_param + concat
+        enh = enh_n.reshape(-1, enh_n.shape[-1]).index_select(0, row * max_points + col)   # agg_param + concat
         if self.fusion_method == "replace":
             fuse_out = enh
         elif self.fusion_method == "concat":

@@ -10,7 +10,9 @@ import re
 import sys
 
 OURS = ("spconv", "msda", "subm_", "conv_", "pairs_", "ddf::", "vox", "round_tf32", "dense_", "transpose_filters",
-        "fill_i32", "fps", "ball", "group", "gather", "bn_", "hash_", "popc", "scan")
+        "fill_i32", "fps", "ball", "group", "gather", "bn_", "hash_", "popc", "scan", "xty_", "bigate_", "bias_relu_",
+        "relu_dropout_", "add_dropout_", "col_sum", "split_", "local_attn", "project_assign", "first_occ", "index_rows",
+        "scatter_first", "bev_", "sparse_to", "mark_", "compact_")
 
 KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
@@ -36,7 +38,13 @@ def launches(path, bench_path=None):
     hdr = rows[hi]
     kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     tot, cnt = {}, collections.Counter()
-    for r in rows[hi + 1:]:
+    body = rows[hi + 1:]
+    if len(sys.argv) > 4:      # "laststep": the launches between the last two optimizer launches = one warm step
+        marks = [i for i, r in enumerate(body) if len(r) > kn and "adam" in r[kn].lower()]
+        ends = [m for i, m in enumerate(marks) if i + 1 == len(marks) or marks[i + 1] - m > 50]   # last launch of each step
+        if len(ends) >= 2:
+            body = body[ends[-2] + 1:ends[-1] + 1]
+    for r in body:
         if len(r) <= mv:
             continue
         n = short(r[kn])
