@@ -82,6 +82,77 @@ group_rank_kernel(const int* __restrict__ group, int n, int* __restrict__ col, i
 }
 }  // namespace
 
+// ---- CenterPoint / Det3D flavour: every camera that sees a voxel makes a query ---------------------------------
+// Replaces Point2ImageProjection.transform_grid / forward of
+//   CenterPoint/det3d/models/fusion/point_to_image_projection.py (+ voxel_with_point_projection.py:160-260): per
+// camera, per-voxel GATHERED copies of the sample's 4x4 / 3x3 matrices, a chain of elementwise / reduction
+// launches over (N, 4, 4) tensors and a rescale to feature-map pixels - 30 ms of a 105 ms CenterPoint step (torch
+// profiler: 18 ms vectorized_gather + 11 ms index).  One thread per voxel walks the cameras; the arithmetic is the
+// module's fp32 sequence (products rounded one by one, sums left to right, IEEE divisions, float -> int64 truncation).
+namespace {
+__global__ void __launch_bounds__(kThreads)
+project_cameras_kernel(const int* __restrict__ indices, const float* __restrict__ pts, const float* __restrict__ l2c,
+                       const float* __restrict__ intr, const float* __restrict__ shape,
+                       const float* __restrict__ thres, int n_cam, int B, float image_scale, float Hf, float Wf, int n,
+                       long long* __restrict__ grid, float* __restrict__ depth, bool* __restrict__ mask,
+                       long long* __restrict__ fx, long long* __restrict__ fy) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int b = indices[4 * (long long)i];
+  const float x = pts[3 * (long long)i], y = pts[3 * (long long)i + 1], z = pts[3 * (long long)i + 2];
+  for (int c = 0; c < n_cam; ++c) {
+    const float* m = l2c + ((long long)c * B + b) * 16;
+    float cam[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      cam[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + 4 * j), x), __fmul_rn(__ldg(m + 4 * j + 1), y)),
+                                   __fmul_rn(__ldg(m + 4 * j + 2), z)),
+                         __ldg(m + 4 * j + 3));
+    const float cx = __fdiv_rn(cam[0], cam[3]), cy = __fdiv_rn(cam[1], cam[3]), cz = __fdiv_rn(cam[2], cam[3]);
+    const float* k = intr + ((long long)c * B + b) * 9;
+    float im[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      im[j] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(k + 3 * j), cx), __fmul_rn(__ldg(k + 3 * j + 1), cy)),
+                        __fmul_rn(__ldg(k + 3 * j + 2), cz));
+    long long gx = (long long)__fdiv_rn(im[0], im[2]), gy = (long long)__fdiv_rn(im[1], im[2]);   // .long()
+    gx = (long long)__fmul_rn(image_scale, (float)gx);                                           // scaled-image pixels
+    gy = (long long)__fmul_rn(image_scale, (float)gy);
+    const float h = __ldg(shape + ((long long)c * B + b) * 2), w = __ldg(shape + ((long long)c * B + b) * 2 + 1);
+    const bool ok = gx > 0 && (float)gx < w && gy > 0 && (float)gy < h && cz > __ldg(thres + c);
+    const long long o = (long long)c * n + i;
+    if (!ok) gx = gy = 0;
+    grid[2 * o] = gx;
+    grid[2 * o + 1] = gy;
+    depth[o] = ok ? cz : 0.f;
+    mask[o] = ok;
+    // feature-map pixel: (grid.float() * (Wf / raw_w)).long()
+    fx[o] = (long long)__fmul_rn((float)gx, __fdiv_rn(Wf, w));
+    fy[o] = (long long)__fmul_rn((float)gy, __fdiv_rn(Hf, h));
+  }
+}
+}  // namespace
+
+// indices [n, 4] int32 (b, z, y, x); pts [n, 3] fp32; lidar2cam [n_cam, B, 4, 4], intrinsic [n_cam, B, 3, 3],
+// image_shape [n_cam, B, 2] = (H, W) as fp32, depth_thres [n_cam]: device tensors.  Outputs, all [n_cam, n(, 2)]:
+// grid int64 (x, y) in scaled-image pixels, depth, mask (bool), feat_x / feat_y int64 = feature-map pixel (Hf x Wf map).
+extern "C" int ddf_project_cameras(const int* indices, const float* pts, const float* lidar2cam, const float* intrinsic,
+                                   const float* image_shape, const float* depth_thres, int64_t n, int64_t n_cam,
+                                   int64_t B, float image_scale, int64_t Hf, int64_t Wf, int64_t* grid, float* depth,
+                                   void* mask, int64_t* feat_x, int64_t* feat_y, void* stream_) {
+  DDF_CHECK_ARG(n >= 0 && n_cam > 0 && B > 0 && Hf > 0 && Wf > 0 && n < (1ll << 31), "project_cameras: bad sizes");
+  if (n == 0) return DDF_OK;
+  DDF_CHECK_ARG(indices && pts && lidar2cam && intrinsic && image_shape && depth_thres && grid && depth && mask &&
+                    feat_x && feat_y,
+                "project_cameras: null pointer");
+  DDF_LAUNCH(project_cameras_kernel, (unsigned)ddf::cdiv(n, kThreads), kThreads, 0, (cudaStream_t)stream_, indices, pts,
+             lidar2cam, intrinsic, image_shape, depth_thres, (int)n_cam, (int)B, image_scale, (float)Hf, (float)Wf, (int)n,
+             reinterpret_cast<long long*>(grid), depth, reinterpret_cast<bool*>(mask),
+             reinterpret_cast<long long*>(feat_x), reinterpret_cast<long long*>(feat_y));
+  DDF_LAUNCH_CHECK();
+  return DDF_OK;
+}
+
 // points [n, stride >= 3] fp32 (xyz first); lidar2img_host [n_cam, 4, 4] HOST floats; group_base = sample * n_cam.
 // Outputs: group [n] int32 = group_base + camera, grid [n, 2] = (x / pad_w, y / pad_h), grid_o [n, 2] padded-image pixels.
 extern "C" int ddf_project_assign(const float* points, int64_t n, int64_t stride, const float* lidar2img_host,

@@ -167,9 +167,41 @@ class Point2ImageProjection(nn.Module):
             pts = out
         return pts
 
+    def project_all(self, indices, pts, image_scale, batch_dict, cam_keys, Hf=1, Wf=1):
+        """All cameras in ONE kernel (csrc/projection.cu: ddf_project_cameras): image_grid (n_cam, N, 2) long, depth,
+        point_mask as ``forward``, plus the pixel of the (Hf, Wf) feature map under every (camera, voxel)."""
+        from .. import lib as _lib
+        dev = indices.device
+        n, n_cam = indices.shape[0], len(cam_keys)
+        keys = [k.lower().lstrip("cam_") for k in cam_keys]          # the reference's (quirky) key derivation
+        l2c = torch.stack([batch_dict["calib"]["lidar2cam_" + k].to(dev) for k in keys]).float().contiguous()
+        intr = torch.stack([batch_dict["calib"]["cam_intrinsic_" + k].to(dev) for k in keys]).float().contiguous()
+        shape = torch.stack([batch_dict["image_shape"][k.lower()].to(dev) for k in cam_keys]).float().contiguous()
+        thres = torch.tensor([float(self.depth_thres[k.upper()]) for k in cam_keys], dtype=torch.float32, device=dev)
+        grid = torch.empty((n_cam, n, 2), dtype=torch.long, device=dev)
+        depth = torch.empty((n_cam, n), dtype=torch.float32, device=dev)
+        mask = torch.empty((n_cam, n), dtype=torch.bool, device=dev)
+        fx = torch.empty((n_cam, n), dtype=torch.long, device=dev)
+        fy = torch.empty((n_cam, n), dtype=torch.long, device=dev)
+        idx = indices.contiguous()
+        p = pts.contiguous().float()
+        with torch.cuda.device(dev):
+            rc = _lib.get_lib().ddf_project_cameras(
+                _lib.ptr(idx), _lib.ptr(p), _lib.ptr(l2c), _lib.ptr(intr), _lib.ptr(shape), _lib.ptr(thres), n, n_cam,
+                l2c.shape[1], float(image_scale), int(Hf), int(Wf), _lib.ptr(grid), _lib.ptr(depth), _lib.ptr(mask),
+                _lib.ptr(fx), _lib.ptr(fy), _lib.current_stream())
+        _lib.check(rc, "project_cameras")
+        return grid, depth, mask, fx, fy
+
     def forward(self, indices, pts, image_scale, batch_dict, cam_keys):
         """Returns image_grid (n_cam, N, 2) long (x, y) in scaled-image pixels, depth (n_cam, N) and
         point_mask (n_cam, N) following transform_grid / forward of the reference projector."""
+        if indices.is_cuda and indices.dtype == torch.int32:
+            return self.project_all(indices, pts, image_scale, batch_dict, cam_keys)[:3]
+        return self.forward_eager(indices, pts, image_scale, batch_dict, cam_keys)
+
+    def forward_eager(self, indices, pts, image_scale, batch_dict, cam_keys):
+        """The tensor-op form (host tensors; the oracle-driven CPU path)."""
         b_idx = indices[:, 0].long()
         grids, depths, masks = [], [], []
         homo = torch.cat([pts, pts.new_ones(pts.shape[0], 1)], 1)
@@ -224,18 +256,27 @@ class VoxelWithPointProjection(nn.Module):
             self.ifat = ifat.__all__[cfg.pop("fusion_method")](**cfg)
         self.seg_cfg = None
 
+    def _feature_pixels(self, indices, pts, batch_dict, cams, Hf, Wf):
+        """Feature-map pixel (x, y) under every (camera, voxel) and the visibility mask, each (n_cam, N):
+        projection + scaled-image pixels -> feature-map pixels (voxel_with_point_projection.py:253-257)."""
+        if indices.is_cuda and indices.dtype == torch.int32:
+            _, _, mask, gx, gy = self.point_projector.project_all(indices, pts, self.image_scale, batch_dict,
+                                                                  self.image_list, Hf, Wf)
+            return gx, gy, mask
+        grid, _, mask = self.point_projector(indices, pts, self.image_scale, batch_dict, self.image_list)
+        b_idx = indices[:, 0].long()
+        raw = torch.stack([batch_dict["image_shape"][c].to(grid.device)[b_idx] for c in cams]).float()  # (n_cam,N,2)
+        gf = grid.float()
+        return (gf[..., 0] * (Wf / raw[..., 1])).long(), (gf[..., 1] * (Hf / raw[..., 0])).long(), mask
+
     def _queries(self, sp_tensor, d_factor, batch_dict, cams, Hf, Wf):
         """(camera, voxel) queries of one backbone scale in (sample, camera)-major, voxel-minor order:
         group id, feature-map pixel (x, y), voxel row, reverse-augmented xyz."""
         indices = sp_tensor.indices
         n_cam = len(cams)
         pts = self.point_projector.lidar_points(indices, d_factor, batch_dict)
-        grid, _, mask = self.point_projector(indices, pts, self.image_scale, batch_dict, self.image_list)
         b_idx = indices[:, 0].long()
-        raw = torch.stack([batch_dict["image_shape"][c].to(grid.device)[b_idx] for c in cams]).float()
-        gf = grid.float()
-        gx = (gf[..., 0] * (Wf / raw[..., 1])).long()
-        gy = (gf[..., 1] * (Hf / raw[..., 0])).long()
+        gx, gy, mask = self._feature_pixels(indices, pts, batch_dict, cams, Hf, Wf)
         cam_id, vox = mask.nonzero(as_tuple=True)
         group = b_idx[vox] * n_cam + cam_id
         order = torch.sort(group, stable=True)[1]
@@ -272,13 +313,8 @@ class VoxelWithPointProjection(nn.Module):
         Hf, Wf = img.shape[-2:]
 
         pts = self.point_projector.lidar_points(indices, d_factor_list[-1], batch_dict)
-        grid, _, mask = self.point_projector(indices, pts, self.image_scale, batch_dict, self.image_list)
-        # scaled-image pixels -> feature-map pixels (voxel_with_point_projection.py:253-257)
         b_idx = indices[:, 0].long()
-        raw = torch.stack([batch_dict["image_shape"][c].to(grid.device)[b_idx] for c in cams]).float()  # (n_cam,N,2)
-        gf = grid.float()
-        gx = (gf[..., 0] * (Wf / raw[..., 1])).long()
-        gy = (gf[..., 1] * (Hf / raw[..., 0])).long()
+        gx, gy, mask = self._feature_pixels(indices, pts, batch_dict, cams, Hf, Wf)
 
         if self.ifat_cfg is not None and fuse_mode == "pfat":
             img = self._gate_image_features(img, encoded_voxel_list, d_factor_list, batch_dict, cams, batch_size)

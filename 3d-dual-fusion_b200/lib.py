@@ -70,6 +70,7 @@ _SIGNATURES = {
     "ddf_add_dropout_layer_norm_backward": [c_ptr] * 9 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_ptr],
     "ddf_project_assign": [c_ptr, c_i64, c_i64, c_ptr, c_i64] + [c_f32] * 9 + [c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "ddf_group_ranks": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "ddf_project_cameras": [c_ptr] * 6 + [c_i64] * 3 + [c_f32, c_i64, c_i64] + [c_ptr] * 6,
     "ddf_col_sum": [c_ptr, c_ptr, c_i64, c_i64, c_ptr],
     "ddf_bigate_sum_forward": [c_ptr] * 9 + [c_i64, c_i64, c_int, c_ptr],
     "ddf_bigate_sum_backward": [c_ptr] * 13 + [c_i64, c_i64, c_int, c_ptr],

@@ -412,6 +412,17 @@ int ddf_project_assign(const float* points, int64_t n, int64_t stride, const flo
                        void* stream);
 int ddf_group_ranks(const int* group, int64_t n, int64_t n_groups, int* col, int* counts, void* stream);
 
+/* CenterPoint / Det3D projection (CenterPoint/det3d/models/fusion/point_to_image_projection.py transform_grid +
+ * forward, voxel_with_point_projection.py:160-260): every camera that sees a voxel makes a query.  indices [n, 4]
+ * int32 (b, z, y, x), pts [n, 3] reverse-augmented voxel corners, lidar2cam [n_cam, B, 4, 4], intrinsic
+ * [n_cam, B, 3, 3], image_shape [n_cam, B, 2] (H, W) fp32, depth_thres [n_cam] - device tensors.  Outputs per
+ * (camera, voxel): grid int64 [n_cam, n, 2] (x, y) in scaled-image pixels (0 where masked), depth, mask (bool bytes),
+ * feat_x / feat_y int64 = pixel of the Hf x Wf feature map. */
+int ddf_project_cameras(const int* indices, const float* pts, const float* lidar2cam, const float* intrinsic,
+                        const float* image_shape, const float* depth_thres, int64_t n, int64_t n_cam, int64_t B,
+                        float image_scale, int64_t Hf, int64_t Wf, int64_t* grid, float* depth, void* mask,
+                        int64_t* feat_x, int64_t* feat_y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

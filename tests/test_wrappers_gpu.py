@@ -311,3 +311,33 @@ def test_projection_and_group_rank_kernels_match_the_tensor_implementation():
     expect = torch.empty_like(order)
     expect[order] = torch.arange(50000, device="cuda") - starts[group.long()[order]]
     assert torch.equal(col.long(), expect)
+
+
+def test_centerpoint_projection_kernel_matches_tensor_ops():
+    """ddf_project_cameras (every camera, one kernel) against the module's tensor-op form (point_to_image_projection.py
+    transform_grid / forward restated op by op): masks, integer pixel grids, depths and feature-map pixels. The order of
+    a 4-term torch sum is unspecified, so a pixel that lands within an ulp of an integer may flip: at most 1e-4 of them."""
+    from ddf_b200.fusion.centerpoint import Point2ImageProjection
+    B = 3
+    bd = synth.centerpoint_batch(B, feat_hw=(38, 67), img_hw=(150, 267), seed=2)
+    for d in (bd["calib"], bd["image_shape"]):
+        for k in d:
+            d[k] = d[k].cuda()
+    depth_thres = {"CAM_FRONT": 1, "CAM_FRONT_LEFT": 0, "CAM_FRONT_RIGHT": 0, "CAM_BACK": 0.5, "CAM_BACK_LEFT": 0, "CAM_BACK_RIGHT": 0}
+    proj = Point2ImageProjection(synth.NUSC_VOXEL, synth.NUSC_RANGE, depth_thres=depth_thres)
+    rng = np.random.default_rng(1)
+    n = 60000
+    idx = np.stack([np.sort(rng.integers(0, B, n)), rng.integers(0, 5, n), rng.integers(0, 180, n), rng.integers(0, 180, n)], 1)
+    idx = torch.from_numpy(idx.astype(np.int32)).cuda()
+    pts = proj.lidar_points(idx, 8, bd)
+    scale = 1.0 / 6
+    g_k, d_k, m_k, fx, fy = proj.project_all(idx, pts, scale, bd, synth.CP_CAMS, 38, 67)
+    g_e, d_e, m_e = proj.forward_eager(idx, pts, scale, bd, synth.CP_CAMS)
+    assert bool(m_e.any()) and float(m_e.float().mean()) > 0.05
+    same = (m_k == m_e) & (g_k == g_e).all(-1)
+    assert float((~same).float().mean()) < 1e-4
+    assert torch.allclose(d_k[same], d_e[same], rtol=1e-5, atol=1e-5)
+    raw = torch.stack([bd["image_shape"][c.lower()][idx[:, 0].long()] for c in synth.CP_CAMS]).float()
+    gf = g_e.float()
+    ex, ey = (gf[..., 0] * (67 / raw[..., 1])).long(), (gf[..., 1] * (38 / raw[..., 0])).long()
+    assert torch.equal(fx[same], ex[same]) and torch.equal(fy[same], ey[same])
