@@ -103,9 +103,9 @@ relu_dropout_bwd_bias_kernel(const float* __restrict__ gy, const float* __restri
 // atomicAdd per column and CTA.  out must be zeroed by the caller.  C / 4 <= 256 and 256 % (C / 4) == 0.
 __global__ void __launch_bounds__(kThreads)
 col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int c4) {
-  const int col = threadIdx.x % c4, rl = threadIdx.x / c4, rpb = kThreads / c4;
+  const int col = threadIdx.x % c4, rl = threadIdx.x / c4, rpb = kThreads / c4;   // threads past rpb * c4 idle
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+  for (long long r = (long long)blockIdx.x * rpb + rl; rl < rpb && r < rows; r += (long long)gridDim.x * rpb) {
     const float4 v = ldg4(x + (r * c4 + col) * 4);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
@@ -125,22 +125,25 @@ col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long r
 }
 
 // ---- s = a + dropout(b);  y = LayerNorm(s) * gamma + beta.  One warp per row, C = 32 * VPL * 4 ---------
-template <int VPL>   // float4 vectors per lane: C = 128 * VPL
+// LPR = lanes per row (32; 16 / 8 for C = 64 / 32: a warp then owns 2 / 4 rows), VPL = float4 vectors per lane
+template <int VPL, int LPR>   // C = 4 * LPR * VPL
 __global__ void __launch_bounds__(kThreads)
 add_dropout_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           float* __restrict__ s_out, float* __restrict__ y, float* __restrict__ mean_out,
                           float* __restrict__ rstd_out, long long rows, unsigned long long seed, unsigned thr,
                           float scale, float eps) {
-  constexpr int C = 128 * VPL;
-  const int lane = threadIdx.x & 31;
-  const long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
-  if (row >= rows) return;
+  constexpr int C = 4 * LPR * VPL;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const long long wrow = (((long long)blockIdx.x * kThreads + threadIdx.x) >> 5) * (32 / LPR);
+  if (wrow >= rows) return;                      // warp-uniform
+  const bool valid = wrow + lane / LPR < rows;   // a warp's last rows may not exist: computed on a copy, not stored
+  const long long row = valid ? wrow + lane / LPR : rows - 1;
   float4 v[VPL];
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const long long e4 = row * (C / 4) + j * 32 + lane;
+    const long long e4 = row * (C / 4) + j * LPR + sub;
     v[j] = ldg4(a + e4 * 4);
     if (b) {
       float4 d = ldg4(b + e4 * 4);
@@ -153,7 +156,7 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__
     sum += v[j].x + v[j].y + v[j].z + v[j].w;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum * (1.f / C);
   float var = 0.f;
 #pragma unroll
@@ -162,16 +165,17 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__
     var += dx * dx + dy * dy + dz * dz + dw * dw;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var * (1.f / C) + eps);
-  if (lane == 0) {
+  if (!valid) return;
+  if (sub == 0) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
   }
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const long long e4 = row * (C / 4) + j * 32 + lane;
-    const int c = (j * 32 + lane) * 4;
+    const long long e4 = row * (C / 4) + j * LPR + sub;
+    const int c = (j * LPR + sub) * 4;
     if (s_out) *reinterpret_cast<float4*>(s_out + e4 * 4) = v[j];
     const float4 g = ldg4(gamma + c), be = ldg4(beta + c);
     float4 o;
@@ -185,30 +189,34 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__
 
 // gs = rstd * (gy*gamma - mean_c(gy*gamma) - xhat * mean_c(gy*gamma*xhat));  ga = gs;  gb = gs * keep * scale
 // ggamma += sum_rows gy * xhat, gbeta += sum_rows gy  (per-CTA partials in shared memory, then atomics)
-template <int VPL>
+template <int VPL, int LPR>
 __global__ void __launch_bounds__(kThreads)
 add_dropout_ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ s,
                           const float* __restrict__ gamma, const float* __restrict__ mean_in,
                           const float* __restrict__ rstd_in, float* __restrict__ ga, float* __restrict__ gb,
                           float* __restrict__ ggamma, float* __restrict__ gbeta, long long rows,
                           unsigned long long seed, unsigned thr, float scale) {
-  constexpr int C = 128 * VPL;
+  constexpr int C = 4 * LPR * VPL, RPW = 32 / LPR;
   __shared__ float sh_g[C], sh_b[C];
   for (int i = threadIdx.x; i < C; i += kThreads) sh_g[i] = sh_b[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
   const long long warps = ((long long)gridDim.x * kThreads) >> 5;
   float4 acc_g[VPL], acc_b[VPL];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) acc_g[j] = acc_b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5; row < rows; row += warps) {
+  for (long long wr = (((long long)blockIdx.x * kThreads + threadIdx.x) >> 5) * RPW; wr < rows; wr += warps * RPW) {
+    const bool valid = wr + lane / LPR < rows;
+    const long long row = valid ? wr + lane / LPR : rows - 1;
     const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
     float4 g[VPL], xh[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const long long e4 = row * (C / 4) + j * 32 + lane;
-      const float4 gyv = ldg4(gy + e4 * 4), sv = ldg4(s + e4 * 4), gm = ldg4(gamma + (j * 32 + lane) * 4);
+      const long long e4 = row * (C / 4) + j * LPR + sub;
+      float4 gyv = ldg4(gy + e4 * 4);
+      if (!valid) gyv = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 sv = ldg4(s + e4 * 4), gm = ldg4(gamma + (j * LPR + sub) * 4);
       xh[j] = make_float4((sv.x - mean) * rstd, (sv.y - mean) * rstd, (sv.z - mean) * rstd, (sv.w - mean) * rstd);
       acc_b[j].x += gyv.x; acc_b[j].y += gyv.y; acc_b[j].z += gyv.z; acc_b[j].w += gyv.w;
       acc_g[j].x += gyv.x * xh[j].x; acc_g[j].y += gyv.y * xh[j].y;
@@ -218,14 +226,15 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict_
       s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = LPR / 2; o > 0; o >>= 1) {
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     const float m1 = s1 * (1.f / C), m2 = s2 * (1.f / C);
+    if (!valid) continue;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const long long e4 = row * (C / 4) + j * 32 + lane;
+      const long long e4 = row * (C / 4) + j * LPR + sub;
       float4 r;
       r.x = rstd * (g[j].x - m1 - xh[j].x * m2);
       r.y = rstd * (g[j].y - m1 - xh[j].y * m2);
@@ -245,7 +254,7 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict_
   }
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const int c = (j * 32 + lane) * 4;
+    const int c = (j * LPR + sub) * 4;
     atomicAdd(&sh_g[c], acc_g[j].x); atomicAdd(&sh_g[c + 1], acc_g[j].y);
     atomicAdd(&sh_g[c + 2], acc_g[j].z); atomicAdd(&sh_g[c + 3], acc_g[j].w);
     atomicAdd(&sh_b[c], acc_b[j].x); atomicAdd(&sh_b[c + 1], acc_b[j].y);
@@ -305,14 +314,16 @@ extern "C" int ddf_bias_relu_dropout_backward(const float* grad_out, const float
   return DDF_OK;
 }
 
-#define DDF_LN_DISPATCH(C, CALL)                     \
-  switch (C) {                                       \
-    case 128: { constexpr int VPL = 1; CALL; } break; \
-    case 256: { constexpr int VPL = 2; CALL; } break; \
-    case 512: { constexpr int VPL = 4; CALL; } break; \
-    default:                                         \
-      ddf::set_error("add_dropout_layer_norm: C must be 128, 256 or 512, got %lld", (long long)(C)); \
-      return DDF_ERR_ARG;                            \
+#define DDF_LN_DISPATCH(C, CALL)                                          \
+  switch (C) {                                                            \
+    case 32: { constexpr int VPL = 1, LPR = 8; CALL; } break;             \
+    case 64: { constexpr int VPL = 1, LPR = 16; CALL; } break;            \
+    case 128: { constexpr int VPL = 1, LPR = 32; CALL; } break;           \
+    case 256: { constexpr int VPL = 2, LPR = 32; CALL; } break;           \
+    case 512: { constexpr int VPL = 4, LPR = 32; CALL; } break;           \
+    default:                                                              \
+      ddf::set_error("add_dropout_layer_norm: C must be 32, 64, 128, 256 or 512, got %lld", (long long)(C)); \
+      return DDF_ERR_ARG;                                                 \
   }
 
 // s = a + dropout(b) (b may be NULL: s = a);  y = LayerNorm(s) * gamma + beta over the last dim C.
@@ -326,8 +337,9 @@ extern "C" int ddf_add_dropout_layer_norm_forward(const float* a, const float* b
   DDF_CHECK_ARG(a && gamma && beta && y && mean && rstd, "add_dropout_layer_norm: null pointer");
   DDF_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(gamma) && aligned16(beta) && aligned16(s_out) && aligned16(y),
                 "add_dropout_layer_norm: misaligned pointer");
-  const unsigned grid = (unsigned)ddf::cdiv(rows * 32, kThreads);
-  DDF_LN_DISPATCH(C, DDF_LAUNCH(add_dropout_ln_fwd_kernel<VPL>, grid, kThreads, 0, (cudaStream_t)stream_, a, b, gamma,
+  const long long wrows = C >= 128 ? rows : ddf::cdiv(rows, 128 / C);     // rows of warps
+  const unsigned grid = (unsigned)ddf::cdiv(wrows * 32, kThreads);
+  DDF_LN_DISPATCH(C, DDF_LAUNCH((add_dropout_ln_fwd_kernel<VPL, LPR>), grid, kThreads, 0, (cudaStream_t)stream_, a, b, gamma,
                                 beta, s_out, y, mean, rstd, (long long)rows, (unsigned long long)seed, threshold(p),
                                 1.f / (1.f - p), eps));
   DDF_LAUNCH_CHECK();
@@ -343,9 +355,9 @@ extern "C" int ddf_add_dropout_layer_norm_backward(const float* grad_y, const fl
   DDF_CHECK_ARG(rows >= 0 && p >= 0.f && p < 1.f, "add_dropout_layer_norm_backward: bad arguments");
   if (rows == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_y && s && gamma && mean && rstd, "add_dropout_layer_norm_backward: null pointer");
-  long long grid = ddf::cdiv(rows * 32, kThreads);
+  long long grid = ddf::cdiv((C >= 128 ? rows : ddf::cdiv(rows, 128 / C)) * 32, kThreads);
   if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;   // grid-stride: bounded number of atomics on grad_gamma / beta
-  DDF_LN_DISPATCH(C, DDF_LAUNCH(add_dropout_ln_bwd_kernel<VPL>, (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_y,
+  DDF_LN_DISPATCH(C, DDF_LAUNCH((add_dropout_ln_bwd_kernel<VPL, LPR>), (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_y,
                                 s, gamma, mean, rstd, grad_a, grad_b, grad_gamma, grad_beta, (long long)rows,
                                 (unsigned long long)seed, threshold(p), 1.f / (1.f - p)));
   DDF_LAUNCH_CHECK();
@@ -355,8 +367,8 @@ extern "C" int ddf_add_dropout_layer_norm_backward(const float* grad_y, const fl
 // out [C] = sum over the rows of x [rows, C] (zeroed inside).  C % 4 == 0, C / 4 <= 256, 256 % (C / 4) == 0.
 extern "C" int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DDF_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0 && C / 4 <= kThreads && kThreads % (C / 4) == 0,
-                "col_sum: C / 4 must divide %d (C=%lld)", kThreads, (long long)C);
+  DDF_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0 && C / 4 <= kThreads, "col_sum: C must be a multiple of 4, <= %d (C=%lld)",
+                4 * kThreads, (long long)C);
   DDF_CHECK_ARG(out != nullptr, "col_sum: null out");
   DDF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, stream));
   if (rows == 0) return DDF_OK;

@@ -166,11 +166,11 @@ class LocalTransformer(nn.Module):
         """TransformerEncoderLayerPreNorm.forward (pointformer.py:33-44) on (T, C) tokens; groups of ``nsample``
         consecutive rows are the sequences."""
         mha = layer.self_attn
-        s = layer.norm1(x)
+        s = _fused.add_dropout_layer_norm(layer.norm1, None, x, None)       # plain LayerNorm, one warp-per-row pass
         qkv = _fused.linear_wb(s, mha.in_proj_weight, mha.in_proj_bias)
         o = _pointops.local_attention(qkv, mha.num_heads, self.nsample)
         s = s + layer.dropout1(_fused.linear_wb(o, mha.out_proj.weight, mha.out_proj.bias))
-        s = layer.norm2(s)
+        s = _fused.add_dropout_layer_norm(layer.norm2, None, s, None)
         hidden = _fused.ffn_hidden(layer.linear1, layer.dropout, s)
         return s + layer.dropout2(_fused.linear(layer.linear2, hidden))
 

@@ -67,6 +67,11 @@ def col_sum(x2d):
 
 
 def _col_sum_ok(C):
+    return C % 4 == 0 and C // 4 <= 256
+
+
+def _bias_in_kernel_ok(C):
+    # relu_dropout_bwd_bias_kernel: a thread row of the CTA per C / 4 columns
     return C % 4 == 0 and C // 4 <= 256 and 256 % (C // 4) == 0
 
 
@@ -215,12 +220,14 @@ class _AddDropoutLayerNorm(Function):
 def add_dropout_layer_norm(norm, dropout, a, b):
     """``norm(a + dropout(b))`` with ``norm`` an ``nn.LayerNorm`` over the last dim."""
     C = a.shape[-1]
-    if (a.dtype != torch.float32 or C not in (128, 256, 512) or not norm.elementwise_affine
+    if (a.dtype != torch.float32 or C not in (32, 64, 128, 256, 512) or not norm.elementwise_affine
             or norm.bias is None or tuple(norm.normalized_shape) != (C,)
             or (b is not None and (b.dtype != torch.float32 or b.shape != a.shape))
             or norm.weight.dtype != torch.float32 or norm.bias.dtype != torch.float32):
         _lib.require_cuda(a)
-        return norm(a + dropout(b))
+        if b is None:
+            return norm(a)
+        return norm(a + (dropout(b) if dropout is not None else b))
     p = dropout.p if (dropout is not None and dropout.training) else 0.0
     return _AddDropoutLayerNorm.apply(a, b, norm.weight, norm.bias, p, norm.eps)
 

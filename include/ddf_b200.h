@@ -375,7 +375,7 @@ int ddf_add_dropout_layer_norm_backward(const float* grad_y, const float* s, con
                                         float p, uint64_t seed, void* stream);
 
 /* out [C] = column sums of x [rows, C] (the bias gradient of a Linear over all tokens; zeroed inside).
- * C % 4 == 0 and C / 4 must divide 256. */
+ * C % 4 == 0, C <= 1024. */
 int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, void* stream);
 
 /* Bi-directional gated fusion of the LiDAR / image query streams (<proj>/models/model_utils/attentions.py:89-117,

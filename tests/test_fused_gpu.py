@@ -57,7 +57,8 @@ def test_ffn_hidden_dropout_invariants():
     assert not torch.equal(out2 != 0, kept)
 
 
-@pytest.mark.parametrize("rows,C", [(1, 128), (777, 128), (50001, 128), (300, 256), (65, 512)])
+@pytest.mark.parametrize("rows,C", [(1, 128), (777, 128), (50001, 128), (300, 256), (65, 512), (1, 64), (50003, 64),
+                                    (131072, 64), (9, 32), (4099, 32)])
 @pytest.mark.parametrize("with_b", [True, False])
 def test_add_layer_norm_eval_matches_module_chain(rows, C, with_b):
     from ddf_b200.ops.fused import add_dropout_layer_norm
@@ -106,8 +107,8 @@ def test_add_dropout_layer_norm_train_consistency():
 
 def test_unsupported_shapes_use_library_ops_and_cpu_is_refused():
     from ddf_b200.ops.fused import add_dropout_layer_norm, ffn_hidden
-    norm, drop = nn.LayerNorm(64).cuda(), nn.Dropout(0.0)
-    x = torch.randn(10, 64, device="cuda")
+    norm, drop = nn.LayerNorm(96).cuda(), nn.Dropout(0.0)
+    x = torch.randn(10, 96, device="cuda")
     assert torch.allclose(add_dropout_layer_norm(norm, drop, x, x), norm(x + x))
     with pytest.raises(RuntimeError):
         ffn_hidden(nn.Linear(128, 256), drop, torch.randn(4, 128))
@@ -219,3 +220,14 @@ def test_bigate_sum_kernel_matches_module_chain(cls_name, C, drop_second):
     else:
         assert rel(gate.a_conv1d.weight.grad, ref.a_conv1d.weight.grad) < 1e-3
         assert rel(gate.a_conv1d.bias.grad, ref.a_conv1d.bias.grad) < 1e-3
+
+
+@pytest.mark.parametrize("rows,C", [(5000, 192), (131072, 192), (4097, 384), (70000, 8), (33333, 1024)])
+def test_col_sum_any_width(rows, C):
+    """ddf_col_sum for widths whose quarter does not divide the CTA (192 = the qkv projection of the 64-channel
+    LocalTransformer): idle threads instead of a fallback to ATen's sum(0)."""
+    from ddf_b200.ops import fused
+    x = torch.randn(rows, C, device="cuda")
+    ref = x.double().sum(0)
+    got = fused.col_sum(x)
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 1e-5
