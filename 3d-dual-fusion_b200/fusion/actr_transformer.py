@@ -55,10 +55,10 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
     def forward_ffn(self, src):
         if self.activation is F.relu:
-            hidden = fused.ffn_hidden(self.linear1, self.dropout2, src)
+            src2 = fused.ffn(self.linear1, self.dropout2, self.linear2, src)     # one kernel forward where supported
         else:
-            hidden = self.dropout2(self.activation(self.linear1(src)))
-        return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, fused.linear(self.linear2, hidden))
+            src2 = fused.linear(self.linear2, self.dropout2(self.activation(self.linear1(src))))
+        return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, src2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,
                 padding_mask=None, q_pos=None, q_feat=None, q_i_feat=None, plan=None):
@@ -107,12 +107,17 @@ class DeformableTransformerFusionEncoderLayer(nn.Module):
             return fused.ffn_hidden(linear, dropout, src)
         return dropout(self.activation(linear(src)))
 
+    def _ffn(self, linear_a, dropout, linear_b, src):
+        if self.activation is F.relu:
+            return fused.ffn(linear_a, dropout, linear_b, src)                   # one kernel forward where supported
+        return fused.linear(linear_b, self._hidden(linear_a, dropout, src))
+
     def forward_i_ffn(self, src):
-        src2 = fused.linear(self.linear2, self._hidden(self.linear1, self.dropout2, src))
+        src2 = self._ffn(self.linear1, self.dropout2, self.linear2, src)
         return fused.add_dropout_layer_norm(self.norm2, self.dropout3, src, src2)
 
     def forward_p_ffn(self, src):
-        src2 = fused.linear(self.linear4, self._hidden(self.linear3, self.dropout4, src))
+        src2 = self._ffn(self.linear3, self.dropout4, self.linear4, src)
         return fused.add_dropout_layer_norm(self.norm3, self.dropout5, src, src2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index,

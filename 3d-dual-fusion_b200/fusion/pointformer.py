@@ -171,8 +171,7 @@ class LocalTransformer(nn.Module):
         o = _pointops.local_attention(qkv, mha.num_heads, self.nsample)
         s = s + layer.dropout1(_fused.linear_wb(o, mha.out_proj.weight, mha.out_proj.bias))
         s = _fused.add_dropout_layer_norm(layer.norm2, None, s, None)
-        hidden = _fused.ffn_hidden(layer.linear1, layer.dropout, s)
-        return s + layer.dropout2(_fused.linear(layer.linear2, hidden))
+        return s + layer.dropout2(_fused.ffn(layer.linear1, layer.dropout, layer.linear2, s))
 
     def forward_tokens(self, xyz, feats_nc, geom=None):
         """feats_nc (B, N, C) row-major voxel features -> (B, N, C). No (B, C, np, ns) tensor, no permutes: the grouped

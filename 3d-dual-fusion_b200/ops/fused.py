@@ -295,3 +295,73 @@ def bigate_sum(b_conv, a_conv, feat1, feat2, fuse_in):
             or b_conv.weight.numel() != C or a_conv.weight.numel() != C):
         return None
     return _BiGateSum.apply(feat1, feat2, b_conv.weight, b_conv.bias, a_conv.weight, a_conv.bias, fuse_in)
+
+
+class _FusedFFN(Function):
+    """y = linear2(dropout(relu(linear1(x)))) with the forward as ONE kernel (ddf_ffn_forward: the [T, d_ffn] hidden
+    activation is written once for backward and never read again in forward). Backward: the split-K weight
+    gradients (xty), the fused ReLU / dropout / bias-gradient pass, library GEMMs for the two input gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, p):
+        _lib.require_cuda(x, w1, b1, w2, b2)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        T, D = x2.shape
+        F_ = w1.shape[0]
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        h = torch.empty((T, F_), dtype=torch.float32, device=x.device)
+        y = torch.empty((T, D), dtype=torch.float32, device=x.device)
+        seed = _seed() if p > 0 else 0
+        ws = torch.empty(2 * D * F_, dtype=torch.float32, device=x.device)     # re-laid weights (ddf_ffn_workspace_bytes)
+        with torch.cuda.device(x.device):
+            rc = _lib.get_lib().ddf_ffn_forward(_lib.ptr(x2), _lib.ptr(w1c), _lib.ptr(b1), _lib.ptr(w2c), _lib.ptr(b2),
+                                                _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws), T, D, F_, float(p), seed,
+                                                _lib.current_stream())
+        _lib.check(rc, "ffn_forward")
+        ctx.p = float(p)
+        ctx.has_b2 = b2 is not None
+        ctx.save_for_backward(x2, h, w1c, w2c)
+        return y.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2, h, w1, w2 = ctx.saved_tensors
+        T, D = x2.shape
+        F_ = w1.shape[0]
+        g2 = gy.reshape(T, D)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        need = ctx.needs_input_grad
+        gb2 = (col_sum(g2) if _col_sum_ok(D) else g2.sum(0)) if (need[4] and ctx.has_b2) else None
+        gw2 = xty(g2, h) if need[3] else None                         # [D, F]
+        gx = gw1 = gb1 = None
+        if need[0] or need[1] or need[2]:
+            gh = g2 @ w2                                               # [T, F]
+            in_kernel = need[2] and _bias_in_kernel_ok(F_)
+            gb1 = torch.zeros(F_, dtype=torch.float32, device=h.device) if in_kernel else None
+            with torch.cuda.device(h.device):
+                rc = _lib.get_lib().ddf_bias_relu_dropout_backward(_lib.ptr(gh), _lib.ptr(h), _lib.ptr(gh), _lib.ptr(gb1),
+                                                                   T, F_, ctx.p, _lib.current_stream())
+            _lib.check(rc, "bias_relu_dropout_backward")
+            if need[2] and not in_kernel:
+                gb1 = gh.sum(0)
+            if need[1]:
+                gw1 = xty(gh, x2)                                      # [F, D]
+            if need[0]:
+                gx = (gh @ w1).view(gy.shape)
+        return gx, gw1, gb1, gw2, gb2, None
+
+
+def ffn(linear1, dropout, linear2, x):
+    """``linear2(dropout(relu(linear1(x))))`` over (..., d_model) tokens: the fused forward kernel when the shape is
+    its (d_model 128, d_ffn % 64 == 0, fp32, tf32 products allowed, many tokens), else the two-GEMM chain."""
+    D, F_ = linear1.in_features, linear1.out_features
+    T = x.numel() // max(x.shape[-1], 1)
+    if (x.is_cuda and x.dtype == torch.float32 and torch.backends.cuda.matmul.allow_tf32 and T >= 4096
+            and linear1.bias is not None and linear1.weight.dtype == torch.float32
+            and linear2.weight.dtype == torch.float32 and linear2.in_features == F_ and linear2.out_features == D
+            and _lib.get_lib().ddf_ffn_supported(T, D, F_)):
+        p = dropout.p if (dropout is not None and dropout.training) else 0.0
+        return _FusedFFN.apply(x, linear1.weight, linear1.bias, linear2.weight, linear2.bias, p)
+    return linear(linear2, ffn_hidden(linear1, dropout, x))

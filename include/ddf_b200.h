@@ -391,6 +391,16 @@ int ddf_bigate_sum_backward(const float* grad_o1, const float* grad_o2, const fl
                             float* grad_wb, float* grad_bb, float* grad_wa, float* grad_ba, int64_t rows, int64_t C,
                             int fuse_in, void* stream);
 
+/* FFN forward of the encoder layers as one kernel (<proj>/models/model_utils/actr_transformer.py:383-397):
+ * h [T, F] = dropout(relu(x [T, D] . w1 [F, D]^T + b1)) (kept for backward), y [T, D] = h . w2 [D, F]^T + b2.
+ * D = 128, F % 64 == 0 (ddf_ffn_supported); fp32 row-major, tf32 products, fp32 accumulation; dropout by a counter
+ * hash of (seed, element index) - nothing is stored, ddf_bias_relu_dropout_backward applies to h unchanged (it reads
+ * the pattern off h != 0). */
+int ddf_ffn_supported(int64_t T, int64_t D, int64_t F);
+int64_t ddf_ffn_workspace_bytes(int64_t D, int64_t F);   /* scratch for the re-laid weights, any content */
+int ddf_ffn_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* h,
+                    float* y, void* workspace, int64_t T, int64_t D, int64_t F, float p, uint64_t seed, void* stream);
+
 /* c [M, N] = a [K, M]^T . b [K, N]: the weight gradient of an nn.Linear over K tokens, W.grad [out, in] =
  * grad_out [K, out]^T . x [K, in] (autograd of F.linear in <proj>/models/model_utils/actr_transformer.py:383-397,
  * ops/modules/ms_deform_attn.py:124-147).  fp32 row-major operands read as tf32 (top 19 bits) by tcgen05, fp32
