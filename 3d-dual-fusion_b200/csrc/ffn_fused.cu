@@ -166,10 +166,10 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   uint64_t* w2_empty = bars + 7;      // 2
   uint64_t* acc1_full = bars + 9;     // 2
   uint64_t* acc1_free = bars + 11;    // 2
-  uint64_t* hs_full = bars + 13;      // 1
-  uint64_t* hs_empty = bars + 14;     // 2: by chunk parity (a waiter must see every phase of its barrier)
-  uint64_t* acc2_full = bars + 16;    // 1
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* hs_full = bars + 13;      // 2: one per 32-column half of Hs (= K-chunk of GEMM2)
+  uint64_t* hs_empty = bars + 15;     // 4: [half][chunk parity] (a waiter must see every phase of its barrier)
+  uint64_t* acc2_full = bars + 19;    // 1
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TT;
@@ -194,9 +194,8 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       mbar_init(acc1_full + s, 1);
       mbar_init(acc1_free + s, kEpiThreads / 2);
     }
-    mbar_init(hs_full, kEpiThreads / 2);
-    mbar_init(hs_empty, 2);            // GEMM2 has read the chunk AND the TMA store of h has read it
-    mbar_init(hs_empty + 1, 2);
+    for (int i = 0; i < 2; ++i) mbar_init(hs_full + i, kEpiThreads / 4);   // the 4 warps that own this half
+    for (int i = 0; i < 4; ++i) mbar_init(hs_empty + i, 2);   // GEMM2 has read the half AND the TMA store of h has read it
     mbar_init(acc2_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -274,36 +273,38 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       for (int c = 0; c < NC; ++c) {
         const int s = c & 1;
         mbar_wait(w2_full + s, (uint32_t)(c >> 1) & 1u);
-        mbar_wait(hs_full, (uint32_t)c & 1u);       // the epilogue warps wrote chunk c
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t bs = b0 + (uint64_t)(s * (kW2Bytes >> 4));
 #pragma unroll
         for (int kc = 0; kc < FC / 32; ++kc) {
+          // the halves of Hs are handed over separately: the 4 MMAs of one half run while the other is being written
+          mbar_wait(hs_full + kc, (uint32_t)c & 1u);
+          if (kc == 0) FTR(3, c);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_tf32(acc2, a0 + (uint64_t)(kc * ((TT * 128) >> 4) + 2 * ks),
                       bs + (uint64_t)(kc * ((DM * 128) >> 4) + 2 * ks), idesc2, (c | kc | ks) ? 1u : 0u);
+          umma_commit(hs_empty + kc * 2 + s);
         }
         umma_commit(w2_empty + s);
-        umma_commit(hs_empty + s);
         FTR(5, c);
       }
       umma_commit(acc2_full);
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ===================== h store: the chunk in Hs IS the swizzled image of two TMA boxes =====================
-    if (lane == 0) {
+    // ===================== h store: each half of Hs IS the swizzled image of one TMA box =====================
+    if (lane < 2) {
+      const int kc = lane;                         // lane = half
       for (int c = 0; c < NC; ++c) {
-        mbar_wait(hs_full, (uint32_t)c & 1u);       // written and fenced (fence.proxy.async) by the epilogue warps
-#pragma unroll
-        for (int kc = 0; kc < FC / 32; ++kc)         // rows past T are clipped by the tensor map
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_h),
-                       "r"(smem_u32(hs + kc * (TT * 128))), "r"(c * FC + kc * 32), "r"(row0)
-                       : "memory");
+        mbar_wait(hs_full + kc, (uint32_t)c & 1u);  // written and fenced (fence.proxy.async) by the epilogue warps
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_h),
+                     "r"(smem_u32(hs + kc * (TT * 128))), "r"(c * FC + kc * 32), "r"(row0)
+                     : "memory");                   // rows past T are clipped by the tensor map
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(hs_empty + (c & 1));
+        if (kc == 0) FTR(4, c);
+        mbar_arrive(hs_empty + kc * 2 + (c & 1));
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // h is in global memory before the CTA ends
     }
@@ -357,14 +358,14 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       }
       if (t0) FTR(8, c >> 1);
       // GEMM2(c - 1) and the store of chunk c - 1 (the other group's chunk) have read Hs
-      if (c > 0) mbar_wait(hs_empty + (grp ^ 1), (uint32_t)((c - 1) >> 1) & 1u);
+      if (c > 0) mbar_wait(hs_empty + half * 2 + (grp ^ 1), (uint32_t)((c - 1) >> 1) & 1u);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hs_row + (uint32_t)((j ^ rx) << 4)), "f"(o[4 * j]),
                      "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
                      : "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(hs_full);
+      mbar_arrive(hs_full + half);
       if (t0) FTR(9, c >> 1);
     }
     // y tile: this thread's 32 columns
@@ -393,7 +394,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   if (trb && tid == 0) {
     const long long t0 = tr[2][0];
     for (int c = 0; c < 16 && c < NC; ++c)
-      printf("ffn %2d: W1 slot %6lld W2 slot %6lld | g1 w1_full %6lld | epi ldtm done %6lld arrived %6lld g2 issued %6lld | epi start %6lld acc1_full %6lld computed %6lld wrote %6lld\n",
+      printf("ffn %2d: W1 slot %6lld W2 slot %6lld | g1 w1_full %6lld | g2 saw hs_full %6lld store read done %6lld g2 issued %6lld | epi(even chunks) start %6lld acc1_full %6lld computed %6lld wrote %6lld\n",
              c, tr[0][c] - t0, tr[1][c] - t0, tr[2][c] - t0, tr[3][c] - t0, tr[4][c] - t0, tr[5][c] - t0, tr[6][c] - t0,
              tr[7][c] - t0, tr[8][c] - t0, tr[9][c] - t0);
   }

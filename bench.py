@@ -424,7 +424,7 @@ class KernelTimer(object):
     """Per-launch CUDA-event timing of this library's kernel families on the launching stream (extra steps after the
     timed region), with their algorithmic FLOPs / bytes. ``finish_step`` closes one step; the summary
     takes, launch by launch, the MEDIAN over the recorded steps (a single step is at the mercy of one stalled launch)."""
-    KINDS = ("conv", "wgrad", "msda_fwd", "msda_bwd")
+    KINDS = ("conv", "wgrad", "msda_fwd", "msda_bwd", "xty")
 
     def __init__(self):
         self.records = {k: [] for k in self.KINDS}
@@ -493,6 +493,9 @@ class KernelTimer(object):
         # arithmetic of the module is inside the kernel
         self._wrap(msda, "msda_tile_forward", "msda_fwd", tile_meta)
         self._wrap(msda, "msda_tile_backward", "msda_bwd", tile_meta)
+        # Linear weight gradients over the tokens (split-K tcgen05 pass): both operands streamed once
+        from ddf_b200.ops import fused
+        self._wrap(fused, "xty", "xty", lambda a, b: (a.shape[0], a.shape[1], b.shape[1]))
 
     def remove(self):
         for mod, name, orig in self.saved:
@@ -514,6 +517,10 @@ class KernelTimer(object):
                 w[1] += dt
                 w[2] += fl
         return len(recs), ms, flops, byts
+
+    def xty_summary(self):
+        recs = [(dt, m) for dt, m in self.launches("xty") if m[0] >= 4096]
+        return len(recs), sum(dt for dt, _ in recs), sum(4.0 * K * (M + N) for _, (K, M, N) in recs)
 
     def msda_summary(self, kind):
         ms = byts = 0.0
@@ -663,6 +670,7 @@ def run_ours(args):
     n_wg, wg_ms, wg_flops, _ = ct.conv_summary("wgrad")
     n_mf, mf_ms, mf_bytes = ct.msda_summary("msda_fwd")
     n_mb, mb_ms, mb_bytes = ct.msda_summary("msda_bwd")
+    n_xt, xt_ms, xt_bytes = ct.xty_summary()
     ct.remove()
     if world > 1:
         dist.barrier()
@@ -701,6 +709,10 @@ def run_ours(args):
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); achieved = ALGORITHMIC flops (2 * pairs * "
                                "Cin * Cout) / median event time: the bf16x3 kernels issue 3 bf16 MMAs per algorithmic "
                                "MAC (ceiling 1/3 of the bf16 peak), the fp32 narrow layers none" % how,
+                "bound_note": "measured (profiles/r2_conv_analysis.md): with the MMAs removed these kernels keep 75-81% of "
+                              "their time - they are bound by the gather of rule-book rows out of L2 (3.9-7.6 TB/s of "
+                              "128-byte rows), not by the tensor pipe; frac is reported against the tensor peak as the "
+                              "contract asks",
                 "timing": "CUDA events around every launch, median per launch over 5 steps after the timed region",
                 "launches_per_step": n_launch, "avg_launch_ms": conv_ms / max(n_launch, 1),
                 "share_of_step": conv_ms / (ms_dev / args.steps),
@@ -718,6 +730,10 @@ def run_ours(args):
                                     "achieved_GBs": mf_bytes / (mf_ms / 1e3) / 1e9 if mf_ms else None,
                                     "peak_GBs": peaks.get("hbm_gbs"),
                                     "frac": mf_bytes / (mf_ms / 1e3) / 1e9 / peaks["hbm_gbs"] if mf_ms else None},
+                "linear_wgrad_xty": {"bound": "hbm", "launches_per_step": n_xt, "ms_per_step": xt_ms,
+                                     "achieved_GBs": xt_bytes / (xt_ms / 1e3) / 1e9 if xt_ms else None,
+                                     "peak_GBs": peaks.get("hbm_gbs"),
+                                     "frac": xt_bytes / (xt_ms / 1e3) / 1e9 / peaks["hbm_gbs"] if xt_ms else None},
                 "deform_attn_bwd": {"bound": "hbm", "launches_per_step": n_mb, "ms_per_step": mb_ms,
                                     "achieved_GBs": mb_bytes / (mb_ms / 1e3) / 1e9 if mb_ms else None,
                                     "peak_GBs": peaks.get("hbm_gbs"),
