@@ -185,7 +185,7 @@ class Point2ImageProjection(nn.Module):
         fy = torch.empty((n_cam, n), dtype=torch.long, device=dev)
         idx = indices.contiguous()
         p = pts.contiguous().float()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = _lib.get_lib().ddf_project_cameras(
                 _lib.ptr(idx), _lib.ptr(p), _lib.ptr(l2c), _lib.ptr(intr), _lib.ptr(shape), _lib.ptr(thres), n, n_cam,
                 l2c.shape[1], float(image_scale), int(Hf), int(Wf), _lib.ptr(grid), _lib.ptr(depth), _lib.ptr(mask),

@@ -85,7 +85,7 @@ def project_to_cameras_cuda(points, img_meta, group_base=0):
     group = torch.empty(n, dtype=torch.int32, device=pts.device)
     grid = torch.empty((n, 2), dtype=torch.float32, device=pts.device)
     grid_o = torch.empty((n, 2), dtype=torch.float32, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _lib.on_device(pts.device):
         rc = _lib.get_lib().ddf_project_assign(
             _lib.ptr(pts), n, pts.shape[1], l2i.ctypes.data_as(ctypes.c_void_p), l2i.shape[0], *_project_params(img_meta),
             int(group_base), _lib.ptr(group), _lib.ptr(grid), _lib.ptr(grid_o), _lib.current_stream())
@@ -99,7 +99,7 @@ def group_ranks(group, n_groups):
     n = group.shape[0]
     col = torch.empty(n, dtype=torch.int32, device=group.device)
     counts = torch.empty(n_groups, dtype=torch.int32, device=group.device)
-    with torch.cuda.device(group.device):
+    with _lib.on_device(group.device):
         rc = _lib.get_lib().ddf_group_ranks(_lib.ptr(group), n, n_groups, _lib.ptr(col), _lib.ptr(counts),
                                             _lib.current_stream())
     _lib.check(rc, "group_ranks")

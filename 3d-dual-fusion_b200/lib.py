@@ -121,8 +121,34 @@ def ptr(t):
 
 
 def current_stream():
+    """Raw handle of torch's current stream on the current device. The ``torch.cuda.current_stream()`` object path costs
+    about 14 us per call (cProfile of a bench step: 220 calls = 3.8 ms of a 34 ms host-side step); the raw query is
+    a fraction of a microsecond."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+class _NoGuard(object):
+    __slots__ = ()
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device):
+    """``with on_device(t.device):`` = ``with torch.cuda.device(t.device):`` when the tensor lives on another device than
+    the current one, and nothing at all (no context-manager churn) in the usual single-device-per-process case."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch._C._cuda_getDevice():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def require_cuda(*tensors):

@@ -27,7 +27,7 @@ class _BiasReluDropout(Function):
         C = h.shape[-1]
         n = h.numel() // C
         seed = _seed() if p > 0 else 0
-        with torch.cuda.device(h.device):
+        with _lib.on_device(h.device):
             rc = _lib.get_lib().ddf_bias_relu_dropout_forward(_lib.ptr(h), _lib.ptr(bias), _lib.ptr(h), n, C,
                                                               float(p), seed, _lib.current_stream())
         _lib.check(rc, "bias_relu_dropout_forward")
@@ -47,7 +47,7 @@ class _BiasReluDropout(Function):
         want_gb = ctx.has_bias and ctx.needs_input_grad[1]
         in_kernel = want_gb and (C // 4) <= 256 and 256 % (C // 4) == 0
         gb = torch.zeros(C, dtype=torch.float32, device=out.device) if in_kernel else None
-        with torch.cuda.device(out.device):
+        with _lib.on_device(out.device):
             rc = _lib.get_lib().ddf_bias_relu_dropout_backward(_lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(gh),
                                                                _lib.ptr(gb), out.numel() // C, C, ctx.p,
                                                                _lib.current_stream())
@@ -60,7 +60,7 @@ class _BiasReluDropout(Function):
 def col_sum(x2d):
     """Column sums of a contiguous fp32 (rows, C) CUDA matrix (ddf_col_sum)."""
     out = torch.empty(x2d.shape[1], dtype=torch.float32, device=x2d.device)
-    with torch.cuda.device(x2d.device):
+    with _lib.on_device(x2d.device):
         rc = _lib.get_lib().ddf_col_sum(_lib.ptr(x2d), _lib.ptr(out), x2d.shape[0], x2d.shape[1], _lib.current_stream())
     _lib.check(rc, "col_sum")
     return out
@@ -86,7 +86,7 @@ def xty(a2d, b2d):
             and a2d.data_ptr() % 16 == 0 and b2d.data_ptr() % 16 == 0
             and _lib.get_lib().ddf_xty_supported(K, M, N)):
         out = torch.empty((M, N), dtype=torch.float32, device=a2d.device)
-        with torch.cuda.device(a2d.device):
+        with _lib.on_device(a2d.device):
             rc = _lib.get_lib().ddf_xty_tf32(_lib.ptr(a2d), _lib.ptr(b2d), _lib.ptr(out), K, M, N, _lib.current_stream())
         _lib.check(rc, "xty_tf32")
         return out
@@ -187,7 +187,7 @@ class _AddDropoutLayerNorm(Function):
         mean = torch.empty(rows, dtype=torch.float32, device=a.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=a.device)
         seed = _seed() if (p > 0 and b is not None) else 0
-        with torch.cuda.device(a.device):
+        with _lib.on_device(a.device):
             rc = _lib.get_lib().ddf_add_dropout_layer_norm_forward(
                 _lib.ptr(a), _lib.ptr(b), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(s), _lib.ptr(y), _lib.ptr(mean),
                 _lib.ptr(rstd), rows, C, float(p), seed, float(eps), _lib.current_stream())
@@ -209,7 +209,7 @@ class _AddDropoutLayerNorm(Function):
         gb = torch.empty_like(s) if (need_b and not share) else None
         gg = torch.zeros(C, dtype=torch.float32, device=s.device)
         gbeta = torch.zeros(C, dtype=torch.float32, device=s.device)
-        with torch.cuda.device(s.device):
+        with _lib.on_device(s.device):
             rc = _lib.get_lib().ddf_add_dropout_layer_norm_backward(
                 _lib.ptr(grad_y), _lib.ptr(s), _lib.ptr(gamma), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(ga),
                 _lib.ptr(gb), _lib.ptr(gg), _lib.ptr(gbeta), rows, C, ctx.p, ctx.seed, _lib.current_stream())
@@ -245,7 +245,7 @@ class _BiGateSum(Function):
         wbv, wav = wb.reshape(-1).contiguous(), wa.reshape(-1).contiguous()
         o1, o2 = torch.empty_like(f1), torch.empty_like(f2)
         gates = torch.empty((rows, 2), dtype=torch.float32, device=f1.device)
-        with torch.cuda.device(f1.device):
+        with _lib.on_device(f1.device):
             rc = _lib.get_lib().ddf_bigate_sum_forward(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(wbv), _lib.ptr(bb),
                                                        _lib.ptr(wav), _lib.ptr(ba), _lib.ptr(o1), _lib.ptr(o2),
                                                        _lib.ptr(gates), rows, C, int(fuse_in), _lib.current_stream())
@@ -275,7 +275,7 @@ class _BiGateSum(Function):
         gbb = new(1) if (need[3] and ctx.has_bias[0] and go1 is not None) else None
         gwa = new(C) if (need[4] and go2 is not None) else None
         gba = new(1) if (need[5] and ctx.has_bias[1] and go2 is not None) else None
-        with torch.cuda.device(f1.device):
+        with _lib.on_device(f1.device):
             rc = _lib.get_lib().ddf_bigate_sum_backward(
                 _lib.ptr(go1), _lib.ptr(go2), _lib.ptr(f1), _lib.ptr(f2), _lib.ptr(gates), _lib.ptr(wbv), _lib.ptr(wav),
                 _lib.ptr(gf1), _lib.ptr(gf2), _lib.ptr(gwb), _lib.ptr(gbb), _lib.ptr(gwa), _lib.ptr(gba), rows, C,
@@ -313,7 +313,7 @@ class _FusedFFN(Function):
         y = torch.empty((T, D), dtype=torch.float32, device=x.device)
         seed = _seed() if p > 0 else 0
         ws = torch.empty(2 * D * F_, dtype=torch.float32, device=x.device)     # re-laid weights (ddf_ffn_workspace_bytes)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             rc = _lib.get_lib().ddf_ffn_forward(_lib.ptr(x2), _lib.ptr(w1c), _lib.ptr(b1), _lib.ptr(w2c), _lib.ptr(b2),
                                                 _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws), T, D, F_, float(p), seed,
                                                 _lib.current_stream())
@@ -340,7 +340,7 @@ class _FusedFFN(Function):
             gh = g2 @ w2                                               # [T, F]
             in_kernel = need[2] and _bias_in_kernel_ok(F_)
             gb1 = torch.zeros(F_, dtype=torch.float32, device=h.device) if in_kernel else None
-            with torch.cuda.device(h.device):
+            with _lib.on_device(h.device):
                 rc = _lib.get_lib().ddf_bias_relu_dropout_backward(_lib.ptr(gh), _lib.ptr(h), _lib.ptr(gh), _lib.ptr(gb1),
                                                                    T, F_, ctx.p, _lib.current_stream())
             _lib.check(rc, "bias_relu_dropout_backward")

@@ -36,7 +36,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     L = spatial_shapes.shape[0]
     Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
     out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with _lib.on_device(value.device):
         rc = _lib.get_lib().ddf_ms_deform_attn_forward(
             _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
             _lib.ptr(sampling_loc), _lib.ptr(attn_weight), _lib.ptr(out), N, S, M, D, L, Lq, P,
@@ -57,7 +57,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty_like(value)  # zeroed inside the library call
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
-    with torch.cuda.device(value.device):
+    with _lib.on_device(value.device):
         rc = _lib.get_lib().ddf_ms_deform_attn_backward(
             _lib.ptr(value), _lib.ptr(spatial_shapes), _lib.ptr(level_start_index),
             _lib.ptr(sampling_loc), _lib.ptr(attn_weight), _lib.ptr(grad_output),
@@ -122,7 +122,7 @@ class TilePlan(object):
         L = _lib.get_lib()
         nbytes = int(L.ddf_msda_plan_bytes(self.N, self.NQ, self.H, self.W))
         self.buf = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=ref.device)
-        with torch.cuda.device(ref.device):
+        with _lib.on_device(ref.device):
             rc = L.ddf_msda_plan(_lib.ptr(self.ref), _lib.ptr(self.qbatch), _lib.ptr(self.buf), self.N, self.NQ, self.Lq,
                                  self.H, self.W, _lib.current_stream())
         _lib.check(rc, "msda_plan")
@@ -131,7 +131,7 @@ class TilePlan(object):
 def msda_tile_forward(value, plan, offsets, logits):
     N, S, M, D = value.shape
     out = torch.empty(tuple(offsets.shape[:2]) + (M * D,), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with _lib.on_device(value.device):
         rc = _lib.get_lib().ddf_msda_tile_forward(
             _lib.ptr(value), _lib.ptr(plan.ref), _lib.ptr(offsets), _lib.ptr(logits), _lib.ptr(plan.buf),
             _lib.ptr(out), N, plan.H, plan.W, M, D, plan.NQ, _lib.current_stream())
@@ -144,7 +144,7 @@ def msda_tile_backward(value, plan, offsets, logits, grad_out):
     grad_value = torch.empty_like(value)   # zeroed inside the library call
     grad_off = torch.empty_like(offsets)
     grad_logit = torch.empty_like(logits)
-    with torch.cuda.device(value.device):
+    with _lib.on_device(value.device):
         rc = _lib.get_lib().ddf_msda_tile_backward(
             _lib.ptr(value), _lib.ptr(plan.ref), _lib.ptr(offsets), _lib.ptr(logits), _lib.ptr(grad_out),
             _lib.ptr(plan.buf), _lib.ptr(grad_value), _lib.ptr(grad_off), _lib.ptr(grad_logit), N, plan.H, plan.W,

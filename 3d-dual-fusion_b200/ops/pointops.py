@@ -25,7 +25,7 @@ class FurthestPointSampling(Function):
         _chk(points_xyz)
         B, N = points_xyz.size()[:2]
         output = torch.empty((B, num_points), dtype=torch.int32, device=points_xyz.device)
-        with torch.cuda.device(points_xyz.device):
+        with _lib.on_device(points_xyz.device):
             rc = _lib.get_lib().ddf_furthest_point_sampling(_lib.ptr(points_xyz.float()), None, _lib.ptr(output),
                                                            B, N, num_points, _lib.current_stream())
         _lib.check(rc, "furthest_point_sampling")
@@ -48,7 +48,7 @@ class BallQuery(Function):
         B, N, _ = xyz.size()
         npoint = center_xyz.size(1)
         idx = torch.zeros((B, npoint, sample_num), dtype=torch.int32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
+        with _lib.on_device(xyz.device):
             rc = _lib.get_lib().ddf_ball_query(_lib.ptr(center_xyz), _lib.ptr(xyz), _lib.ptr(idx), B, N, npoint,
                                               float(min_radius), float(max_radius), sample_num,
                                               _lib.current_stream())
@@ -71,7 +71,7 @@ class GroupingOperation(Function):
         B, nfeatures, nsample = indices.size()
         _, C, N = features.size()
         output = torch.empty((B, C, nfeatures, nsample), dtype=features.dtype, device=features.device)
-        with torch.cuda.device(features.device):
+        with _lib.on_device(features.device):
             rc = _lib.get_lib().ddf_group_points(_lib.ptr(features), _lib.ptr(indices), _lib.ptr(output), B, C, N,
                                                 nfeatures, nsample, _lib.current_stream())
         _lib.check(rc, "group_points")
@@ -84,7 +84,7 @@ class GroupingOperation(Function):
         B, C, npoint, nsample = grad_out.size()
         grad_out = grad_out.contiguous()
         grad_features = torch.empty((B, C, N), dtype=grad_out.dtype, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on_device(grad_out.device):
             rc = _lib.get_lib().ddf_group_points_grad(_lib.ptr(grad_out), _lib.ptr(idx), _lib.ptr(grad_features),
                                                      B, C, N, npoint, nsample, _lib.current_stream())
         _lib.check(rc, "group_points_grad")
@@ -101,7 +101,7 @@ class GatherPoints(Function):
         B, npoint = indices.size()
         _, C, N = features.size()
         output = torch.empty((B, C, npoint), dtype=features.dtype, device=features.device)
-        with torch.cuda.device(features.device):
+        with _lib.on_device(features.device):
             rc = _lib.get_lib().ddf_gather_points(_lib.ptr(features), _lib.ptr(indices), _lib.ptr(output), B, C, N,
                                                  npoint, _lib.current_stream())
         _lib.check(rc, "gather_points")
@@ -115,7 +115,7 @@ class GatherPoints(Function):
         B, npoint = idx.size()
         grad_out = grad_out.contiguous()
         grad_features = torch.empty((B, C, N), dtype=grad_out.dtype, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on_device(grad_out.device):
             rc = _lib.get_lib().ddf_gather_points_grad(_lib.ptr(grad_out), _lib.ptr(idx), _lib.ptr(grad_features),
                                                       B, C, N, npoint, _lib.current_stream())
         _lib.check(rc, "gather_points_grad")
@@ -142,7 +142,7 @@ class ScatterFirst(Function):
         out = features.clone(memory_format=torch.contiguous_format)
         first = torch.empty((B, N), dtype=torch.int32, device=features.device)
         L = _lib.get_lib()
-        with torch.cuda.device(features.device):
+        with _lib.on_device(features.device):
             rc = L.ddf_first_occurrence(_lib.ptr(idx), _lib.ptr(first), B, N, E, _lib.current_stream())
             _lib.check(rc, "first_occurrence")
             rc = L.ddf_scatter_first(_lib.ptr(feats), _lib.ptr(first), _lib.ptr(out), B, C, N, E, _lib.current_stream())
@@ -159,7 +159,7 @@ class ScatterFirst(Function):
         grad_out = grad_out.contiguous()
         g_feats = torch.empty((B, C, E), dtype=grad_out.dtype, device=grad_out.device)
         g_features = torch.empty_like(grad_out)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on_device(grad_out.device):
             rc = _lib.get_lib().ddf_scatter_first_grad(_lib.ptr(grad_out), _lib.ptr(first), _lib.ptr(g_feats),
                                                        _lib.ptr(g_features), B, C, N, E, _lib.current_stream())
         _lib.check(rc, "scatter_first_grad")
@@ -176,7 +176,7 @@ def first_occurrence(idx, N):
     idx = idx.contiguous()
     B, E = idx.shape[0], idx.shape[1] * idx.shape[2]
     first = torch.empty((B, N), dtype=torch.int32, device=idx.device)
-    with torch.cuda.device(idx.device):
+    with _lib.on_device(idx.device):
         rc = _lib.get_lib().ddf_first_occurrence(_lib.ptr(idx), _lib.ptr(first), B, N, E, _lib.current_stream())
     _lib.check(rc, "first_occurrence")
     return first
@@ -199,7 +199,7 @@ class LocalAttention(Function):
         T, C3 = qkv.shape
         C = C3 // 3
         out = torch.empty((T, C), dtype=qkv.dtype, device=qkv.device)
-        with torch.cuda.device(qkv.device):
+        with _lib.on_device(qkv.device):
             rc = _lib.get_lib().ddf_local_attn_forward(_lib.ptr(qkv), _lib.ptr(out), T // group_size, heads, C // heads,
                                                        group_size, _lib.current_stream())
         _lib.check(rc, "local_attn_forward")
@@ -215,7 +215,7 @@ class LocalAttention(Function):
         grad_out = grad_out.contiguous()
         T, C3 = qkv.shape
         g = torch.empty_like(qkv)
-        with torch.cuda.device(qkv.device):
+        with _lib.on_device(qkv.device):
             rc = _lib.get_lib().ddf_local_attn_backward(_lib.ptr(qkv), _lib.ptr(grad_out), _lib.ptr(g), T // group_size,
                                                         heads, C3 // 3 // heads, group_size, _lib.current_stream())
         _lib.check(rc, "local_attn_backward")

@@ -17,7 +17,7 @@ _workspaces = {}
 
 def _workspace(device, C):
     """Zero-initialised once per (device, stream, C); the kernels leave it reusable."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, C)
+    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index), C)
     ws = _workspaces.get(key)
     if ws is None:
         nbytes = int(_lib.get_lib().ddf_sparse_bn_workspace_bytes(C))
@@ -46,7 +46,7 @@ class _BatchNormAct(Function):
             invstd = torch.empty(C, dtype=torch.float32, device=x.device)
         else:
             mean = invstd = None
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             rc = _lib.get_lib().ddf_sparse_bn_forward(
                 _lib.ptr(x), _lib.ptr(residual), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(running_mean),
                 _lib.ptr(running_var), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(invstd), n, C, int(training),
@@ -76,7 +76,7 @@ class _BatchNormAct(Function):
         gw = torch.empty(C, dtype=torch.float32, device=x.device) if (need_w and weight is not None) else None
         gb = torch.empty(C, dtype=torch.float32, device=x.device) if need_b else None
         ws = _workspace(x.device, C)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             rc = _lib.get_lib().ddf_sparse_bn_backward(
                 _lib.ptr(grad_y), _lib.ptr(y), _lib.ptr(x), _lib.ptr(weight), _lib.ptr(mean), _lib.ptr(invstd),
                 _lib.ptr(gx), _lib.ptr(gres_out), _lib.ptr(gw), _lib.ptr(gb), n, C, int(ctx.training),

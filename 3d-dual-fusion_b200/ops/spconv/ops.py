@@ -106,7 +106,7 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize=3, stride=1, paddin
     num = None if lazy else torch.empty((kvol,), dtype=torch.int32, device=dev)
     scatter_t = torch.empty((n, kvol), dtype=torch.int32, device=dev) if with_tables else None
     stream = _lib.current_stream()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         if subm:
             gather_t = torch.empty((n, kvol), dtype=torch.int32, device=dev) if with_tables else None
             rc = L.ddf_subm_indice_pairs(_lib.ptr(indices), n, batch_size, geo[1], geo[2], geo[5],
@@ -159,7 +159,7 @@ def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_o
     kvol = indice_pairs.shape[0]
     out = torch.empty((num_activate_out, cout), dtype=features.dtype, device=features.device)
     table_ws = torch.empty((max(num_activate_out, 1), kvol), dtype=torch.int32, device=features.device)
-    with torch.cuda.device(features.device):
+    with _lib.on_device(features.device):
         rc = _lib.get_lib().ddf_indice_conv(
             _lib.ptr(features), _lib.ptr(filters), _lib.ptr(indice_pairs), _lib.ptr(indice_pair_num),
             indice_pairs.shape[2], _lib.ptr(out), num_activate_out, kvol, cin, cout, int(inverse),
@@ -180,7 +180,7 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     gw = torch.empty_like(filters)
     table_ws = torch.empty((max(n_in, 1), kvol), dtype=torch.int32, device=features.device)
     wt_ws = torch.empty_like(filters)
-    with torch.cuda.device(features.device):
+    with _lib.on_device(features.device):
         rc = _lib.get_lib().ddf_indice_conv_backward(
             _lib.ptr(features), _lib.ptr(filters), _lib.ptr(out_bp), _lib.ptr(indice_pairs),
             _lib.ptr(indice_pair_num), indice_pairs.shape[2], _lib.ptr(gin), _lib.ptr(gw), n_in, kvol,
@@ -209,7 +209,7 @@ def round_tf32(x):
     """Copy of ``x`` rounded to the nearest tf32 (operand preparation for the tensor-core kernels)."""
     x = x.contiguous()
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         rc = _lib.get_lib().ddf_round_tf32(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.current_stream())
     _lib.check(rc, "round_tf32")
     return out
@@ -222,7 +222,7 @@ def split_bf16x3(x, want_rounded=False):
     x = x.contiguous()
     split = torch.empty_like(x)
     rounded = torch.empty_like(x) if want_rounded else None
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         rc = _lib.get_lib().ddf_split_bf16x3(_lib.ptr(x), _lib.ptr(split), _lib.ptr(rounded), x.shape[0], x.shape[1],
                                              _lib.current_stream())
     _lib.check(rc, "split_bf16x3")
@@ -235,7 +235,7 @@ def sparse_conv_forward(features, filters, gather_table, bias, n_out, operand_fo
     kvol = gather_table.shape[1] if gather_table.numel() else filters.numel() // (cin * cout)
     out = torch.empty((n_out, cout), dtype=features.dtype, device=features.device)
     wt_ws = torch.empty_like(filters)
-    with torch.cuda.device(features.device):
+    with _lib.on_device(features.device):
         rc = _lib.get_lib().ddf_sparse_conv_forward(
             _lib.ptr(features), _lib.ptr(filters), _lib.ptr(gather_table), _lib.ptr(bias), _lib.ptr(out),
             _lib.ptr(wt_ws), n_out, features.shape[0], kvol, cin, cout, int(operand_format),
@@ -249,7 +249,7 @@ def sparse_conv_dgrad(filters, grad_out, scatter_table, n_in, operand_format=0):
     kvol = filters.numel() // (cin * cout)
     gin = torch.empty((n_in, cin), dtype=grad_out.dtype, device=grad_out.device)
     wt_ws = torch.empty_like(filters)
-    with torch.cuda.device(grad_out.device):
+    with _lib.on_device(grad_out.device):
         rc = _lib.get_lib().ddf_sparse_conv_dgrad(_lib.ptr(grad_out), _lib.ptr(filters),
                                                   _lib.ptr(scatter_table), _lib.ptr(gin), _lib.ptr(wt_ws),
                                                   n_in, grad_out.shape[0], kvol, cin, cout,
@@ -262,7 +262,7 @@ def sparse_conv_wgrad(features, filters, grad_out, indice_pairs, indice_pair_num
     cin, cout = filters.shape[-2], filters.shape[-1]
     kvol = indice_pairs.shape[0]
     gw = torch.empty_like(filters)
-    with torch.cuda.device(features.device):
+    with _lib.on_device(features.device):
         rc = _lib.get_lib().ddf_sparse_conv_wgrad(_lib.ptr(features), _lib.ptr(grad_out),
                                                   _lib.ptr(indice_pairs), _lib.ptr(indice_pair_num),
                                                   indice_pairs.shape[2], _lib.ptr(gw), kvol, cin, cout, 0,
@@ -276,7 +276,7 @@ def sparse_conv_wgrad_table(features, filters, grad_out, gather_table):
     cin, cout = filters.shape[-2], filters.shape[-1]
     kvol = gather_table.shape[1]
     gw = torch.empty_like(filters)
-    with torch.cuda.device(features.device):
+    with _lib.on_device(features.device):
         rc = _lib.get_lib().ddf_sparse_conv_wgrad_table(_lib.ptr(features), _lib.ptr(grad_out), _lib.ptr(gather_table),
                                                         _lib.ptr(gw), grad_out.shape[0], features.shape[0], kvol, cin,
                                                         cout, _lib.current_stream())

@@ -20,7 +20,7 @@ class _ToDense(Function):
         n, C = features.shape
         D, H, W = [int(s) for s in spatial_shape]
         out = torch.empty((batch_size, C, D, H, W), dtype=features.dtype, device=features.device)
-        with torch.cuda.device(features.device):
+        with _lib.on_device(features.device):
             rc = _lib.get_lib().ddf_sparse_to_dense(_lib.ptr(features), _lib.ptr(indices), _lib.ptr(out),
                                                     n, C, batch_size, D, H, W, _lib.current_stream())
         _lib.check(rc, "sparse_to_dense")
@@ -34,7 +34,7 @@ class _ToDense(Function):
         n, C, B, D, H, W = ctx.dims
         grad_out = grad_out.contiguous()
         gfeat = torch.empty((n, C), dtype=grad_out.dtype, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on_device(grad_out.device):
             rc = _lib.get_lib().ddf_dense_to_sparse(_lib.ptr(grad_out), _lib.ptr(indices), _lib.ptr(gfeat),
                                                     n, C, B, D, H, W, _lib.current_stream())
         _lib.check(rc, "dense_to_sparse")
@@ -55,7 +55,7 @@ class _ToBevNhwcBf16(Function):
         D, H, W = [int(s) for s in spatial_shape]
         out = torch.empty((batch_size, C * D, H, W), dtype=torch.bfloat16, device=features.device,
                           memory_format=torch.channels_last)
-        with torch.cuda.device(features.device):
+        with _lib.on_device(features.device):
             rc = _lib.get_lib().ddf_sparse_to_bev_nhwc_bf16(_lib.ptr(features), _lib.ptr(indices), _lib.ptr(out),
                                                             n, C, batch_size, D, H, W, _lib.current_stream())
         _lib.check(rc, "sparse_to_bev_nhwc_bf16")
@@ -69,7 +69,7 @@ class _ToBevNhwcBf16(Function):
         n, C, B, D, H, W = ctx.dims
         grad_out = grad_out.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         gfeat = torch.empty((n, C), dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on_device(grad_out.device):
             rc = _lib.get_lib().ddf_bev_nhwc_bf16_to_sparse(_lib.ptr(grad_out), _lib.ptr(indices), _lib.ptr(gfeat),
                                                             n, C, B, D, H, W, _lib.current_stream())
         _lib.check(rc, "bev_nhwc_bf16_to_sparse")

@@ -33,7 +33,7 @@ def dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3):
     points = _check_points(points)
     if NDim != 3:
         raise RuntimeError("only NDim=3 is supported")
-    with torch.cuda.device(points.device):
+    with _lib.on_device(points.device):
         rc = _lib.get_lib().ddf_dynamic_voxelize(
             _lib.ptr(points), _lib.ptr(coors), _f32_array(voxel_size, 3), _f32_array(coors_range, 6),
             points.size(0), points.size(1), _lib.current_stream())
@@ -52,7 +52,7 @@ def hard_voxelize_device(points, voxels, coors, num_points_per_voxel, voxel_size
         raise RuntimeError("hard_voxelize: bad sizes")
     ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=points.device)
     voxel_num = torch.empty(1, dtype=torch.int32, device=points.device)
-    with torch.cuda.device(points.device):
+    with _lib.on_device(points.device):
         rc = L.ddf_hard_voxelize(
             _lib.ptr(points), _lib.ptr(voxels), _lib.ptr(coors), _lib.ptr(num_points_per_voxel),
             _lib.ptr(voxel_num), _f32_array(voxel_size, 3), _f32_array(coors_range, 6), n, f,
@@ -87,7 +87,7 @@ def hard_voxelize_mean(points, voxel_size, coors_range, max_points, max_voxels, 
         raise RuntimeError("hard_voxelize_mean: bad sizes")
     ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=points.device)
     voxel_num = torch.empty(1, dtype=torch.int32, device=points.device)
-    with torch.cuda.device(points.device):
+    with _lib.on_device(points.device):
         rc = L.ddf_hard_voxelize_mean(
             _lib.ptr(points), _lib.ptr(mean), _lib.ptr(coors), _lib.ptr(num), _lib.ptr(voxel_num),
             _f32_array(voxel_size, 3), _f32_array(coors_range, 6), n, f, int(num_features), int(max_points), cap,
