@@ -14,6 +14,8 @@
 // fixed-order fold of per-CTA partials).
 // Algorithmic bytes: forward 4*N*C*(2 reads + [1 residual read] + 1 write); backward
 // 4*N*C*(3 reads + 3 reads + 1-2 writes).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -186,6 +188,85 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
   *reinterpret_cast<float4*>(y + i * 4) = o;
 }
 
+// bn_apply for layers whose output feeds a bf16x3 tcgen05 conv: the same pass also writes the conv's operand format
+// ([32 x bf16 hi | 32 x bf16 lo] per 32 channels, csrc/sparse_conv.cu ddf_split_bf16x3) and the tf32-rounded copy the
+// wgrad kernels read - the separate split pass re-read y for every conv input (31 launches, 1.2 ms of a step).
+// One thread = 8 consecutive channels (one 16-byte store of hi, one of lo).  C % 32 == 0.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(kThreads)
+bn_apply_split_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ mean,
+                      const float* __restrict__ invstd, const float* __restrict__ w, const float* __restrict__ b,
+                      float* __restrict__ y, uint8_t* __restrict__ split, float* __restrict__ rounded, long long n8,
+                      int C, int relu, int stat_is_var, float eps) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n8) return;
+  const long long e = t * 8;
+  const long long row = e / C;
+  const int c = (int)(e % C);
+  float v[8], o[8];
+  *reinterpret_cast<float4*>(v) = ldg4(x + e);
+  *reinterpret_cast<float4*>(v + 4) = ldg4(x + e + 4);
+  float m[8], s[8], bb[8];
+  *reinterpret_cast<float4*>(m) = ldg4(mean + c);
+  *reinterpret_cast<float4*>(m + 4) = ldg4(mean + c + 4);
+  *reinterpret_cast<float4*>(s) = ldg4(invstd + c);
+  *reinterpret_cast<float4*>(s + 4) = ldg4(invstd + c + 4);
+  if (stat_is_var) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 1.f / sqrtf(s[i] + eps);
+  }
+  if (w) {
+    float g[8];
+    *reinterpret_cast<float4*>(g) = ldg4(w + c);
+    *reinterpret_cast<float4*>(g + 4) = ldg4(w + c + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] *= g[i];
+  }
+  if (b) {
+    *reinterpret_cast<float4*>(bb) = ldg4(b + c);
+    *reinterpret_cast<float4*>(bb + 4) = ldg4(b + c + 4);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bb[i] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaf(v[i] - m[i], s[i], bb[i]);
+  if (res) {
+    float r[8];
+    *reinterpret_cast<float4*>(r) = ldg4(res + e);
+    *reinterpret_cast<float4*>(r + 4) = ldg4(res + e + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += r[i];
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+  }
+  *reinterpret_cast<float4*>(y + e) = *reinterpret_cast<float4*>(o);
+  *reinterpret_cast<float4*>(y + e + 4) = *reinterpret_cast<float4*>(o + 4);
+  unsigned short hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(o[i]);
+    const __nv_bfloat16 l = __float2bfloat16_rn(o[i] - __bfloat162float(h));
+    hi[i] = __bfloat16_as_ushort(h);
+    lo[i] = __bfloat16_as_ushort(l);
+  }
+  uint8_t* dst = split + row * C * 4 + (c >> 5) * 128 + (c & 31) * 2;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(dst + 64) = *reinterpret_cast<const uint4*>(lo);
+  if (rounded) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = tf32_rn(o[i]);
+    *reinterpret_cast<float4*>(rounded + e) = *reinterpret_cast<float4*>(o);
+    *reinterpret_cast<float4*>(rounded + e + 4) = *reinterpret_cast<float4*>(o + 4);
+  }
+}
+
 // sums over rows of g and g * xhat, g = gy masked by (y > 0) when relu.
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
@@ -297,11 +378,37 @@ static inline unsigned* ws_counter(void* ws, int64_t C) {
   return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (int64_t)kMaxGrid * 2 * C * 8 + 2 * C * 4 + 128);
 }
 
+static int bn_forward_impl(const float* x, const float* residual, const float* weight, const float* bias,
+                           float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd,
+                           void* split, float* rounded, int64_t n, int64_t C, int training, float momentum, float eps,
+                           int relu, void* workspace, void* stream_);
+
 extern "C" int ddf_sparse_bn_forward(const float* x, const float* residual, const float* weight,
                                      const float* bias, float* running_mean, float* running_var,
                                      float* y, float* save_mean, float* save_invstd, int64_t n,
                                      int64_t C, int training, float momentum, float eps, int relu,
                                      void* workspace, void* stream_) {
+  return bn_forward_impl(x, residual, weight, bias, running_mean, running_var, y, save_mean, save_invstd, nullptr, nullptr,
+                         n, C, training, momentum, eps, relu, workspace, stream_);
+}
+
+// As ddf_sparse_bn_forward; additionally writes y in the bf16x3 operand layout of the tcgen05 convs (split, same bytes
+// as y; C % 32 == 0) and, when rounded != NULL, the tf32-rounded copy of y the wgrad kernels read.
+extern "C" int ddf_sparse_bn_forward_split(const float* x, const float* residual, const float* weight,
+                                           const float* bias, float* running_mean, float* running_var, float* y,
+                                           float* save_mean, float* save_invstd, void* split, float* rounded,
+                                           int64_t n, int64_t C, int training, float momentum, float eps, int relu,
+                                           void* workspace, void* stream_) {
+  DDF_CHECK_ARG(split != nullptr && C % 32 == 0, "sparse_bn_forward_split: needs the split buffer and C %% 32 == 0");
+  DDF_CHECK_ARG(aligned16(split) && aligned16(rounded), "sparse_bn_forward_split: misaligned pointer");
+  return bn_forward_impl(x, residual, weight, bias, running_mean, running_var, y, save_mean, save_invstd, split, rounded, n,
+                         C, training, momentum, eps, relu, workspace, stream_);
+}
+
+static int bn_forward_impl(const float* x, const float* residual, const float* weight, const float* bias,
+                           float* running_mean, float* running_var, float* y, float* save_mean, float* save_invstd,
+                           void* split, float* rounded, int64_t n, int64_t C, int training, float momentum, float eps,
+                           int relu, void* workspace, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DDF_CHECK_ARG(n >= 0 && pow2(C) && C >= 4 && C <= 1024,
                 "sparse_bn_forward: C must be a power of two in [4, 1024], got n=%lld C=%lld",
@@ -318,12 +425,22 @@ extern "C" int ddf_sparse_bn_forward(const float* x, const float* residual, cons
     DDF_LAUNCH(bn_stats_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, x, (int)n,
                (int)C, (double*)workspace, ws_counter(workspace, C), save_mean, save_invstd,
                running_mean, running_var, momentum, eps);
-    DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
-               (const float*)save_mean, (const float*)save_invstd, weight, bias, y, n4, (int)C, relu, 0, eps);
+    if (split)
+      DDF_LAUNCH(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
+                 (const float*)save_mean, (const float*)save_invstd, weight, bias, y, reinterpret_cast<uint8_t*>(split),
+                 rounded, n4 / 2, (int)C, relu, 0, eps);
+    else
+      DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
+                 (const float*)save_mean, (const float*)save_invstd, weight, bias, y, n4, (int)C, relu, 0, eps);
   } else {
     DDF_CHECK_ARG(running_mean && running_var, "sparse_bn_forward: eval mode needs running statistics");
-    DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
-               (const float*)running_mean, (const float*)running_var, weight, bias, y, n4, (int)C, relu, 1, eps);
+    if (split)
+      DDF_LAUNCH(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
+                 (const float*)running_mean, (const float*)running_var, weight, bias, y,
+                 reinterpret_cast<uint8_t*>(split), rounded, n4 / 2, (int)C, relu, 1, eps);
+    else
+      DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
+                 (const float*)running_mean, (const float*)running_var, weight, bias, y, n4, (int)C, relu, 1, eps);
   }
   DDF_LAUNCH_CHECK();
   return DDF_OK;

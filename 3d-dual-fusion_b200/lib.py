@@ -63,6 +63,7 @@ _SIGNATURES = {
     "ddf_bev_nhwc_bf16_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_sparse_bn_workspace_bytes": [c_i64],
     "ddf_sparse_bn_forward": [c_ptr] * 9 + [c_i64, c_i64, c_int, c_f32, c_f32, c_int, c_ptr, c_ptr],
+    "ddf_sparse_bn_forward_split": [c_ptr] * 11 + [c_i64, c_i64, c_int, c_f32, c_f32, c_int, c_ptr, c_ptr],
     "ddf_sparse_bn_backward": [c_ptr] * 10 + [c_i64, c_i64, c_int, c_int, c_ptr, c_ptr],
     "ddf_bias_relu_dropout_forward": [c_ptr] * 3 + [c_i64, c_i64, c_f32, ctypes.c_uint64, c_ptr],
     "ddf_bias_relu_dropout_backward": [c_ptr] * 4 + [c_i64, c_i64, c_f32, c_ptr],

@@ -88,8 +88,14 @@ class TableConvFunction(Function):
         fmt = 0
         if features.shape[0]:
             if mode & 16:
-                # bf16x3 forward: hi/lo split operands; the same pass writes the tf32-rounded copy wgrad reads
-                features, rounded = ops.split_bf16x3(features, want_rounded=bool(mode & 12))
+                # bf16x3 forward: hi/lo split operands; the same pass writes the tf32-rounded copy wgrad reads.  A
+                # BatchNorm that produced these features has written both already (ops/sparse_norm.py)
+                pre = getattr(features, "_ddf_operands", None) if not pad else None
+                want_rounded = bool(mode & 12) and ctx.needs_input_grad[1]
+                if pre is not None and pre[0].shape == features.shape and (pre[1] is not None or not want_rounded):
+                    features, rounded = pre[0], (pre[1] if want_rounded else None)
+                else:
+                    features, rounded = ops.split_bf16x3(features, want_rounded=bool(mode & 12))
                 saved = rounded if rounded is not None else saved
                 fmt = 1
             elif mode & 5:

@@ -215,6 +215,11 @@ def round_tf32(x):
     return out
 
 
+def bf16x3_on(C):
+    """True when a SubM 3x3x3 conv of C -> C channels runs on the bf16x3 tcgen05 kernels (mode bit 16)."""
+    return bool(tc_mode(27, C, C) & 16)
+
+
 def split_bf16x3(x, want_rounded=False):
     """``x`` fp32 [rows, C] (C % 32 == 0) -> (split, rounded): ``split`` holds every row as blocks of
     [32 x bf16 hi | 32 x bf16 lo] (same bytes as fp32; carried in a float32 tensor of x's shape), the operand

@@ -342,6 +342,13 @@ int ddf_sparse_bn_forward(const float* x, const float* residual, const float* we
                           float* running_mean, float* running_var, float* y, float* save_mean,
                           float* save_invstd, int64_t n, int64_t C, int training, float momentum,
                           float eps, int relu, void* workspace, void* stream);
+/* As ddf_sparse_bn_forward; the same pass also writes y in the bf16x3 operand layout of the tcgen05 convs (split: same
+ * bytes as y, [32 x bf16 hi | 32 x bf16 lo] per 32 channels as ddf_split_bf16x3; C % 32 == 0) and, when rounded != NULL,
+ * the tf32-rounded copy of y the wgrad kernels read. */
+int ddf_sparse_bn_forward_split(const float* x, const float* residual, const float* weight, const float* bias,
+                                float* running_mean, float* running_var, float* y, float* save_mean,
+                                float* save_invstd, void* split, float* rounded, int64_t n, int64_t C, int training,
+                                float momentum, float eps, int relu, void* workspace, void* stream);
 /* mean / invstd: what forward normalised with (saved batch statistics in training; running_mean and
  * 1/sqrt(running_var + eps) in eval).  y is read only for the ReLU mask.  grad_x / grad_residual /
  * grad_weight / grad_bias may be NULL. */

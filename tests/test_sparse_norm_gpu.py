@@ -90,3 +90,44 @@ def test_unsupported_width_uses_library_modules_and_cpu_is_refused():
     assert y.shape == x.shape and float(y.min()) >= 0
     with pytest.raises(RuntimeError):
         batch_norm_act(nn.BatchNorm1d(16), torch.randn(8, 16), None, True)
+
+
+@pytest.mark.parametrize("C,with_res,relu", [(32, False, True), (64, True, True), (128, False, False)])
+def test_bn_forward_split_writes_conv_operands(C, with_res, relu):
+    """ddf_sparse_bn_forward_split: y is unchanged, the operand copies equal ddf_split_bf16x3(y) bit for bit, the
+    conv Function picks them up (same conv output as from the separate split pass) and backward is untouched."""
+    import ddf_b200.ops.spconv as sp
+    from ddf_b200.ops import sparse_norm
+    from ddf_b200.ops.spconv import ops, functional
+    from ddf_b200 import lib as _lib
+    torch.manual_seed(C)
+    n = 20011
+    bn = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    x = torch.randn(n, C, device="cuda", requires_grad=True)
+    res = torch.randn(n, C, device="cuda") if with_res else None
+    prev = _lib.get_lib().ddf_set_tensor_cores(4)
+    try:
+        y = sparse_norm.batch_norm_act(bn, x, res, relu)
+        assert hasattr(y, "_ddf_operands")
+        split, rounded = y._ddf_operands
+        ref_split, ref_rounded = ops.split_bf16x3(y.detach(), want_rounded=True)
+        assert torch.equal(split.view(torch.int32), ref_split.view(torch.int32))
+        assert torch.equal(rounded, ref_rounded)
+        _lib.get_lib().ddf_set_tensor_cores(0)
+        bn2 = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).cuda().train()
+        bn2.load_state_dict({k: v.clone() for k, v in bn.state_dict().items() if k != "num_batches_tracked"}, strict=False)
+        with torch.no_grad():
+            bn2.running_mean.zero_(); bn2.running_var.fill_(1.0)
+        x2 = x.detach().clone().requires_grad_()
+        y2 = sparse_norm.batch_norm_act(bn2, x2, res, relu)
+        assert not hasattr(y2, "_ddf_operands")
+        assert torch.equal(y.detach(), y2.detach())
+        go = torch.randn_like(y)
+        y.backward(go)
+        y2.backward(go)
+        assert torch.equal(x.grad, x2.grad)
+    finally:
+        _lib.get_lib().ddf_set_tensor_cores(prev)
