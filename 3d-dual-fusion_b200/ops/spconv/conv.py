@@ -41,12 +41,23 @@ class _IndiceTuple(object):
         return 5
 
 
+def conv1x1_only(kernel_size, ndim):
+    ks = list(kernel_size) if isinstance(kernel_size, (list, tuple)) else [kernel_size] * ndim
+    return all(k == 1 for k in ks)
+
+
 class SparseConvolution(SparseModule):
     def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1,
                  groups=1, bias=True, subm=False, output_padding=0, transposed=False, inverse=False,
                  indice_key=None, fused_bn=False):
         super(SparseConvolution, self).__init__()
         assert groups == 1
+        # the names of the reference's 2-D / 4-D / transposed layers resolve (configs that merely import them keep
+        # loading), but only what the 3D-DF hot path uses is built: fail at construction, not at the first forward
+        if ndim != 3 and not (conv1x1_only(kernel_size, ndim)):
+            raise NotImplementedError("%d-D sparse convolutions are not part of the 3D-DF hot path (3-D only)" % ndim)
+        if transposed:
+            raise NotImplementedError("transposed sparse convolutions are not part of the 3D-DF hot path")
         as_list = lambda v: list(v) if isinstance(v, (list, tuple)) else [v] * ndim
         kernel_size, stride, padding = as_list(kernel_size), as_list(stride), as_list(padding)
         dilation, output_padding = as_list(dilation), as_list(output_padding)
