@@ -264,9 +264,14 @@ class DeformableTransformerACTR(nn.Module):
         src_flatten = torch.cat(src_flatten, 1) if len(src_flatten) > 1 else src_flatten[0].contiguous()
         self.encoder.spatial_hw = spatial_shapes[0] if len(spatial_shapes) == 1 else None   # python ints: no sync
         device = src_flatten.device
-        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=device)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)),
-                                       spatial_shapes.prod(1).cumsum(0)[:-1]))
+        key = (tuple(spatial_shapes), device)
+        cached = getattr(self, "_shape_cache", None)
+        if cached is None or cached[0] != key:
+            # level shapes / start offsets on the device: the same every step, so built once (no per-forward pageable copy)
+            ss = torch.as_tensor(spatial_shapes, dtype=torch.long, device=device)
+            lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+            cached = self._shape_cache = (key, ss, lsi)
+        spatial_shapes, level_start_index = cached[1], cached[2]
         if masks is not None:
             valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
             mask_flatten = torch.cat(mask_flatten, 1)

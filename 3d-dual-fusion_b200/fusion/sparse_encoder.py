@@ -54,10 +54,15 @@ class SparseEncoderFusion(nn.Module):
         (sparse_encoder.py:309-319; same fp32 expression order)."""
         ratio = self.sparse_shape[1] / x.spatial_shape[1]
         dev = x.indices.device
-        scale = torch.tensor((list(self.voxel_size) + [1])[::-1], device=dev)
+        consts = getattr(self, "_coor2pts_consts", None)
+        if consts is None or consts[0].device != dev:
+            # two configuration constants: made once per device, not by a pageable host->device copy in every forward
+            consts = self._coor2pts_consts = (torch.tensor((list(self.voxel_size) + [1])[::-1], device=dev),
+                                              torch.tensor(list(self.point_cloud_range[:3])[::-1], device=dev))
+        scale, origin = consts
         pts = (x.indices.to(torch.float) + pad) * scale * ratio
         pts[:, 0] = pts[:, 0] / ratio - pad
-        pts[:, 1:] += torch.tensor(list(self.point_cloud_range[:3])[::-1], device=dev)
+        pts[:, 1:] += origin
         pts[:, 1:] = pts[:, [3, 2, 1]]
         # rows are grouped by sample already (voxelization order at stride 1, sorted flat index after
         # a strided conv), so per-sample lists are contiguous slices: one count read, no masks

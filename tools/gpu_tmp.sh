@@ -1,4 +1,2 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 600 python bench.py --config tf --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_tf.err | tee gpurun_out/bench_tf.json | python tools/print_bench.py
-timeout 600 python bench.py --config kitti --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_kitti.err | tee gpurun_out/bench_kitti.json | python tools/print_bench.py
+timeout 600 python tools/gap_report.py --config tf 2>&1 | grep -v Warning | tail -45
