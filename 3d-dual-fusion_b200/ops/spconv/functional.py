@@ -133,8 +133,9 @@ class TableConvFunction(Function):
                 gin = ops.sparse_conv_dgrad(filters, grad_output if ctx.mode & 2 else grad_exact, rb.scatter_table,
                                             features.shape[0])
         if ctx.needs_input_grad[1]:
-            if ctx.mode & 8 and getattr(rb, "subm", False) and grad_output.shape[0]:
-                # dense SubM layers: walk the output rows once through the gather table
+            if ctx.mode & 8 and rb.gather_table is not None and grad_output.shape[0]:
+                # Cin == Cout layers (SubM or not: the gather table of a strided / (3,1,1) conv is the same object):
+                # walk the output rows once through the gather table
                 gw = ops.sparse_conv_wgrad_table(features, filters, grad_output, rb.gather_table)
             else:
                 gw = ops.sparse_conv_wgrad(features, filters, grad_output, rb.indice_pairs, rb.indice_pair_num)

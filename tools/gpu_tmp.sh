@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 600 python tools/gap_report.py --config tf 2>&1 | grep -v Warning | tail -45
+mkdir -p gpurun_out
+for i in 1 2 3; do timeout 600 python bench.py --config tf --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_tf.err | tee gpurun_out/bench_tf.json | python tools/print_bench.py; done
