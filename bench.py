@@ -44,6 +44,9 @@ def parse():
                          "with the camera branch on the device; cp / cp_pfatv2 = "
                          "configs[1] (CenterPoint hybrid+IFAT / its ACTRv2 variant); kitti = configs[3]; dense200k = configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", action="store_true",
+                    help="N > 1: average gradients with torch's DistributedDataParallel wrapper instead of "
+                         "ddf_b200.data_parallel.GradientExchange (one flat all-reduce per step)")
     ap.add_argument("--fp32-gemm", action="store_true",
                     help="keep the library GEMMs (nn.Linear / 1x1 conv) in full fp32 instead of tf32")
     return ap.parse_args()
@@ -570,8 +573,14 @@ def run_ours(args):
             return wl.forward(self.model, t, static)
 
     net = StepModule()
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
+    exchange = None
+    if world > 1 and args.ddp:
+        # the generic wrapper, as the reference launches it (mmdet3d/apis/train.py:105: broadcast_buffers=False)
+        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], broadcast_buffers=False)
+    elif world > 1:
+        from ddf_b200.data_parallel import GradientExchange
+        GradientExchange.broadcast_initial_state(model)
+        exchange = GradientExchange(model.parameters())
     # same optimizer as the reference config (AdamW lr 1e-4 wd 0.01), PyTorch's single-kernel variant
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.01, fused=True)
 
@@ -588,6 +597,8 @@ def run_ours(args):
         loss = out.square().mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if exchange is not None:
+            exchange.exchange()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
         opt.step()
         return loss

@@ -49,18 +49,34 @@ def sample(rank):
     return [torch.from_numpy(pts)], feats, [meta]
 
 
-def worker(rank, world, port, out_dir):
+def worker(rank, world, port, out_dir, flat=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import cpu_path
     torch.set_num_threads(2)
     model, frozen = small_model()
-    net = torch.nn.parallel.DistributedDataParallel(model)
+    exchange = None
+    if flat:
+        # bench.py's default N > 1 path: plain module + one flat all-reduce after backward
+        from ddf_b200.data_parallel import GradientExchange
+        if rank != 0:
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.add_(1.0)                     # the broadcast must undo this
+        GradientExchange.broadcast_initial_state(model)
+        exchange = GradientExchange(model.parameters())
+        net = model
+    else:
+        net = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=False)
     pts, feats, metas = sample(rank)
     with cpu_path.reference_cpu_ops():
         out = net(pts, [feats], metas)
         loss = out.square().mean()
         loss.backward()
+    if exchange is not None:
+        exchange.exchange()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(exchange.params, exchange.views))
+        exchange.exchange()                         # gradients already in the flat buffer: no copy, averages again (no-op on equal values)
     grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
     assert not (set(grads) & frozen)
     torch.save(dict(grads=grads, loss=float(loss.detach())), os.path.join(out_dir, "rank%d.pt" % rank))
@@ -68,9 +84,10 @@ def worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_data_parallel_step(tmp_path):
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("flat", [False, True], ids=["ddp_wrapper", "gradient_exchange"])
+def test_two_rank_data_parallel_step(tmp_path, flat):
+    port = 29500 + (os.getpid() + 7 * flat) % 2000
+    mp.spawn(worker, args=(2, port, str(tmp_path), flat), nprocs=2, join=True)
     r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
     r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
     assert r0["loss"] != r1["loss"]                      # different samples per rank (weak scaling)
