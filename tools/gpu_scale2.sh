@@ -8,4 +8,4 @@ python -c "
 import json; d=json.load(open('gpurun_out/bench_${n}gpu$1.json')); print('rank ms dev', [round(x,2) for x in d['rank_ms_per_step']['device_resident']]); print('rank ms e2e', [round(x,2) for x in d['rank_ms_per_step']['e2e']])"
 }
 run "" ""
-[ -n "$DDP" ] && run _ddp --ddp
+if [ -n "$DDP" ]; then run _ddp --ddp; fi
