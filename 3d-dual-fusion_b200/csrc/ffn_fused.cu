@@ -442,6 +442,16 @@ extern "C" int ddf_ffn_supported(int64_t T, int64_t D, int64_t F) {
 // counter hash of (seed, element index); ddf_bias_relu_dropout_backward applies to h unchanged (it reads h != 0).
 extern "C" int64_t ddf_ffn_workspace_bytes(int64_t D, int64_t F) { return D > 0 && F > 0 ? 2 * D * F * 4 : -1; }
 
+// 8-bit drop threshold of the kernel: u < t8 is dropped, t8 = round(256 p), at least 1 when p > 0
+static unsigned drop_threshold8(float p) {
+  if (!(p > 0.f)) return 0;
+  unsigned t8 = (unsigned)(p * 256.f + 0.5f);
+  return t8 < 1 ? 1 : (t8 > 255 ? 255 : t8);
+}
+// The drop probability ddf_ffn_forward really applies for a requested p (quantised to 1 / 256): backward must scale
+// by 1 / (1 - this), not by 1 / (1 - p).
+extern "C" float ddf_ffn_dropout_p(float p) { return (float)drop_threshold8(p) / 256.f; }
+
 extern "C" int ddf_ffn_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                float* h, float* y, void* workspace, int64_t T, int64_t D, int64_t F, float p,
                                uint64_t seed, void* stream_) {
@@ -463,8 +473,7 @@ extern "C" int ddf_ffn_forward(const float* x, const float* w1, const float* b1,
   unsigned thr = 0;
   float scale = 1.f;
   if (p > 0.f) {
-    unsigned t8 = (unsigned)(p * 256.f + 0.5f);
-    t8 = t8 < 1 ? 1 : (t8 > 255 ? 255 : t8);
+    const unsigned t8 = drop_threshold8(p);
     thr = t8 * 0x01010101u;
     scale = 256.f / (float)(256 - t8);
   }

@@ -78,12 +78,13 @@ _SIGNATURES = {
     "ddf_ffn_supported": [c_i64] * 3,
     "ddf_ffn_workspace_bytes": [c_i64] * 2,
     "ddf_ffn_forward": [c_ptr] * 8 + [c_i64] * 3 + [c_f32, ctypes.c_uint64, c_ptr],
+    "ddf_ffn_dropout_p": [c_f32],
     "ddf_xty_supported": [c_i64] * 3,
     "ddf_xty_tf32": [c_ptr] * 3 + [c_i64] * 3 + [c_ptr],
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
     "ddf_dense_to_sparse": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],
 }
-_RESTYPES = {"ddf_ffn_workspace_bytes": c_i64, "ddf_launch_count": c_i64, "ddf_msda_plan_bytes": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64,
+_RESTYPES = {"ddf_ffn_workspace_bytes": c_i64, "ddf_ffn_dropout_p": c_f32, "ddf_launch_count": c_i64, "ddf_msda_plan_bytes": c_i64, "ddf_hard_voxelize_workspace_bytes": c_i64, "ddf_indice_pairs_workspace_bytes": c_i64,
              "ddf_sparse_bn_workspace_bytes": c_i64}
 
 

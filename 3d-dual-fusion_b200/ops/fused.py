@@ -318,7 +318,8 @@ class _FusedFFN(Function):
                                                 _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws), T, D, F_, float(p), seed,
                                                 _lib.current_stream())
         _lib.check(rc, "ffn_forward")
-        ctx.p = float(p)
+        # the kernel's drop threshold is quantised to 1 / 256: backward scales by 1 / (1 - the probability it applied)
+        ctx.p = float(_lib.get_lib().ddf_ffn_dropout_p(float(p))) if p > 0 else 0.0
         ctx.has_b2 = b2 is not None
         ctx.save_for_backward(x2, h, w1c, w2c)
         return y.view(x.shape)

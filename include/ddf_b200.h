@@ -407,6 +407,9 @@ int ddf_ffn_supported(int64_t T, int64_t D, int64_t F);
 int64_t ddf_ffn_workspace_bytes(int64_t D, int64_t F);   /* scratch for the re-laid weights, any content */
 int ddf_ffn_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* h,
                     float* y, void* workspace, int64_t T, int64_t D, int64_t F, float p, uint64_t seed, void* stream);
+/* the drop probability ddf_ffn_forward really applies for a requested p (its threshold is quantised to 1 / 256):
+ * pass THIS to ddf_bias_relu_dropout_backward, which scales by 1 / (1 - p) */
+float ddf_ffn_dropout_p(float p);
 
 /* c [M, N] = a [K, M]^T . b [K, N]: the weight gradient of an nn.Linear over K tokens, W.grad [out, in] =
  * grad_out [K, out]^T . x [K, in] (autograd of F.linear in <proj>/models/model_utils/actr_transformer.py:383-397,

@@ -336,5 +336,25 @@ def test_fused_ffn_dropout_statistics_and_backward():
         # h' that backward saved, through the bias gradient of linear1 (sum over tokens of the masked hidden gradient)
         assert l1.bias.grad is not None and float(l1.bias.grad.abs().sum()) > 0
         assert xg.grad is not None and bool(torch.isfinite(xg.grad).all())
+        # the backward is the derivative of THIS forward: same pattern, and the kernel's quantised 1 / (1 - p)
+        # (p = 0.1 drops 26 / 256: kept values are scaled by 256 / 230, not by 1 / 0.9)
+        from unittest import mock
+        drop1 = nn.Dropout(0.1).train()
+        with mock.patch.object(fused, "_seed", return_value=4242):
+            l1.zero_grad(); l2.zero_grad()
+            xg2 = x.clone().requires_grad_()
+            fused.ffn(l1, drop1, l2, xg2).backward(go)
+        _lib.check(L.ddf_ffn_forward(_lib.ptr(x), _lib.ptr(l1.weight), _lib.ptr(l1.bias), _lib.ptr(l2.weight),
+                                     _lib.ptr(l2.bias), _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws), T, 128, F_, 0.1, 4242,
+                                     _lib.current_stream()), "ffn_forward")
+        unscaled = (go.double() @ l2.weight.double()) * (h != 0)
+        assert abs(L.ddf_ffn_dropout_p(0.1) - 26.0 / 256.0) < 1e-7 and L.ddf_ffn_dropout_p(0.0) == 0.0
+        gb1 = l1.bias.grad.double()
+        ls = float((gb1 * unscaled.sum(0)).sum() / (unscaled.sum(0) ** 2).sum())
+        assert abs(ls - 256.0 / 230.0) < 8e-4, ls
+        gh_ref = unscaled * (256.0 / 230.0)
+        assert rel(xg2.grad, (gh_ref @ l1.weight.double()).cpu()) < 4e-3
+        assert rel(l1.weight.grad, (gh_ref.t() @ x.double()).cpu()) < 4e-3
+        assert rel(gb1, gh_ref.sum(0).cpu()) < 4e-3
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev

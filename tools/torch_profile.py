@@ -30,6 +30,8 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=45,
                                                           max_shapes_column_width=70))
+if os.environ.get("DDF_PROFILE_FLAT"):
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=110, max_name_column_width=90))
 if os.environ.get("DDF_PROFILE_STACKS"):
     # second pass: attribute the ATen kernels to source lines of this package
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof2:
