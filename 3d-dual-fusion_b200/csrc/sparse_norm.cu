@@ -5,8 +5,8 @@
 // conv -> BN1d(eps 1e-3, momentum 0.01) -> [+ identity] -> ReLU), the chain of separate elementwise
 // kernels over (N, C): batch_norm statistics + transform, add, clamp in forward (4 launches) and
 // threshold_backward, batch_norm backward reduce + elemt, add in backward (4-5 launches) by
-//   forward : bn_stats_kernel (column sums; the last CTA to finish folds the partials, writes
-//             mean / invstd and updates the running statistics) + bn_apply_kernel
+//   forward : bn_stats_kernel (column sums; the partials are folded in two levels by the last CTAs to finish, the
+//             very last one writes mean / invstd and updates the running statistics) + bn_apply_kernel
 //   backward: bn_bwd_reduce_kernel (ReLU mask applied on the fly; last CTA writes grad_weight /
 //             grad_bias and the two per-channel coefficients) + bn_bwd_apply_kernel
 // HBM-bound streaming kernels: rows are read as 16-byte vectors, a thread owns 4 channels of a row,
@@ -27,12 +27,38 @@ struct Acc8 {
   double v[8];
 };
 
-// Block-level fold of the per-thread (sum[4], sq[4]) accumulators over the rows of the block, then
-// one partial per CTA: part[blockIdx.x][0..1][C].  Returns true in the last CTA to arrive.
-__device__ __forceinline__ bool fold_and_publish(Acc8& a, int tpr, int cg, int rl, int rpb, int C,
-                                                 double* __restrict__ part, unsigned* counter) {
-  __shared__ double sm[kThreads * 8];
+// Two-level, fixed-order fold of the per-CTA partials.  One CTA folding all 592 partials was the tail of every
+// statistics launch: 2 * C columns x 592 doubles (1.2 MB at C = 128) through ONE SM, 11-22 us of a 30-50 us kernel.
+// Now the last CTA to arrive in each group of kFoldGroup consecutive CTAs folds that group (16 loads per column, all in
+// flight, on 37 SMs at once) and the last group to finish folds the 37 group sums.  Still deterministic: the order of
+// the additions depends on the indices only, not on the arrival order.
+constexpr int kFoldGroup = 16;
+constexpr int kMaxGroups = (kMaxGrid + kFoldGroup - 1) / kFoldGroup;
+
+// counters[0]: groups finished; counters[1 + g]: CTAs of group g finished.  All zero between launches.
+__device__ __forceinline__ bool arrive_last(unsigned* counter, unsigned expected) {
   __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = ticket == expected - 1;
+    if (s_last) *counter = 0;  // ready for the next launch on this workspace
+  }
+  __syncthreads();
+  const bool last = s_last;
+  if (last) __threadfence();
+  __syncthreads();             // s_last is reused by the second level
+  return last;
+}
+
+// Block-level fold of the per-thread (sum[4], sq[4]) accumulators over the rows of the block, one partial per CTA
+// (part[blockIdx.x][0..1][C]), then the two-level fold.  Returns true in the ONE CTA that ends up with the totals of
+// all 2 * C columns in tot[] (shared memory).
+__device__ __forceinline__ bool fold_and_publish(Acc8& a, int tpr, int cg, int rl, int rpb, int C,
+                                                 double* __restrict__ part, double* __restrict__ part2,
+                                                 unsigned* counters, double* tot) {
+  __shared__ double sm[kThreads * 8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sm[i * kThreads + threadIdx.x] = a.v[i];
   __syncthreads();
@@ -43,69 +69,50 @@ __device__ __forceinline__ bool fold_and_publish(Acc8& a, int tpr, int cg, int r
     }
     __syncthreads();
   }
+  const int cols = 2 * C;
   if (rl == 0) {
-    double* p = part + (long long)blockIdx.x * 2 * C + cg * 4;
+    double* p = part + (long long)blockIdx.x * cols + cg * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       p[i] = sm[i * kThreads + threadIdx.x];
       p[C + i] = sm[(4 + i) * kThreads + threadIdx.x];
     }
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(counter, 1u);
-    s_last = ticket == gridDim.x - 1;
-    if (s_last) *counter = 0;  // ready for the next launch on this workspace
+  const int grp = blockIdx.x / kFoldGroup, ngroups = (gridDim.x + kFoldGroup - 1) / kFoldGroup;
+  const int g0 = grp * kFoldGroup;
+  const int gsize = min(kFoldGroup, (int)gridDim.x - g0);
+  if (!arrive_last(counters + 1 + grp, (unsigned)gsize)) return false;
+  for (int col = threadIdx.x; col < cols; col += kThreads) {
+    const double* p = part + (long long)g0 * cols + col;
+    double v[kFoldGroup];
+#pragma unroll
+    for (int u = 0; u < kFoldGroup; ++u) v[u] = u < gsize ? __ldcg(p + (long long)u * cols) : 0.0;
+    double s = v[0];
+#pragma unroll
+    for (int u = 1; u < kFoldGroup; ++u) s += v[u];
+    part2[(long long)grp * cols + col] = s;
   }
-  __syncthreads();
-  if (s_last) __threadfence();
-  return s_last;
-}
-
-// Last CTA: totals of the 2*C columns over all CTAs' partials, in a fixed order -> tot[2*C] (shared).  The partials
-// of a column are read with 16 independent loads in flight per thread: a serial chain of up to 296 dependent L2 reads
-// (about 50 us) WAS the tail of every statistics launch.
-__device__ __forceinline__ double fold_column(const double* __restrict__ p, int first, int stride, int G, int cols) {
-  constexpr int U = 16;
-  double s[U];
+  if (!arrive_last(counters, (unsigned)ngroups)) return false;
+  for (int col = threadIdx.x; col < cols; col += kThreads) {
+    const double* p = part2 + col;
+    double s = 0.0;
+    int g = 0;
+    for (; g + kFoldGroup <= ngroups; g += kFoldGroup) {
+      double v[kFoldGroup];
 #pragma unroll
-  for (int u = 0; u < U; ++u) s[u] = 0.0;
-  int g = first;
-  for (; g + (U - 1) * stride < G; g += U * stride) {
+      for (int u = 0; u < kFoldGroup; ++u) v[u] = __ldcg(p + (long long)(g + u) * cols);
 #pragma unroll
-    for (int u = 0; u < U; ++u) s[u] += __ldcg(p + (long long)(g + u * stride) * cols);
-  }
-  for (; g < G; g += stride) s[0] += __ldcg(p + (long long)g * cols);   // fewer than U left
-#pragma unroll
-  for (int w = U / 2; w > 0; w >>= 1) {
-#pragma unroll
-    for (int u = 0; u < w; ++u) s[u] += s[u + w];
-  }
-  return s[0];
-}
-__device__ __forceinline__ void fold_partials(const double* __restrict__ part, int C, double* tot) {
-  __shared__ double sm[kThreads];
-  const int cols = 2 * C;
-  const int G = gridDim.x;
-  if (cols >= kThreads) {
-    for (int col = threadIdx.x; col < cols; col += kThreads) tot[col] = fold_column(part + col, 0, 1, G, cols);
-  } else {
-    const int nsl = kThreads / cols;  // cols is a power of two >= 8
-    const int col = threadIdx.x % cols, sl = threadIdx.x / cols;
-    double s = fold_column(part + col, sl, nsl, G, cols);
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    if (sl == 0) {
-      for (int j = 1; j < nsl; ++j) s += sm[j * cols + col];
-      tot[col] = s;
+      for (int u = 0; u < kFoldGroup; ++u) s += v[u];
     }
+    for (; g < ngroups; ++g) s += __ldcg(p + (long long)g * cols);
+    tot[col] = s;
   }
   __syncthreads();
+  return true;
 }
 
 __global__ void __launch_bounds__(kThreads)
-bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ part,
+bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ part, double* __restrict__ part2,
                 unsigned* counter, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                 float* running_mean, float* running_var, float momentum, float eps) {
   extern __shared__ double tot[];  // [2*C]
@@ -139,8 +146,7 @@ bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ 
     a.v[4] += s2.x; a.v[5] += s2.y; a.v[6] += s2.z; a.v[7] += s2.w;
   }
   for (; r < n; r += step) add(ldg4(px + r * C));
-  if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
-  fold_partials(part, C, tot);
+  if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, part2, counter, tot)) return;
   for (int c = threadIdx.x; c < C; c += kThreads) {
     const double mean = tot[c] / n;
     double var = tot[C + c] / n - mean * mean;  // biased, used for normalisation
@@ -272,7 +278,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                      const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ invstd, int n, int C, int relu, int train,
-                     double* __restrict__ part, unsigned* counter, float* __restrict__ gweight,
+                     double* __restrict__ part, double* __restrict__ part2, unsigned* counter,
+                     float* __restrict__ gweight,
                      float* __restrict__ gbias, float* __restrict__ coef) {
   extern __shared__ double tot[];
   const int tpr = C >> 2, rpb = kThreads / tpr;
@@ -309,8 +316,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
     const long long o = r * C + cg * 4;
     add(ldg4(gy + o), relu ? ldg4(y + o) : one, ldg4(x + o));
   }
-  if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, counter)) return;
-  fold_partials(part, C, tot);
+  if (!fold_and_publish(a, tpr, cg, rl, rpb, C, part, part2, counter, tot)) return;
   for (int c = threadIdx.x; c < C; c += kThreads) {
     if (gbias) gbias[c] = (float)tot[c];
     if (gweight) gweight[c] = (float)tot[C + c];
@@ -367,15 +373,21 @@ inline unsigned stats_grid(int64_t n, int64_t C) {
 
 extern "C" int64_t ddf_sparse_bn_workspace_bytes(int64_t C) {
   if (!pow2(C) || C < 4 || C > 1024) return -1;
-  // per-CTA partials [kMaxGrid][2][C] doubles + coefficient block [2][C] floats + arrival counter
-  return (int64_t)kMaxGrid * 2 * C * 8 + 2 * C * 4 + 256;
+  // per-CTA partials [kMaxGrid][2][C] doubles + group sums [kMaxGroups][2][C] doubles + coefficient block [2][C]
+  // floats + arrival counters [1 + kMaxGroups].  Zero-filled by the caller before its FIRST use; the kernels leave the
+  // counters at zero.
+  return (int64_t)(kMaxGrid + kMaxGroups) * 2 * C * 8 + 2 * C * 4 + 128 + 4 * (1 + kMaxGroups + 25);
 }
 
+static inline double* ws_part2(void* ws, int64_t C) {
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + (int64_t)kMaxGrid * 2 * C * 8);
+}
 static inline float* ws_coef(void* ws, int64_t C) {
-  return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (int64_t)kMaxGrid * 2 * C * 8);
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + (int64_t)(kMaxGrid + kMaxGroups) * 2 * C * 8);
 }
 static inline unsigned* ws_counter(void* ws, int64_t C) {
-  return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (int64_t)kMaxGrid * 2 * C * 8 + 2 * C * 4 + 128);
+  return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + (int64_t)(kMaxGrid + kMaxGroups) * 2 * C * 8 + 2 * C * 4 +
+                                     128);
 }
 
 static int bn_forward_impl(const float* x, const float* residual, const float* weight, const float* bias,
@@ -420,10 +432,8 @@ static int bn_forward_impl(const float* x, const float* residual, const float* w
   const long long n4 = n * C / 4;
   if (training) {
     DDF_CHECK_ARG(workspace && save_mean && save_invstd, "sparse_bn_forward: training needs workspace and save buffers");
-    // the arrival counter is reset by the last CTA of a launch; an aborted launch must not poison the next one
-    DDF_CUDA(cudaMemsetAsync(ws_counter(workspace, C), 0, sizeof(unsigned), stream));
     DDF_LAUNCH(bn_stats_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, x, (int)n,
-               (int)C, (double*)workspace, ws_counter(workspace, C), save_mean, save_invstd,
+               (int)C, (double*)workspace, ws_part2(workspace, C), ws_counter(workspace, C), save_mean, save_invstd,
                running_mean, running_var, momentum, eps);
     if (split)
       DDF_LAUNCH(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
@@ -467,9 +477,9 @@ extern "C" int ddf_sparse_bn_backward(const float* grad_y, const float* y, const
                     aligned16(weight) && aligned16(mean) && aligned16(invstd),
                 "sparse_bn_backward: tensors must be 16-byte aligned");
   float* coef = ws_coef(workspace, C);
-  DDF_CUDA(cudaMemsetAsync(ws_counter(workspace, C), 0, sizeof(unsigned), stream));
   DDF_LAUNCH(bn_bwd_reduce_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, grad_y, y, x,
-             mean, invstd, (int)n, (int)C, relu, training, (double*)workspace, ws_counter(workspace, C),
+             mean, invstd, (int)n, (int)C, relu, training, (double*)workspace, ws_part2(workspace, C),
+             ws_counter(workspace, C),
              grad_weight, grad_bias, coef);
   if (grad_x || grad_residual) {
     const long long n4 = n * C / 4;
