@@ -592,11 +592,13 @@ def run_ours(args):
     # inputs smaller than L2 (the KITTI-shaped config): evict them between timed steps
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if h2d < (192 << 20) else None
 
-    def step(t):
+    def step(t, after_forward=None):
         if flush is not None:
             flush.fill_(1)
         out = net(t)
         loss = out.square().mean()
+        if after_forward is not None:
+            after_forward()
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if exchange is not None:
@@ -666,13 +668,15 @@ def run_ours(args):
     turn = [0]
     seen = []
 
-    def stage_inputs():
+    def stage_inputs(after=None):
         k = turn[0] & 1
         turn[0] += 1
         dst = dev_sets[k]
         with torch.cuda.stream(copy_stream):
             if set_free[k] is not None:
                 copy_stream.wait_event(set_free[k])       # GPU-side: do not overwrite inputs a running step still reads
+            if after is not None:
+                copy_stream.wait_event(after)
             for d, h in zip(flat_tensors(dst), flat_tensors(h_t)):
                 d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
@@ -686,8 +690,14 @@ def run_ours(args):
         t, ev, k = staged.pop("next")
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
-        stage_inputs()                      # next step's host->device copy overlaps this step
-        loss = step(t)
+        def prefetch():
+            # next step's host->device copy is released when THIS step's forward has run on the GPU: the 148 MB DMA
+            # then overlaps the backward (long kernels, the host far ahead) instead of the launch-bound start of the
+            # forward, where bulk PCIe reads delay the launches (visible at N = 8: eight ranks share the host's links)
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(cur)
+            stage_inputs(after=fwd_done)
+        loss = step(t, prefetch)
         i = len(seen) & 1
         h_losses[i].copy_(loss.detach().reshape(1), non_blocking=True)
         done = torch.cuda.Event()
@@ -756,7 +766,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "every step copies its inputs from pinned host memory (side stream, two persistent device "
-                                "staging sets, enqueued while the previous step computes) and copies its loss to pinned "
+                                "staging sets, enqueued while the previous step computes, released on the GPU when that step's forward is done) and copies its loss to pinned "
                                 "host memory; the host reads the loss of step i while step i + 1 runs",
                     "losses_read_on_host": sum(1 for v in seen if v is not None)},
             "gpu_launches": launches,
