@@ -1,4 +1,5 @@
 // Library-level entry points: error string, ABI version.
+#include <stdlib.h>
 #include <stdarg.h>
 
 #include <atomic>
@@ -18,6 +19,13 @@ const char* get_error() { return g_err; }
 
 static std::atomic<long long> g_launches{0};
 void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int pdl_enabled() {
+  static const int on = [] {
+    const char* e = getenv("DDF_PDL");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on;
+}
 }  // namespace ddf
 
 extern "C" {

@@ -86,6 +86,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
 __global__ void __launch_bounds__(kThreads)
 xty_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ c,
            int K, int M, int N, int n_tile, int m_tiles, int n_tiles, int splits, int n_stages) {
+  ddf::pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tile = blockIdx.x % (m_tiles * n_tiles), split = blockIdx.x / (m_tiles * n_tiles);
@@ -251,7 +252,7 @@ extern "C" int ddf_xty_tf32(const float* a, const float* b, float* c, int64_t K,
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   const int smem = n_stages * stage_bytes + 256 + 1024;
   DDF_SET_SMEM_ONCE(xty_kernel, 227 * 1024);
-  DDF_LAUNCH(xty_kernel, (unsigned)(tiles * splits), kThreads, smem, stream, map_a, map_b, c, (int)K, (int)M, (int)N,
+  DDF_LAUNCH_PDL(xty_kernel, (unsigned)(tiles * splits), kThreads, smem, stream, map_a, map_b, c, (int)K, (int)M, (int)N,
              n_tile, m_tiles, n_tiles, (int)splits, n_stages);
   DDF_LAUNCH_CHECK();
   return DDF_OK;

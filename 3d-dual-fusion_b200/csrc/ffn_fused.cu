@@ -127,6 +127,7 @@ __device__ __forceinline__ unsigned keep4(uint32_t seed, uint32_t i, uint32_t th
 __global__ void __launch_bounds__(256)
 ffn_pack_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ p1,
                         float* __restrict__ p2, int F) {
+  ddf::pdl_sync();
   const int t = blockIdx.x * 256 + threadIdx.x;          // one 16-byte piece each
   const int n1 = F * DM / 4;
   if (t < n1) {
@@ -152,6 +153,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
                const float* __restrict__ p2, const __grid_constant__ CUtensorMap map_h,
                const float* __restrict__ b1, const float* __restrict__ b2, float* __restrict__ y, int T, int F,
                unsigned long long seed, unsigned thr, float scale) {
+  ddf::pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* xs = smem;
@@ -481,7 +483,7 @@ extern "C" int ddf_ffn_forward(const float* x, const float* w1, const float* b1,
   float* p2 = p1 + D * F;
   DDF_LAUNCH(ffn_pack_weights_kernel, (unsigned)ddf::cdiv(2 * F * D / 4, 256), 256, 0, stream, w1, w2, p1, p2, (int)F);
   DDF_SET_SMEM_ONCE(ffn_fwd_kernel, kSmemBytes);
-  DDF_LAUNCH(ffn_fwd_kernel, (unsigned)ddf::cdiv(T, TT), kThreads, kSmemBytes, stream, map_x, p1, p2, map_h, b1, b2, y,
+  DDF_LAUNCH_PDL(ffn_fwd_kernel, (unsigned)ddf::cdiv(T, TT), kThreads, kSmemBytes, stream, map_x, p1, p2, map_h, b1, b2, y,
              (int)T, (int)F, (unsigned long long)seed, thr, scale);
   DDF_LAUNCH_CHECK();
   return DDF_OK;

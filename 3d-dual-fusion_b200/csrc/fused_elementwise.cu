@@ -34,6 +34,7 @@ __device__ __forceinline__ unsigned keep4(unsigned long long seed, unsigned long
 __global__ void __launch_bounds__(kThreads)
 bias_relu_dropout_kernel(const float* __restrict__ h, const float* __restrict__ bias, float* __restrict__ out,
                          long long n4, int c4, unsigned long long seed, unsigned thr, float scale) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n4) return;
   float4 v = ldg4(h + i * 4);
@@ -52,6 +53,7 @@ bias_relu_dropout_kernel(const float* __restrict__ h, const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 relu_dropout_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ out, float* __restrict__ gx,
                         long long n4, float scale) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n4) return;
   const float4 g = ldg4(gy + i * 4), o = ldg4(out + i * 4);
@@ -69,6 +71,7 @@ relu_dropout_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 relu_dropout_bwd_bias_kernel(const float* __restrict__ gy, const float* __restrict__ out, float* __restrict__ gx,
                              float* __restrict__ gbias, long long rows, int c4, float scale) {
+  ddf::pdl_sync();
   const int col = threadIdx.x % c4, rl = threadIdx.x / c4, rpb = kThreads / c4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
@@ -103,11 +106,24 @@ relu_dropout_bwd_bias_kernel(const float* __restrict__ gy, const float* __restri
 // atomicAdd per column and CTA.  out must be zeroed by the caller.  C / 4 <= 256 and 256 % (C / 4) == 0.
 __global__ void __launch_bounds__(kThreads)
 col_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int c4) {
+  ddf::pdl_sync();
   const int col = threadIdx.x % c4, rl = threadIdx.x / c4, rpb = kThreads / c4;   // threads past rpb * c4 idle
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long r = (long long)blockIdx.x * rpb + rl; rl < rpb && r < rows; r += (long long)gridDim.x * rpb) {
-    const float4 v = ldg4(x + (r * c4 + col) * 4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + rl;
+  if (rl < rpb) {
+    const float* px = x + col * 4;
+    for (; r + 7 * step < rows; r += 8 * step) {   // eight independent 16-byte loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ldg4(px + (r + u * step) * c4 * 4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; r < rows; r += step) {
+      const float4 v = ldg4(px + r * c4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
   __shared__ float4 sh[kThreads];
   sh[threadIdx.x] = acc;
@@ -133,6 +149,7 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ a, const float* __restrict__
                           float* __restrict__ s_out, float* __restrict__ y, float* __restrict__ mean_out,
                           float* __restrict__ rstd_out, long long rows, unsigned long long seed, unsigned thr,
                           float scale, float eps) {
+  ddf::pdl_sync();
   constexpr int C = 4 * LPR * VPL;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const long long wrow = (((long long)blockIdx.x * kThreads + threadIdx.x) >> 5) * (32 / LPR);
@@ -196,6 +213,7 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ gy, const float* __restrict_
                           const float* __restrict__ rstd_in, float* __restrict__ ga, float* __restrict__ gb,
                           float* __restrict__ ggamma, float* __restrict__ gbeta, long long rows,
                           unsigned long long seed, unsigned thr, float scale) {
+  ddf::pdl_sync();
   constexpr int C = 4 * LPR * VPL, RPW = 32 / LPR;
   __shared__ float sh_g[C], sh_b[C];
   for (int i = threadIdx.x; i < C; i += kThreads) sh_g[i] = sh_b[i] = 0.f;
@@ -303,7 +321,7 @@ extern "C" int ddf_bias_relu_dropout_backward(const float* grad_out, const float
     const int rpb = kThreads / c4;
     long long grid = ddf::cdiv(n, rpb);
     if (grid > 8 * ddf::kNumSM) grid = 8 * ddf::kNumSM;
-    DDF_LAUNCH(relu_dropout_bwd_bias_kernel, (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_out, out, grad_h,
+    DDF_LAUNCH_PDL(relu_dropout_bwd_bias_kernel, (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_out, out, grad_h,
                grad_bias, (long long)n, c4, 1.f / (1.f - p));
   } else {
     DDF_CHECK_ARG(grad_bias == nullptr, "bias_relu_dropout_backward: grad_bias needs C/4 to divide 256");
@@ -339,7 +357,7 @@ extern "C" int ddf_add_dropout_layer_norm_forward(const float* a, const float* b
                 "add_dropout_layer_norm: misaligned pointer");
   const long long wrows = C >= 128 ? rows : ddf::cdiv(rows, 128 / C);     // rows of warps
   const unsigned grid = (unsigned)ddf::cdiv(wrows * 32, kThreads);
-  DDF_LN_DISPATCH(C, DDF_LAUNCH((add_dropout_ln_fwd_kernel<VPL, LPR>), grid, kThreads, 0, (cudaStream_t)stream_, a, b, gamma,
+  DDF_LN_DISPATCH(C, DDF_LAUNCH_PDL((add_dropout_ln_fwd_kernel<VPL, LPR>), grid, kThreads, 0, (cudaStream_t)stream_, a, b, gamma,
                                 beta, s_out, y, mean, rstd, (long long)rows, (unsigned long long)seed, threshold(p),
                                 1.f / (1.f - p), eps));
   DDF_LAUNCH_CHECK();
@@ -357,7 +375,7 @@ extern "C" int ddf_add_dropout_layer_norm_backward(const float* grad_y, const fl
   DDF_CHECK_ARG(grad_y && s && gamma && mean && rstd, "add_dropout_layer_norm_backward: null pointer");
   long long grid = ddf::cdiv((C >= 128 ? rows : ddf::cdiv(rows, 128 / C)) * 32, kThreads);
   if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;   // grid-stride: bounded number of atomics on grad_gamma / beta
-  DDF_LN_DISPATCH(C, DDF_LAUNCH((add_dropout_ln_bwd_kernel<VPL, LPR>), (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_y,
+  DDF_LN_DISPATCH(C, DDF_LAUNCH_PDL((add_dropout_ln_bwd_kernel<VPL, LPR>), (unsigned)grid, kThreads, 0, (cudaStream_t)stream_, grad_y,
                                 s, gamma, mean, rstd, grad_a, grad_b, grad_gamma, grad_beta, (long long)rows,
                                 (unsigned long long)seed, threshold(p), 1.f / (1.f - p)));
   DDF_LAUNCH_CHECK();
@@ -376,7 +394,7 @@ extern "C" int ddf_col_sum(const float* x, float* out, int64_t rows, int64_t C, 
   const int c4 = (int)(C / 4), rpb = kThreads / c4;
   long long grid = ddf::cdiv(rows, rpb);
   if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;
-  DDF_LAUNCH(col_sum_kernel, (unsigned)grid, kThreads, 0, stream, x, out, (long long)rows, c4);
+  DDF_LAUNCH_PDL(col_sum_kernel, (unsigned)grid, kThreads, 0, stream, x, out, (long long)rows, c4);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
 }
@@ -403,6 +421,7 @@ bigate_sum_fwd_kernel(const float* __restrict__ f1, const float* __restrict__ f2
                       const float* __restrict__ bb, const float* __restrict__ wa, const float* __restrict__ ba,
                       float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ gates, long long rows,
                       int fuse_in) {
+  ddf::pdl_sync();
   constexpr int C = 128 * VPL;
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -446,6 +465,7 @@ bigate_sum_bwd_kernel(const float* __restrict__ go1, const float* __restrict__ g
                       const float* __restrict__ wa, float* __restrict__ gf1, float* __restrict__ gf2,
                       float* __restrict__ gwb, float* __restrict__ gbb, float* __restrict__ gwa,
                       float* __restrict__ gba, long long rows, int fuse_in) {
+  ddf::pdl_sync();
   constexpr int C = 128 * VPL;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 w1[VPL], w2[VPL], aw1[VPL], aw2[VPL];
@@ -564,7 +584,7 @@ extern "C" int ddf_bigate_sum_forward(const float* f1, const float* f2, const fl
                     (reinterpret_cast<uintptr_t>(gates) & 7u) == 0,
                 "bigate_sum_forward: misaligned pointer");
   const unsigned grid = (unsigned)ddf::cdiv(rows * 32, kThreads);
-  DDF_GATE_DISPATCH(C, DDF_LAUNCH(bigate_sum_fwd_kernel<VPL>, grid, kThreads, 0, (cudaStream_t)stream_, f1, f2, wb, bb,
+  DDF_GATE_DISPATCH(C, DDF_LAUNCH_PDL(bigate_sum_fwd_kernel<VPL>, grid, kThreads, 0, (cudaStream_t)stream_, f1, f2, wb, bb,
                                   wa, ba, o1, o2, gates, (long long)rows, fuse_in));
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -589,7 +609,7 @@ extern "C" int ddf_bigate_sum_backward(const float* grad_o1, const float* grad_o
                 "bigate_sum_backward: misaligned pointer");
   long long grid = ddf::cdiv(rows * 32, kThreads);
   if (grid > 4 * ddf::kNumSM) grid = 4 * ddf::kNumSM;
-  DDF_GATE_DISPATCH(C, DDF_LAUNCH(bigate_sum_bwd_kernel<VPL>, (unsigned)grid, kThreads, 0, stream, grad_o1, grad_o2, f1,
+  DDF_GATE_DISPATCH(C, DDF_LAUNCH_PDL(bigate_sum_bwd_kernel<VPL>, (unsigned)grid, kThreads, 0, stream, grad_o1, grad_o2, f1,
                                   f2, gates, wb, wa, grad_f1, grad_f2, grad_wb, grad_bb, grad_wa, grad_ba,
                                   (long long)rows, fuse_in));
   DDF_LAUNCH_CHECK();

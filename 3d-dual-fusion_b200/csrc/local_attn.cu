@@ -26,6 +26,7 @@ constexpr int kWarps = 4;          // (group, head) pairs per CTA
 template <int HD>
 __global__ void __launch_bounds__(kWarps * 32)
 local_attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, long long n_pairs, int heads, float scale) {
+  ddf::pdl_sync();
   __shared__ __align__(16) float s_k[kWarps][kNS][HD];
   __shared__ __align__(16) float s_v[kWarps][kNS][HD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,6 +92,7 @@ template <int HD>
 __global__ void __launch_bounds__(kWarps * 32)
 local_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ gout, float* __restrict__ gqkv,
                       long long n_pairs, int heads, float scale) {
+  ddf::pdl_sync();
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per warp: Q (scaled), K, V, dO: 4 x [32][HD]; P, dS: 2 x [32][33]

@@ -90,6 +90,7 @@ msda_fwd_vec4_kernel(const float* __restrict__ value, const int64_t* __restrict_
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ attn, float* __restrict__ out, int S, int M, int L,
                      int Lq, int P, long long total) {
+  ddf::pdl_sync();
   __shared__ LevelTable lv;
   load_levels(lv, shapes, lsi, L);
   const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -156,6 +157,7 @@ msda_bwd_vec4_kernel(const float* __restrict__ value, const int64_t* __restrict_
                      float* __restrict__ gvalue, float* __restrict__ gloc,
                      float* __restrict__ gattn, int S, int M, int L, int Lq, int P,
                      long long total) {
+  ddf::pdl_sync();
   __shared__ LevelTable lv;
   load_levels(lv, shapes, lsi, L);
   long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -304,6 +306,7 @@ msda_fwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__
                         const int64_t* __restrict__ lsi, const T* __restrict__ loc,
                         const T* __restrict__ attn, T* __restrict__ out, int S, int M, int D,
                         int L, int Lq, int P, long long total) {
+  ddf::pdl_sync();
   __shared__ LevelTable lv;
   load_levels(lv, shapes, lsi, L);
   const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -340,6 +343,7 @@ msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__
                         const T* __restrict__ attn, const T* __restrict__ gout,
                         T* __restrict__ gvalue, T* __restrict__ gloc, T* __restrict__ gattn, int S,
                         int M, int D, int L, int Lq, int P, long long n_qm) {
+  ddf::pdl_sync();
   __shared__ LevelTable lv;
   load_levels(lv, shapes, lsi, L);
   const int lane = threadIdx.x & 31;

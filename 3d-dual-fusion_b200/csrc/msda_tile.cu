@@ -75,6 +75,7 @@ __host__ __device__ inline PlanLayout plan_layout(long long N, long long NQ, int
 __global__ void __launch_bounds__(kThreads)
 msda_plan_count_kernel(const float* __restrict__ ref, const int* __restrict__ qbatch, int* __restrict__ plan,
                        PlanLayout pl, long long NQ, int Lq, int H, int W) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= NQ) return;
   const float2 r = __ldg(reinterpret_cast<const float2*>(ref) + i);
@@ -90,6 +91,7 @@ msda_plan_count_kernel(const float* __restrict__ ref, const int* __restrict__ qb
 
 // single block: tile_start = exclusive scan of counts; work items = (tile, first query slot, count <= kQC)
 __global__ void __launch_bounds__(1024) msda_plan_scan_kernel(int* __restrict__ plan, PlanLayout pl) {
+  ddf::pdl_sync();
   __shared__ int s_q[32], s_w[32];
   __shared__ int carry_q, carry_w;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(1024) msda_plan_scan_kernel(int* __restrict__ 
 
 __global__ void __launch_bounds__(kThreads)
 msda_plan_scatter_kernel(int* __restrict__ plan, PlanLayout pl, long long NQ) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= NQ) return;
   plan[pl.perm + plan[pl.tile_start + plan[pl.q_tile + i]] + plan[pl.q_rank + i]] = (int)i;
@@ -288,6 +291,7 @@ msda_tile_fwd_kernel(const __grid_constant__ CUtensorMap map_value, const float*
                      const float* __restrict__ ref, const float* __restrict__ off, const float* __restrict__ logit,
                      const int* __restrict__ plan, long long perm_off, long long work_off, float* __restrict__ out,
                      int H, int W, int M, int Lq, int TX, int TY) {
+  ddf::pdl_sync();
   constexpr int D = 4 * TPH, HPC = 8 / TPH, PPL = kP / TPH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -398,6 +402,7 @@ msda_tile_bwd_kernel(const __grid_constant__ CUtensorMap map_value, const float*
                      const float* __restrict__ gout, const int* __restrict__ plan, long long perm_off,
                      long long work_off, float* __restrict__ gvalue, float* __restrict__ goff,
                      float* __restrict__ glogit, int H, int W, int M, int Lq, int TX, int TY) {
+  ddf::pdl_sync();
   constexpr int D = 4 * TPH, HPC = 8 / TPH, PPL = kP / TPH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -651,7 +656,7 @@ extern "C" int ddf_msda_tile_forward(const float* value, const float* reference_
 #define DDF_TILE_FWD(TPH, TMA)                                                                                   \
   do {                                                                                                            \
     DDF_SET_SMEM_ONCE((msda_tile_fwd_kernel<TPH, TMA>), smem);                                                    \
-    DDF_LAUNCH((msda_tile_fwd_kernel<TPH, TMA>), grid, kThreads, smem, stream, map, value, reference_points,      \
+    DDF_LAUNCH_PDL((msda_tile_fwd_kernel<TPH, TMA>), grid, kThreads, smem, stream, map, value, reference_points,      \
                offsets, logits, plan, pl.perm, pl.work, out, (int)H, (int)W, (int)M, (int)NQ, pl.TX, pl.TY);      \
   } while (0)
   if (D == 16) {
@@ -692,7 +697,7 @@ extern "C" int ddf_msda_tile_backward(const float* value, const float* reference
 #define DDF_TILE_BWD(TPH, TMA)                                                                                   \
   do {                                                                                                            \
     DDF_SET_SMEM_ONCE((msda_tile_bwd_kernel<TPH, TMA>), smem);                                                    \
-    DDF_LAUNCH((msda_tile_bwd_kernel<TPH, TMA>), grid, kThreads, smem, stream, map, value, reference_points,      \
+    DDF_LAUNCH_PDL((msda_tile_bwd_kernel<TPH, TMA>), grid, kThreads, smem, stream, map, value, reference_points,      \
                offsets, logits, grad_out, plan, pl.perm, pl.work, grad_value, grad_offsets, grad_logits, (int)H,  \
                (int)W, (int)M, (int)NQ, pl.TX, pl.TY);                                                            \
   } while (0)

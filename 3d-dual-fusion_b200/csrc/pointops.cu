@@ -82,6 +82,7 @@ template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads)
 fps_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* __restrict__ idxs, int n,
            int m, int ref_block, int cs) {
+  ddf::pdl_sync();
   __shared__ unsigned long long s_key[kFpsThreads / 32];
   __shared__ FpsSlot s_slot[2][kMaxCluster];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -196,6 +197,7 @@ template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads)
 fps_single_kernel(const float* __restrict__ xyz, float* __restrict__ temp, int* __restrict__ idxs, int n, int m,
                   int ref_block) {
+  ddf::pdl_sync();
   __shared__ FpsSlot s_warp[2][kFpsThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* row = xyz + (long long)blockIdx.x * n * 3;
@@ -307,6 +309,7 @@ constexpr int kBqTile = 1024;  // points per smem tile
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz,
                   int* __restrict__ idx, int n, int m, float min_r2, float max_r2, int nsample) {
+  ddf::pdl_sync();
   __shared__ float s_pts[kBqTile * 3];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -352,6 +355,7 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
 __global__ void __launch_bounds__(256)
 index_rows_kernel(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
                   int C, int N, long long E) {
+  ddf::pdl_sync();
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
   if (e >= E) return;
@@ -363,6 +367,7 @@ index_rows_kernel(const float* __restrict__ feat, const int* __restrict__ idx, f
 __global__ void __launch_bounds__(256)
 index_rows_grad_kernel(const float* __restrict__ gout, const int* __restrict__ idx,
                        float* __restrict__ gfeat, int C, int N, long long E) {
+  ddf::pdl_sync();
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
   if (e >= E) return;
@@ -375,12 +380,14 @@ index_rows_grad_kernel(const float* __restrict__ gout, const int* __restrict__ i
 // flattened (group, slot) order (what the reference's unique + flip + scatter_ yields on the CPU; its CUDA scatter_
 // with duplicate indices is nondeterministic).  first[b, n] = min position of voxel n.
 __global__ void __launch_bounds__(256) fill_int_kernel(int* __restrict__ p, int v, long long n) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < n) p[i] = v;
 }
 
 __global__ void __launch_bounds__(256)
 first_occurrence_kernel(const int* __restrict__ idx, int* __restrict__ first, int N, long long E) {
+  ddf::pdl_sync();
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
   const int b = blockIdx.y;
   if (e >= E) return;
@@ -391,6 +398,7 @@ first_occurrence_kernel(const int* __restrict__ idx, int* __restrict__ first, in
 __global__ void __launch_bounds__(256)
 scatter_first_kernel(const float* __restrict__ feats, const int* __restrict__ first, float* __restrict__ out,
                      int C, int N, long long E) {
+  ddf::pdl_sync();
   const int n = blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
   if (n >= N) return;
@@ -403,6 +411,7 @@ scatter_first_kernel(const float* __restrict__ feats, const int* __restrict__ fi
 __global__ void __launch_bounds__(256)
 scatter_first_grad_kernel(const float* __restrict__ gout, const int* __restrict__ first,
                           float* __restrict__ gfeats, float* __restrict__ gfeatures, int C, int N, long long E) {
+  ddf::pdl_sync();
   const int n = blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
   if (n >= N) return;

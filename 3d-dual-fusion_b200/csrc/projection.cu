@@ -28,6 +28,7 @@ struct ProjParams {
 __global__ void __launch_bounds__(kThreads)
 project_assign_kernel(const float* __restrict__ pts, int stride, ProjParams P, int n, int group_base,
                       int* __restrict__ group, float* __restrict__ grid, float* __restrict__ grid_o) {
+  ddf::pdl_sync();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
   const float x = pts[(long long)i * stride], y = pts[(long long)i * stride + 1], z = pts[(long long)i * stride + 2];
@@ -60,6 +61,7 @@ project_assign_kernel(const float* __restrict__ pts, int stride, ProjParams P, i
 // one CTA per group: col[i] = number of j < i with group[j] == g (stable rank), counts[g] = group size
 __global__ void __launch_bounds__(1024)
 group_rank_kernel(const int* __restrict__ group, int n, int* __restrict__ col, int* __restrict__ counts) {
+  ddf::pdl_sync();
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -96,6 +98,7 @@ project_cameras_kernel(const int* __restrict__ indices, const float* __restrict_
                        const float* __restrict__ thres, int n_cam, int B, float image_scale, float Hf, float Wf, int n,
                        long long* __restrict__ grid, float* __restrict__ depth, bool* __restrict__ mask,
                        long long* __restrict__ fx, long long* __restrict__ fy) {
+  ddf::pdl_sync();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
   const int b = indices[4 * (long long)i];

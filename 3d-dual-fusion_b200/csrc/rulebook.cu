@@ -55,6 +55,7 @@ __device__ __forceinline__ long long flat_in(const ConvGeom& g, int b, int z, in
 __global__ void __launch_bounds__(kThreads)
 hash_insert_kernel(const int* __restrict__ indices, int n, ConvGeom g, unsigned long long* keys,
                    int* vals, unsigned mask) {
+  ddf::pdl_sync();
   const int j = blockIdx.x * kThreads + threadIdx.x;
   if (j >= n) return;
   const int4 c = reinterpret_cast<const int4*>(indices)[j];  // b, z, y, x
@@ -88,6 +89,7 @@ subm_tables_kernel(const int* __restrict__ indices, int n, ConvGeom g,
                    const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
                    unsigned mask, int* __restrict__ scatter_t, int* __restrict__ gather_t,
                    int* __restrict__ flags, int symmetric) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= (long long)n * g.kvol) return;
   const int j = (int)(t / g.kvol), k = (int)(t % g.kvol);
@@ -134,6 +136,7 @@ __device__ __forceinline__ long long conv_out_cell(const ConvGeom& g, int4 c, in
 
 __global__ void __launch_bounds__(kThreads)
 conv_mark_kernel(const int* __restrict__ indices, int n, ConvGeom g, unsigned* bitmap) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= (long long)n * g.kvol) return;
   const int j = (int)(t / g.kvol), k = (int)(t % g.kvol);
@@ -144,6 +147,7 @@ conv_mark_kernel(const int* __restrict__ indices, int n, ConvGeom g, unsigned* b
 
 __global__ void __launch_bounds__(kThreads)
 popc_kernel(const unsigned* __restrict__ bitmap, long long nwords, int* __restrict__ counts) {
+  ddf::pdl_sync();
   const long long w = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (w < nwords) counts[w] = __popc(bitmap[w]);
 }
@@ -153,6 +157,7 @@ conv_tables_kernel(const int* __restrict__ indices, int n, ConvGeom g,
                    const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
                    int* __restrict__ scatter_t, int* __restrict__ gather_t,
                    int* __restrict__ flags) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= (long long)n * g.kvol) return;
   const int j = (int)(t / g.kvol), k = (int)(t % g.kvol);
@@ -171,6 +176,7 @@ conv_tables_kernel(const int* __restrict__ indices, int n, ConvGeom g,
 __global__ void __launch_bounds__(kThreads)
 conv_outids_kernel(const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
                    long long nwords, ConvGeom g, int* __restrict__ out_indices) {
+  ddf::pdl_sync();
   const long long w = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (w >= nwords) return;
   unsigned bits = bitmap[w];
@@ -194,6 +200,7 @@ conv_outids_kernel(const unsigned* __restrict__ bitmap, const int* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 pairs_compact_kernel(const int* __restrict__ scatter_t, const int* __restrict__ prefix, int n,
                      int kvol, int* __restrict__ indice_pairs, int* __restrict__ indice_num) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= (long long)n * kvol) return;
   const int k = (int)(t / n), j = (int)(t % n);  // k-major so writes of one offset are coalesced
@@ -208,6 +215,7 @@ pairs_compact_kernel(const int* __restrict__ scatter_t, const int* __restrict__ 
 }
 
 __global__ void __launch_bounds__(kThreads) fill_i32_kernel(int* p, long long n, int v) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t < n) p[t] = v;
 }

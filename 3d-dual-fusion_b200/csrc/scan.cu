@@ -36,6 +36,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total) {
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __restrict__ in,
                                                                     long long n,
                                                                     int* __restrict__ block_sums) {
+  ddf::pdl_sync();
   const long long base = (long long)blockIdx.x * kScanTile;
   int s = 0;
 #pragma unroll
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __
 
 // single block: exclusive scan of the nb block sums in place, total -> block_sums[nb]
 __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nb) {
+  ddf::pdl_sync();
   int carry = 0;
   for (int base = 0; base < nb; base += kScanThreads) {
     const int i = base + threadIdx.x;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int* __r
                                                                    long long n,
                                                                    const int* __restrict__ block_sums,
                                                                    int nb) {
+  ddf::pdl_sync();
   // thread owns kScanItems CONSECUTIVE elements so the in-thread order is the global order
   const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
   int v[kScanItems];

@@ -78,6 +78,7 @@ spconv_gather_gemm_kernel(const float* __restrict__ feat, const float* __restric
                           const int* __restrict__ table, const float* __restrict__ bias,
                           float* __restrict__ out, int n_out, int kvol, int cin, int cout,
                           int co_base) {
+  ddf::pdl_sync();
   constexpr int TX = CO / 4;          // threads along channels
   constexpr int TY = kThreads / TX;   // threads along rows
   constexpr int RM = TM / TY;         // rows per thread
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kThreads)
 spconv_wgrad_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
                     const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
                     int cin, int cout, int inverse, float* __restrict__ gw) {
+  ddf::pdl_sync();
   // thread tile: (CI_T*CO_T)/256 outputs, laid out TI x TJ
   constexpr int TJ = 4;
   constexpr int TXN = CO_T / TJ;           // threads along cout
@@ -238,6 +240,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
 __global__ void __launch_bounds__(kThreads)
 transpose_filters_kernel(const float* __restrict__ w, float* __restrict__ wt, int kvol, int cin,
                          int cout, bool round_tf32) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const long long per = (long long)cin * cout;
   if (t >= per * kvol) return;
@@ -253,6 +256,7 @@ transpose_filters_kernel(const float* __restrict__ w, float* __restrict__ wt, in
 // 2^-12 relative rounding instead of a systematic 2^-11 shrink per operand)
 __global__ void __launch_bounds__(kThreads)
 round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4, long long n) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t < n4) {
     float4 v = reinterpret_cast<const float4*>(src)[t];
@@ -281,6 +285,7 @@ __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned
 __global__ void __launch_bounds__(kThreads)
 split_bf16x3_kernel(const float* __restrict__ src, uint8_t* __restrict__ split, float* __restrict__ rounded,
                     long long n8, int cols) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= n8) return;
   const long long e = t * 8;
@@ -308,6 +313,7 @@ split_bf16x3_kernel(const float* __restrict__ src, uint8_t* __restrict__ split, 
 __global__ void __launch_bounds__(kThreads)
 split_filters_kernel(const float* __restrict__ w, uint8_t* __restrict__ ws, int kvol, int cin, int cout,
                      bool transpose) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const long long per = (long long)cin * cout;
   if (t >= per * kvol) return;
@@ -327,6 +333,7 @@ split_filters_kernel(const float* __restrict__ w, uint8_t* __restrict__ ws, int 
 __global__ void __launch_bounds__(kThreads)
 pairs_to_table_kernel(const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
                       int kvol, int key_col, int* __restrict__ table) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= (long long)kvol * pair_stride) return;
   const int k = (int)(t / pair_stride), s = (int)(t % pair_stride);
@@ -350,6 +357,7 @@ __global__ void __launch_bounds__(kThreads)
 spconv_sparse_rows_kernel(const float* __restrict__ feat, const float* __restrict__ filt,
                           const int* __restrict__ table, const float* __restrict__ bias,
                           float* __restrict__ out, int n_out, int kvol) {
+  ddf::pdl_sync();
   extern __shared__ float s_w[];   // [kvol][CI][CO]
   for (int e = threadIdx.x; e < kvol * CI * CO; e += kThreads) s_w[e] = __ldg(filt + e);
   __syncthreads();
@@ -450,7 +458,7 @@ extern "C" int ddf_sparse_conv_forward(const float* features, const float* filte
                   "sparse_conv_forward: split operands need the multi-tile kernel (K=%lld Cin=%lld Cout=%lld)",
                   (long long)kvol, (long long)cin, (long long)cout);
     const long long nw = kvol * cin * cout;
-    DDF_LAUNCH(split_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, filters,
+    DDF_LAUNCH_PDL(split_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, filters,
                reinterpret_cast<uint8_t*>(filters_t_ws), (int)kvol, (int)cin, (int)cout, true);
     return ddf::spconv_tma_launch(features, filters_t_ws, gather_table, bias, out, n_out, n_in, (int)kvol,
                                   (int)cin, (int)cout, false, true, stream);
@@ -489,7 +497,7 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
     DDF_CHECK_ARG(n_out >= 0 && ddf::spconv_tma_supported((int)kvol, (int)cout, (int)cin),
                   "sparse_conv_dgrad: split operands need the multi-tile kernel (K=%lld Cin=%lld Cout=%lld)",
                   (long long)kvol, (long long)cin, (long long)cout);
-    DDF_LAUNCH(split_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, filters,
+    DDF_LAUNCH_PDL(split_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream, filters,
                reinterpret_cast<uint8_t*>(filters_t_ws), (int)kvol, (int)cin, (int)cout, false);
     return ddf::spconv_tma_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, n_out, (int)kvol,
                                   (int)cout, (int)cin, false, true, stream);
@@ -501,7 +509,7 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
                                 (int)cin, stream);
   }
   if (tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cout, (int)cin)) {
-    DDF_LAUNCH(round_tf32_kernel, (unsigned)ddf::cdiv(nw / 4 + 1, kThreads), kThreads, 0, stream, filters,
+    DDF_LAUNCH_PDL(round_tf32_kernel, (unsigned)ddf::cdiv(nw / 4 + 1, kThreads), kThreads, 0, stream, filters,
                filters_t_ws, nw / 4, nw);
     if (n_out >= 0 && tma_enabled() && ddf::spconv_tma_supported((int)kvol, (int)cout, (int)cin))
       return ddf::spconv_tma_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, n_out,
@@ -605,7 +613,7 @@ extern "C" int ddf_round_tf32(const float* src, float* dst, int64_t n, void* str
   DDF_CHECK_ARG(n >= 0, "round_tf32: bad size");
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(src && dst, "round_tf32: null pointer");
-  DDF_LAUNCH(round_tf32_kernel, (unsigned)ddf::cdiv(n / 4 + 1, kThreads), kThreads, 0,
+  DDF_LAUNCH_PDL(round_tf32_kernel, (unsigned)ddf::cdiv(n / 4 + 1, kThreads), kThreads, 0,
              (cudaStream_t)stream_, src, dst, n / 4, n);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -619,7 +627,7 @@ extern "C" int ddf_split_bf16x3(const float* src, void* split, float* rounded, i
   if (rows == 0) return DDF_OK;
   DDF_CHECK_ARG(src && split, "split_bf16x3: null pointer");
   const long long n8 = rows * cols / 8;
-  DDF_LAUNCH(split_bf16x3_kernel, (unsigned)ddf::cdiv(n8, kThreads), kThreads, 0, (cudaStream_t)stream_, src,
+  DDF_LAUNCH_PDL(split_bf16x3_kernel, (unsigned)ddf::cdiv(n8, kThreads), kThreads, 0, (cudaStream_t)stream_, src,
              reinterpret_cast<uint8_t*>(split), rounded, n8, (int)cols);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -683,6 +691,7 @@ namespace {
 __global__ void __launch_bounds__(kThreads)
 dense_scatter_kernel(const float* __restrict__ feat, const int* __restrict__ indices, int n, int C,
                      int D, int H, int W, float* __restrict__ out) {
+  ddf::pdl_sync();
   // one warp per voxel row keeps the feature read coalesced; the NCDHW write is a C-strided scatter
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int row = (int)(t >> 5), lane = (int)(t & 31);
@@ -696,6 +705,7 @@ dense_scatter_kernel(const float* __restrict__ feat, const int* __restrict__ ind
 __global__ void __launch_bounds__(kThreads)
 dense_gather_kernel(const float* __restrict__ gdense, const int* __restrict__ indices, int n, int C,
                     int D, int H, int W, float* __restrict__ gfeat) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int row = (int)(t >> 5), lane = (int)(t & 31);
   if (row >= n) return;
@@ -744,6 +754,7 @@ namespace {
 __global__ void __launch_bounds__(kThreads)
 bev_nhwc_bf16_scatter_kernel(const float* __restrict__ feat, const int* __restrict__ indices, int n, int C, int D,
                              int H, int W, __nv_bfloat16* __restrict__ out) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int row = (int)(t >> 5), lane = (int)(t & 31);
   if (row >= n) return;
@@ -755,6 +766,7 @@ bev_nhwc_bf16_scatter_kernel(const float* __restrict__ feat, const int* __restri
 __global__ void __launch_bounds__(kThreads)
 bev_nhwc_bf16_gather_kernel(const __nv_bfloat16* __restrict__ gdense, const int* __restrict__ indices, int n, int C,
                             int D, int H, int W, float* __restrict__ gfeat) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int row = (int)(t >> 5), lane = (int)(t & 31);
   if (row >= n) return;

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kThreadsTC)
 spconv_tc_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
                  const int* __restrict__ table, const float* __restrict__ bias,
                  float* __restrict__ out, int n_out, int kvol, int cin, int cout) {
+  ddf::pdl_sync();
   using Cfg = TcCfg<CO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(kThreadsTC)
 spconv_wgrad_tc_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
                        const int* __restrict__ pairs, const int* __restrict__ num, int pair_stride,
                        int kvol, int cin, int cout, int inverse, float* __restrict__ gw) {
+  ddf::pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   int* s_pidx = reinterpret_cast<int*>(smem + kWgStages * kWgStageBytes + 2048);  // [2][128]

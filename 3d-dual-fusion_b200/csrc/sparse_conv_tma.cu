@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kThreads)
 spconv_tma_kernel(const __grid_constant__ CUtensorMap map_feat, const __grid_constant__ CUtensorMap map_w,
                   const float* __restrict__ feat, const int* __restrict__ table, const float* __restrict__ bias, float* __restrict__ out,
                   int n_out, int n_in, int kvol, int cin, int cout, int T, int n_slots, int n_sb) {
+  ddf::pdl_sync();
   using C = Cfg<CO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -664,6 +665,7 @@ __global__ void __launch_bounds__(kWgThreads)
 spconv_wgrad_table_kernel(const float* __restrict__ feat, const float* __restrict__ gout,
                           const int* __restrict__ table, float* __restrict__ gw, int n_out, int n_in,
                           int kvol, int cin, int cout, int KG, int G) {
+  ddf::pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kTblBytes = (SR * kMaxKvol * 4 + 1023) / 1024 * 1024;
@@ -930,7 +932,7 @@ int launch_wgrad_table(const float* feat, const float* gout, const int* table, f
   long long S = (ddf::kNumSM * per_sm) / G;
   if (S > NS) S = NS;
   if (S < 1) S = 1;
-  DDF_LAUNCH((spconv_wgrad_table_kernel<CO, SR, PK>), (unsigned)(G * S), kWgThreads, smem, stream, feat, gout, table, gw,
+  DDF_LAUNCH_PDL((spconv_wgrad_table_kernel<CO, SR, PK>), (unsigned)(G * S), kWgThreads, smem, stream, feat, gout, table, gw,
              (int)n_out, (int)n_in, kvol, cin, cout, KG, G);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -997,7 +999,7 @@ int launch_tma(const float* feat, const float* wt, const int* table, const float
 #endif
   const int smem = n_slots * kABytes + n_sb * C::kBBytes + T * TM * kMaxKvol * 4 + 512 + 1024;
   const unsigned grid = (unsigned)ddf::cdiv(ntiles, T);
-  DDF_LAUNCH((spconv_tma_kernel<CO, GATHER4, PREC, RT>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
+  DDF_LAUNCH_PDL((spconv_tma_kernel<CO, GATHER4, PREC, RT>), grid, kThreads, smem, stream, map_feat, map_w, feat, table,
              bias, out, (int)n_out, (int)n_in, kvol, cin, cout, T, n_slots, n_sb);
   DDF_LAUNCH_CHECK();
   return DDF_OK;

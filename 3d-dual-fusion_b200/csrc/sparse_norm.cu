@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads)
 bn_stats_kernel(const float* __restrict__ x, int n, int C, double* __restrict__ part, double* __restrict__ part2,
                 unsigned* counter, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                 float* running_mean, float* running_var, float momentum, float eps) {
+  ddf::pdl_sync();
   extern __shared__ double tot[];  // [2*C]
   const int tpr = C >> 2, rpb = kThreads / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -167,6 +168,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
                 const float* __restrict__ mean, const float* __restrict__ invstd,
                 const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y,
                 long long n4, int C, int relu, int stat_is_var, float eps) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)(i % (C >> 2)) * 4;
@@ -208,6 +210,7 @@ bn_apply_split_kernel(const float* __restrict__ x, const float* __restrict__ res
                       const float* __restrict__ invstd, const float* __restrict__ w, const float* __restrict__ b,
                       float* __restrict__ y, uint8_t* __restrict__ split, float* __restrict__ rounded, long long n8,
                       int C, int relu, int stat_is_var, float eps) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= n8) return;
   const long long e = t * 8;
@@ -281,6 +284,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                      double* __restrict__ part, double* __restrict__ part2, unsigned* counter,
                      float* __restrict__ gweight,
                      float* __restrict__ gbias, float* __restrict__ coef) {
+  ddf::pdl_sync();
   extern __shared__ double tot[];
   const int tpr = C >> 2, rpb = kThreads / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -332,6 +336,7 @@ bn_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                     const float* __restrict__ invstd, const float* __restrict__ w,
                     const float* __restrict__ coef, float* __restrict__ gx,
                     float* __restrict__ gres, long long n4, int C, int relu) {
+  ddf::pdl_sync();
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)(i % (C >> 2)) * 4;
@@ -432,24 +437,24 @@ static int bn_forward_impl(const float* x, const float* residual, const float* w
   const long long n4 = n * C / 4;
   if (training) {
     DDF_CHECK_ARG(workspace && save_mean && save_invstd, "sparse_bn_forward: training needs workspace and save buffers");
-    DDF_LAUNCH(bn_stats_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, x, (int)n,
+    DDF_LAUNCH_PDL(bn_stats_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, x, (int)n,
                (int)C, (double*)workspace, ws_part2(workspace, C), ws_counter(workspace, C), save_mean, save_invstd,
                running_mean, running_var, momentum, eps);
     if (split)
-      DDF_LAUNCH(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
+      DDF_LAUNCH_PDL(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
                  (const float*)save_mean, (const float*)save_invstd, weight, bias, y, reinterpret_cast<uint8_t*>(split),
                  rounded, n4 / 2, (int)C, relu, 0, eps);
     else
-      DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
+      DDF_LAUNCH_PDL(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
                  (const float*)save_mean, (const float*)save_invstd, weight, bias, y, n4, (int)C, relu, 0, eps);
   } else {
     DDF_CHECK_ARG(running_mean && running_var, "sparse_bn_forward: eval mode needs running statistics");
     if (split)
-      DDF_LAUNCH(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
+      DDF_LAUNCH_PDL(bn_apply_split_kernel, (unsigned)ddf::cdiv(n4 / 2, kThreads), kThreads, 0, stream, x, residual,
                  (const float*)running_mean, (const float*)running_var, weight, bias, y,
                  reinterpret_cast<uint8_t*>(split), rounded, n4 / 2, (int)C, relu, 1, eps);
     else
-      DDF_LAUNCH(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
+      DDF_LAUNCH_PDL(bn_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, x, residual,
                  (const float*)running_mean, (const float*)running_var, weight, bias, y, n4, (int)C, relu, 1, eps);
   }
   DDF_LAUNCH_CHECK();
@@ -477,13 +482,13 @@ extern "C" int ddf_sparse_bn_backward(const float* grad_y, const float* y, const
                     aligned16(weight) && aligned16(mean) && aligned16(invstd),
                 "sparse_bn_backward: tensors must be 16-byte aligned");
   float* coef = ws_coef(workspace, C);
-  DDF_LAUNCH(bn_bwd_reduce_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, grad_y, y, x,
+  DDF_LAUNCH_PDL(bn_bwd_reduce_kernel, stats_grid(n, C), kThreads, 2 * C * sizeof(double), stream, grad_y, y, x,
              mean, invstd, (int)n, (int)C, relu, training, (double*)workspace, ws_part2(workspace, C),
              ws_counter(workspace, C),
              grad_weight, grad_bias, coef);
   if (grad_x || grad_residual) {
     const long long n4 = n * C / 4;
-    DDF_LAUNCH(bn_bwd_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, grad_y, y, x, mean,
+    DDF_LAUNCH_PDL(bn_bwd_apply_kernel, (unsigned)ddf::cdiv(n4, kThreads), kThreads, 0, stream, grad_y, y, x, mean,
                invstd, weight, (const float*)coef, grad_x, grad_residual, n4, (int)C, relu);
   }
   DDF_LAUNCH_CHECK();

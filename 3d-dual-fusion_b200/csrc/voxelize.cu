@@ -61,6 +61,7 @@ __device__ __forceinline__ int point_key(const float* p, const Grid3& g, int* cz
 __global__ void __launch_bounds__(kThreads)
 dynamic_voxelize_kernel(const float* __restrict__ points, int* __restrict__ coors, Grid3 g, int n,
                         int F) {
+  ddf::pdl_sync();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
   int cz, cy, cx;
@@ -79,6 +80,7 @@ dynamic_voxelize_kernel(const float* __restrict__ points, int* __restrict__ coor
 __global__ void __launch_bounds__(kThreads)
 vox_insert_kernel(const float* __restrict__ points, Grid3 g, int n, int F, int T, int* keys,
                   unsigned mask, int* lists, int* __restrict__ slot_of_point) {
+  ddf::pdl_sync();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
   int cz, cy, cx;
@@ -108,6 +110,7 @@ vox_insert_kernel(const float* __restrict__ points, Grid3 g, int n, int F, int T
 __global__ void __launch_bounds__(kThreads)
 vox_flag_first_kernel(const int* __restrict__ slot_of_point, const int* __restrict__ lists, int T,
                       int n, int* __restrict__ is_first) {
+  ddf::pdl_sync();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
   const int h = slot_of_point[i];
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(kThreads)
 vox_rank_kernel(const int* __restrict__ is_first, const int* __restrict__ rank, int n,
                 int max_voxels, int* __restrict__ first_point, int* __restrict__ cut,
                 int* __restrict__ voxel_num) {
+  ddf::pdl_sync();
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i == 0) {
     const int total = rank[n];
@@ -139,6 +143,7 @@ vox_gather_kernel(const float* __restrict__ points, Grid3 g, int F, int T,
                   const int* __restrict__ cut_p, const int* __restrict__ voxel_num_p,
                   float* __restrict__ voxels, int* __restrict__ coors,
                   int* __restrict__ num_points, long long total) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= total) return;
   const int TF = T * F;
@@ -172,6 +177,7 @@ vox_mean_kernel(const float* __restrict__ points, Grid3 g, int F, int T, int NF,
                 const int* __restrict__ keys, const int* __restrict__ lists,
                 const int* __restrict__ cut_p, const int* __restrict__ voxel_num_p,
                 float* __restrict__ mean, int* __restrict__ coors, int* __restrict__ num_points, long long total) {
+  ddf::pdl_sync();
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (t >= total) return;
   const int v = (int)(t / NF);

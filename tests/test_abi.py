@@ -46,3 +46,27 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError):
         MSDeformAttnFunction.apply(v, torch.tensor([[2, 3]]), torch.tensor([0]),
                                    torch.zeros(1, 2, 2, 1, 4, 2), torch.zeros(1, 2, 2, 1, 4), 64)
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """Every launch of the library allows programmatic dependent launch (csrc/common.cuh DDF_LAUNCH), so every kernel
+    must begin with griddepcontrol.wait (SASS: ACQBULK) before it touches memory a predecessor wrote. Checked on the
+    SASS of the built library: a kernel added without ddf::pdl_sync() fails here, not as a race on the GPU."""
+    import shutil
+    import subprocess
+    from ddf_b200 import lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels, cur = {}, None
+    for line in sass.splitlines():
+        line = line.strip()
+        if line.startswith("Function :"):
+            cur = line.split(":", 1)[1].strip()
+            kernels[cur] = False
+        elif cur is not None and "ACQBULK" in line:
+            kernels[cur] = True
+    assert len(kernels) >= 72
+    missing = [k for k, ok in kernels.items() if not ok]
+    assert not missing, "kernels without griddepcontrol.wait: %s" % missing[:5]
