@@ -395,7 +395,7 @@ int launch_sparse_rows(const float* feat, const float* filt, const int* table, c
   long long grid = ddf::cdiv(n_out * 32, kThreads);
   const long long cap = (long long)ddf::kNumSM * (smem > 48 * 1024 ? 3 : 6);   // persistent: the filter bank is staged once per CTA
   if (grid > cap) grid = cap;
-  DDF_LAUNCH((spconv_sparse_rows_kernel<CI, CO>), (unsigned)grid, kThreads, smem, stream, feat, filt, table, bias, out,
+  DDF_LAUNCH_PDL((spconv_sparse_rows_kernel<CI, CO>), (unsigned)grid, kThreads, smem, stream, feat, filt, table, bias, out,
              (int)n_out, kvol);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -468,7 +468,7 @@ extern "C" int ddf_sparse_conv_forward(const float* features, const float* filte
   if (filters_t_ws && tc_enabled() && ddf::spconv_tc_supported((int)kvol, (int)cin, (int)cout)) {
     // tensor-core path wants the filter slice K-major: Wt[k] = [cout, cin]
     const long long nw = kvol * cin * cout;
-    DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+    DDF_LAUNCH_PDL(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
                filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, true);
     if (tma_enabled() && ddf::spconv_tma_supported((int)kvol, (int)cin, (int)cout))
       return ddf::spconv_tma_launch(features, filters_t_ws, gather_table, bias, out, n_out, n_in, (int)kvol,
@@ -503,7 +503,7 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
                                   (int)cout, (int)cin, false, true, stream);
   }
   if (sparse_rows_enabled() && sparse_rows_supported(kvol, cout, cin)) {
-    DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+    DDF_LAUNCH_PDL(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
                filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, false);
     return sparse_rows_dispatch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, (int)kvol, (int)cout,
                                 (int)cin, stream);
@@ -517,7 +517,7 @@ extern "C" int ddf_sparse_conv_dgrad(const float* grad_out, const float* filters
     return ddf::spconv_tc_launch(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in, (int)kvol,
                                  (int)cout, (int)cin, stream);
   }
-  DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+  DDF_LAUNCH_PDL(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
              filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, false);
   // dgrad is a conv with Cin<->Cout swapped through the transposed table
   return launch_gather_gemm(grad_out, filters_t_ws, scatter_table, nullptr, grad_in, n_in,
@@ -678,7 +678,7 @@ extern "C" int ddf_indice_conv_backward(const float* features, const float* filt
     DDF_LAUNCH(pairs_to_table_kernel, (unsigned)ddf::cdiv(np, kThreads), kThreads, 0, stream, 
         indice_pairs, indice_num, (int)pair_stride, (int)kvol, inverse ? 1 : 0, table_ws);
   const long long nw = kvol * cin * cout;
-  DDF_LAUNCH(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
+  DDF_LAUNCH_PDL(transpose_filters_kernel, (unsigned)ddf::cdiv(nw, kThreads), kThreads, 0, stream,
              filters, filters_t_ws, (int)kvol, (int)cin, (int)cout, false);
   return launch_gather_gemm(grad_out, filters_t_ws, table_ws, nullptr, grad_in, n_in, (int)kvol, (int)cout,
                             (int)cin, stream);
@@ -726,7 +726,7 @@ extern "C" int ddf_sparse_to_dense(const float* features, const int* indices, fl
   DDF_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(B * C * D * H * W), stream));
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(features && indices, "sparse_to_dense: null pointer");
-  DDF_LAUNCH(dense_scatter_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, 
+  DDF_LAUNCH_PDL(dense_scatter_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, 
       features, indices, (int)n, (int)C, (int)D, (int)H, (int)W, out);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -740,7 +740,7 @@ extern "C" int ddf_dense_to_sparse(const float* grad_dense, const int* indices,
   DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "dense_to_sparse: bad sizes");
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_dense && indices && grad_features, "dense_to_sparse: null pointer");
-  DDF_LAUNCH(dense_gather_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, 
+  DDF_LAUNCH_PDL(dense_gather_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, 
       grad_dense, indices, (int)n, (int)C, (int)D, (int)H, (int)W, grad_features);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -785,7 +785,7 @@ extern "C" int ddf_sparse_to_bev_nhwc_bf16(const float* features, const int* ind
   DDF_CUDA(cudaMemsetAsync(out, 0, 2 * (size_t)(B * C * D * H * W), stream));
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(features && indices, "sparse_to_bev_nhwc_bf16: null pointer");
-  DDF_LAUNCH(bev_nhwc_bf16_scatter_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, features,
+  DDF_LAUNCH_PDL(bev_nhwc_bf16_scatter_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, stream, features,
              indices, (int)n, (int)C, (int)D, (int)H, (int)W, reinterpret_cast<__nv_bfloat16*>(out));
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -797,7 +797,7 @@ extern "C" int ddf_bev_nhwc_bf16_to_sparse(const void* grad_dense, const int* in
   DDF_CHECK_ARG(n >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "bev_nhwc_bf16_to_sparse: bad sizes");
   if (n == 0) return DDF_OK;
   DDF_CHECK_ARG(grad_dense && indices && grad_features, "bev_nhwc_bf16_to_sparse: null pointer");
-  DDF_LAUNCH(bev_nhwc_bf16_gather_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, (cudaStream_t)stream_,
+  DDF_LAUNCH_PDL(bev_nhwc_bf16_gather_kernel, (unsigned)ddf::cdiv(n * 32, kThreads), kThreads, 0, (cudaStream_t)stream_,
              reinterpret_cast<const __nv_bfloat16*>(grad_dense), indices, (int)n, (int)C, (int)D, (int)H, (int)W,
              grad_features);
   DDF_LAUNCH_CHECK();

@@ -288,7 +288,7 @@ int launch_tc(const float* feat, const float* wt, const int* table, const float*
   using Cfg = TcCfg<CO>;
   DDF_SET_SMEM_ONCE(spconv_tc_kernel<CO>, Cfg::kSmemBytes);
   const unsigned grid = (unsigned)ddf::cdiv(n_out, TM);
-  DDF_LAUNCH(spconv_tc_kernel<CO>, grid, kThreadsTC, Cfg::kSmemBytes, stream, feat, wt, table, bias,
+  DDF_LAUNCH_PDL(spconv_tc_kernel<CO>, grid, kThreadsTC, Cfg::kSmemBytes, stream, feat, wt, table, bias,
              out, (int)n_out, kvol, cin, cout);
   DDF_LAUNCH_CHECK();
   return DDF_OK;
@@ -517,7 +517,7 @@ int launch_wgrad_tc(const float* feat, const float* gout, const int* pairs, cons
   const long long max_useful = ddf::cdiv((long long)pair_stride * kvol, 256);
   if (grid > max_useful) grid = max_useful;
   if (grid < 1) grid = 1;
-  DDF_LAUNCH(spconv_wgrad_tc_kernel<CO>, (unsigned)grid, kThreadsTC, kWgSmemBytes, stream, feat, gout,
+  DDF_LAUNCH_PDL(spconv_wgrad_tc_kernel<CO>, (unsigned)grid, kThreadsTC, kWgSmemBytes, stream, feat, gout,
              pairs, num, (int)pair_stride, kvol, cin, cout, inverse, gw);
   DDF_LAUNCH_CHECK();
   return DDF_OK;

@@ -28,7 +28,7 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=45,
+print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=130, max_name_column_width=45,
                                                           max_shapes_column_width=70))
 if os.environ.get("DDF_PROFILE_FLAT"):
     print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=110, max_name_column_width=90))
