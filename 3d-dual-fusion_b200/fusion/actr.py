@@ -76,16 +76,39 @@ class ACTR(nn.Module):
             # Conv1d(k=1) on (B', C, Lq) == Linear on (B', Lq, C): skip the two transposes around it
             conv, gn = self.i_input_proj[0], self.i_input_proj[1]
             q_i_feat = _fused.linear_wb(v_i_feat, conv.weight.squeeze(-1), conv.bias)
-            q_i_feat = gn(q_i_feat.transpose(1, 2)).transpose(1, 2)
+            q_i_feat = _fused.group_norm_rows(gn, q_i_feat)       # GroupNorm on (B', C, Lq) without the two transposes
             if self.feature_modal == "image":
                 q_feat = q_i_feat
         if self.pos_encode_method == "image_coor":
             q_pos = self.q_position_embedding(grid).transpose(1, 2)
         else:
             q_pos = self.q_position_embedding(lidar_grid[..., 0].clone()).transpose(1, 2)
-        srcs = [self.input_proj[l](src) for l, src in enumerate(i_feats)]
+        srcs = [self._project_map(l, src) for l, src in enumerate(i_feats)]
         return self.transformer(srcs, None, None, q_feat, q_pos, grid, q_lidar_grid=lidar_grid,
                                 q_i_feat_flatten=q_i_feat, valid_index=valid_index)
+
+
+def _project_map(self, lvl, src):
+    """input_proj[lvl] = Conv2d(k=1) + GroupNorm on one camera map (actr.py:172-187). On the device the map becomes
+    rows [B', H*W, Cin] once, the 1x1 convolution is a row-major GEMM and GroupNorm runs on rows; the result is handed
+    on as the NCHW VIEW of those rows, so the transformer's flatten(2).transpose(1, 2) is the rows again (no copy)."""
+    proj = self.input_proj[lvl]
+    conv, gn = proj[0], proj[1]
+    rows_in = isinstance(src, _fused.CameraRows)
+    t = src.rows if rows_in else src
+    fast = (t.is_cuda and isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
+            and conv.padding == (0, 0) and conv.groups == 1 and conv.weight.dtype == torch.float32
+            and not t.requires_grad and _fused.group_norm_rows_ok(gn, conv.out_channels))
+    if not fast:
+        x = src.nchw() if rows_in else src
+        return proj(x if x.dtype == conv.weight.dtype else x.to(conv.weight.dtype))
+    cam = src if rows_in else _fused.nchw_to_rows(src)
+    y = _fused.linear_wb(cam.rows, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+    y = _fused.group_norm_rows(gn, y)
+    return _fused.CameraRows(y, cam.H, cam.W).nchw()
+
+
+ACTR._project_map = _project_map
 
 
 def _cfg_get(cfg, key, default=None):

@@ -22,6 +22,7 @@ from ..ops import spconv
 from ..ops.spconv import SparseConv3d, SubMConv3d
 from ..registry import BACKBONES, FUSION
 from .actr import build as build_actr
+from ..ops import fused as _fused
 from ..ops import sparse_norm
 from .sparse_block import build_norm_layer
 
@@ -324,7 +325,13 @@ class VoxelWithPointProjection(nn.Module):
         order = torch.sort(group, stable=True)[1]            # keeps voxel order inside a (sample, camera)
         cam_id, vox, group = cam_id[order], vox[order], group[order]
         qx, qy = gx[cam_id, vox], gy[cam_id, vox]
-        v_i = img[group, :, qy, qx]                           # camera feature under each query
+        if img.is_cuda and not img.requires_grad and fuse_mode == "pfat":
+            # frozen camera features: token-major once - the feature under a query is one contiguous row, and ACTR's
+            # input projection runs on the same rows
+            img = _fused.nchw_to_rows(img.contiguous())
+            v_i = img.rows.view(-1, img.rows.shape[-1]).index_select(0, (group * Hf + qy.remainder(Hf)) * Wf + qx.remainder(Wf))
+        else:
+            v_i = img[group, :, qy, qx]                       # camera feature under each query
 
         if fuse_mode in ("sum", "mean"):
             upd = torch.zeros_like(feats).index_add_(0, vox, v_i)

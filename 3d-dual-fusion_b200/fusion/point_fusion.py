@@ -19,6 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ..ops import fused as _fused
 from ..registry import FUSION_LAYERS
 from .actr import build as build_actr
 
@@ -213,7 +214,14 @@ class ACTR(nn.Module):
         stride = self.img_stride
         ix = grid_o[:, 0].to(torch.long) // stride
         iy = grid_o[:, 1].to(torch.long) // stride
-        img_at_query = img_feats[0][row, :, iy, ix]                          # (n, C_img)
+        if isinstance(img_feats[0], _fused.CameraRows):
+            # token-major map: the camera feature under a query is ONE contiguous row (the NCHW gather reads C_img
+            # values H * W * 4 bytes apart).  Negative pixel indices wrap like the reference's advanced indexing does
+            cam = img_feats[0]
+            flat_px = (row * cam.H + iy.remainder(cam.H)) * cam.W + ix.remainder(cam.W)
+            img_at_query = cam.rows.view(-1, cam.rows.shape[-1]).index_select(0, flat_px)
+        else:
+            img_at_query = img_feats[0][row, :, iy, ix]                      # (n, C_img)
         return (pad(pts_feats), pad(img_at_query), pad(grid), pad(pts_xyz), row, col, max_points)
 
     def forward(self, img_feats, pts, pts_feats, img_metas, imgs=None):
@@ -236,6 +244,13 @@ class ACTR(nn.Module):
             sids.append(torch.full_like(cam, b))
         cam, grid, grid_o, sid = (torch.cat(x) for x in (cams, grids, grids_o, sids))
         xyz = torch.cat([p[:, :3] for p in pts])
+        if (pts_feats.is_cuda and len(img_feats) == 1 and torch.is_tensor(img_feats[0])
+                and not img_feats[0].requires_grad and not os.environ.get("DDF_NO_CAMERA_ROWS")):
+            # frozen camera features (fp32, or bf16 straight from a bf16 camera branch): token-major once, for the
+            # per-query gather here and for ACTR's input projection
+            img_feats = [_fused.nchw_to_rows(img_feats[0])]
+        else:
+            img_feats = [f if f.dtype == pts_feats.dtype else f.to(pts_feats.dtype) for f in img_feats]
         feats_n, img_n, grid_n, xyz_n, row, col, max_points = self.split_param(
             pts_feats, cam, grid, grid_o, img_feats, xyz, sid, n_cam)
         # when the per-camera counts are unbalanced (real data: voxels no camera sees all become camera-0 queries) the

@@ -79,6 +79,10 @@ _SIGNATURES = {
     "ddf_ffn_workspace_bytes": [c_i64] * 2,
     "ddf_ffn_forward": [c_ptr] * 8 + [c_i64] * 3 + [c_f32, ctypes.c_uint64, c_ptr],
     "ddf_ffn_dropout_p": [c_f32],
+    "ddf_group_norm_rows_supported": [c_i64] * 2,
+    "ddf_nchw_to_rows": [c_ptr, c_int, c_ptr] + [c_i64] * 3 + [c_ptr],
+    "ddf_group_norm_rows_forward": [c_ptr] * 7 + [c_i64] * 4 + [c_f32, c_ptr],
+    "ddf_group_norm_rows_backward": [c_ptr] * 9 + [c_i64] * 4 + [c_ptr],
     "ddf_xty_supported": [c_i64] * 3,
     "ddf_xty_tf32": [c_ptr] * 3 + [c_i64] * 3 + [c_ptr],
     "ddf_sparse_to_dense": [c_ptr] * 3 + [c_i64] * 6 + [c_ptr],

@@ -297,6 +297,92 @@ def bigate_sum(b_conv, a_conv, feat1, feat2, fuse_in):
     return _BiGateSum.apply(feat1, feat2, b_conv.weight, b_conv.bias, a_conv.weight, a_conv.bias, fuse_in)
 
 
+class CameraRows:
+    """A camera feature map kept token-major: ``rows`` [N, H*W, C] fp32 (what ``nchw_to_rows`` returns) with its
+    (H, W). ACTR accepts it in place of the NCHW tensor of the same map, so a wrapper that already needs the rows (the
+    per-query camera feature is a row gather) converts once."""
+
+    def __init__(self, rows, H, W):
+        self.rows, self.H, self.W = rows, int(H), int(W)
+
+    @property
+    def shape(self):            # the NCHW shape of the map this stands for
+        n, _, c = self.rows.shape
+        return torch.Size((n, c, self.H, self.W))
+
+    def nchw(self):
+        n, _, c = self.rows.shape
+        return self.rows.view(n, self.H, self.W, c).permute(0, 3, 1, 2)
+
+
+def nchw_to_rows(x):
+    """(N, C, H, W) fp32 / bf16 -> CameraRows with rows [N, H*W, C] fp32 in one transposing pass (ddf_nchw_to_rows)."""
+    N, C, H, W = x.shape
+    if (not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or x.requires_grad or N >= 65536
+            or not x.is_contiguous()):
+        return CameraRows(x.flatten(2).transpose(1, 2).float().contiguous(), H, W)
+    rows = torch.empty((N, H * W, C), dtype=torch.float32, device=x.device)
+    with _lib.on_device(x.device):
+        rc = _lib.get_lib().ddf_nchw_to_rows(_lib.ptr(x), 1 if x.dtype == torch.bfloat16 else 0, _lib.ptr(rows), N, C,
+                                             H * W, _lib.current_stream())
+    _lib.check(rc, "nchw_to_rows")
+    return CameraRows(rows, H, W)
+
+
+class _GroupNormRows(Function):
+    """torch.nn.GroupNorm over token-major data x [N, L, C] (statistics over the (L, C / G) elements of a (sample,
+    group)) without the transposes to and from (N, C, L): ddf_group_norm_rows_forward / _backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, G, eps):
+        _lib.require_cuda(x, weight, bias)
+        x = x.contiguous()
+        N, L, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty((N, G), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((N, G), dtype=torch.float32, device=x.device)
+        ws = torch.empty(2 * N * G, dtype=torch.float64, device=x.device)
+        with _lib.on_device(x.device):
+            rc = _lib.get_lib().ddf_group_norm_rows_forward(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y),
+                                                            _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(ws), N, L, C, G,
+                                                            float(eps), _lib.current_stream())
+        _lib.check(rc, "group_norm_rows_forward")
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.G = G
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        N, L, C = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        need = ctx.needs_input_grad
+        gw = torch.empty(C, dtype=torch.float32, device=x.device) if need[1] else None
+        gb = torch.empty(C, dtype=torch.float32, device=x.device) if need[2] else None
+        ws = torch.empty(2 * N * ctx.G, dtype=torch.float64, device=x.device)
+        with _lib.on_device(x.device):
+            rc = _lib.get_lib().ddf_group_norm_rows_backward(_lib.ptr(gy), _lib.ptr(x), _lib.ptr(weight), _lib.ptr(mean),
+                                                             _lib.ptr(rstd), _lib.ptr(gx), _lib.ptr(gw), _lib.ptr(gb),
+                                                             _lib.ptr(ws), N, L, C, ctx.G, _lib.current_stream())
+        _lib.check(rc, "group_norm_rows_backward")
+        return (gx if need[0] else None), gw, gb, None, None
+
+
+def group_norm_rows_ok(gn, C, device_is_cuda=True):
+    return bool(device_is_cuda and gn.affine and gn.weight.dtype == torch.float32 and gn.num_channels == C
+                and _lib.get_lib().ddf_group_norm_rows_supported(C, gn.num_groups))
+
+
+def group_norm_rows(gn, x):
+    """``gn(x.transpose(1, 2)).transpose(1, 2)`` for token-major x [N, L, C] (the reference's GroupNorm around Conv1d /
+    Conv2d(k=1) projections, actr.py:150-158): the rows kernel when C == 4 * groups, else the transposes."""
+    if x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and group_norm_rows_ok(gn, x.shape[-1]):
+        return _GroupNormRows.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
+    return gn(x.transpose(1, 2)).transpose(1, 2)
+
+
 class _FusedFFN(Function):
     """y = linear2(dropout(relu(linear1(x)))) with the forward as ONE kernel (ddf_ffn_forward: the [T, d_ffn] hidden
     activation is written once for backward and never read again in forward). Backward: the split-K weight

@@ -113,7 +113,8 @@ class TransFusionWorkload(Workload):
         return {"pts": pts, "feats": feats}, [synth.nusc_img_meta(N_CAM) for _ in range(batch)]
 
     def forward(self, model, t, metas):
-        return model(t["pts"], [t["feats"].float()], metas)
+        f = t["feats"]       # on the device the fusion wrapper takes the bf16 maps as they are (widened while it re-lays them)
+        return model(t["pts"], [f if f.is_cuda else f.float()], metas)
 
 
 class TransFusionCameraWorkload(TransFusionWorkload):

@@ -411,6 +411,24 @@ int ddf_ffn_forward(const float* x, const float* w1, const float* b1, const floa
  * pass THIS to ddf_bias_relu_dropout_backward, which scales by 1 / (1 - p) */
 float ddf_ffn_dropout_p(float p);
 
+/* ---- camera-side input projection in the token-major ("rows") layout -------------------------------------------
+ * The reference runs Conv2d(k=1) + GroupNorm(32, d_model) on NCHW camera maps and flattens / transposes the result to
+ * [B', H*W, d_model] (<proj>/models/model_utils/actr.py:131-187, actr_transformer.py:255-264); the per-query camera
+ * feature takes Conv1d(k=1) + GroupNorm between two transposes (actr.py:150-158).  Here the map becomes rows once, the
+ * 1x1 convolution is a row-major GEMM and GroupNorm runs on rows (same arithmetic as torch.nn.GroupNorm: biased
+ * variance over the (L, C / G) elements of a (sample, group)).
+ * ddf_nchw_to_rows: src [N, C, HW] (dtype 0 = fp32, 1 = bf16) -> dst [N, HW, C] fp32.
+ * ddf_group_norm_rows_*: x / y [N, L, C], C == 4 * G (ddf_group_norm_rows_supported), w / b [C] may be NULL, mean / rstd
+ * [N, G] saved by forward for backward, ws = N * G * 2 doubles of scratch (any content); backward overwrites grad_w /
+ * grad_b [C] (may be NULL). */
+int ddf_group_norm_rows_supported(int64_t C, int64_t G);
+int ddf_nchw_to_rows(const void* src, int dtype, float* dst, int64_t N, int64_t C, int64_t HW, void* stream);
+int ddf_group_norm_rows_forward(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                                void* ws, int64_t N, int64_t L, int64_t C, int64_t G, float eps, void* stream);
+int ddf_group_norm_rows_backward(const float* grad_y, const float* x, const float* w, const float* mean,
+                                 const float* rstd, float* grad_x, float* grad_w, float* grad_b, void* ws, int64_t N,
+                                 int64_t L, int64_t C, int64_t G, void* stream);
+
 /* c [M, N] = a [K, M]^T . b [K, N]: the weight gradient of an nn.Linear over K tokens, W.grad [out, in] =
  * grad_out [K, out]^T . x [K, in] (autograd of F.linear in <proj>/models/model_utils/actr_transformer.py:383-397,
  * ops/modules/ms_deform_attn.py:124-147).  fp32 row-major operands read as tf32 (top 19 bits) by tcgen05, fp32

@@ -358,3 +358,88 @@ def test_fused_ffn_dropout_statistics_and_backward():
         assert rel(gb1, gh_ref.sum(0).cpu()) < 4e-3
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("N,C,H,W", [(1, 32, 1, 1), (2, 256, 7, 9), (3, 100, 33, 31), (12, 256, 112, 200)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_nchw_to_rows_is_the_transpose(N, C, H, W, dtype):
+    """ddf_nchw_to_rows: (N, C, H, W) fp32 / bf16 -> token-major rows [N, H*W, C] fp32, bit-exact (a widening copy)."""
+    from ddf_b200.ops import fused
+    torch.manual_seed(N * C + H)
+    x = torch.randn(N, C, H, W, device="cuda").to(dtype)
+    cam = fused.nchw_to_rows(x)
+    assert cam.rows.dtype == torch.float32 and tuple(cam.shape) == (N, C, H, W)
+    assert torch.equal(cam.rows, x.float().flatten(2).transpose(1, 2))
+    assert torch.equal(cam.nchw(), x.float())
+    # the transformer's flatten(2).transpose(1, 2) of the NCHW view is the rows again, without a copy
+    back = cam.nchw().flatten(2).transpose(1, 2)
+    assert back.is_contiguous() and back.data_ptr() == cam.rows.data_ptr()
+
+
+@pytest.mark.parametrize("N,L,C", [(1, 1, 128), (2, 37, 128), (12, 12168, 128), (3, 22400, 128), (5, 4099, 64), (2, 333, 256)])
+def test_group_norm_rows_matches_torch_group_norm(N, L, C):
+    """GroupNorm(C / 4 groups) on token-major [N, L, C] against torch.nn.GroupNorm on the transposed (N, C, L) tensor in
+    float64 (actr.py:150-158, 172-187: Conv(k=1) + GroupNorm(32, 128)); forward 1e-5, gradients 1e-4 of the largest value."""
+    from ddf_b200.ops import fused
+    torch.manual_seed(L + C)
+    gn = nn.GroupNorm(C // 4, C).cuda()
+    with torch.no_grad():
+        gn.weight.uniform_(0.5, 1.5)
+        gn.bias.normal_()
+    x = (torch.randn(N, L, C, device="cuda") * 2 + 0.5).requires_grad_()
+    go = torch.randn(N, L, C, device="cuda")
+    assert fused.group_norm_rows_ok(gn, C)
+    y = fused.group_norm_rows(gn, x)
+    y.backward(go)
+    ref_gn = copy.deepcopy(gn).double().cpu()
+    ref_gn.zero_grad()
+    xr = x.detach().double().cpu().requires_grad_()
+    yr = ref_gn(xr.transpose(1, 2)).transpose(1, 2)
+    yr.backward(go.double().cpu())
+    assert rel(y.detach(), yr.detach()) < 1e-5
+    assert rel(x.grad, xr.grad) < 1e-4
+    assert rel(gn.weight.grad, ref_gn.weight.grad) < 1e-4
+    assert rel(gn.bias.grad, ref_gn.bias.grad) < 1e-4
+
+
+def test_group_norm_rows_falls_back_when_groups_are_not_four_wide():
+    from ddf_b200.ops import fused
+    gn = nn.GroupNorm(32, 64).cuda()          # 2 channels per group: the transposing path
+    x = torch.randn(2, 50, 64, device="cuda")
+    assert not fused.group_norm_rows_ok(gn, 64)
+    assert torch.allclose(fused.group_norm_rows(gn, x), gn(x.transpose(1, 2)).transpose(1, 2))
+
+
+def test_actr_projects_camera_rows_like_the_module_chain():
+    """ACTR._project_map (rows: GEMM + GroupNorm on rows, result handed on as an NCHW view) against
+    input_proj = Conv2d(k=1) + GroupNorm on the NCHW map, outputs and parameter gradients; fp32 and bf16 maps."""
+    from ddf_b200.fusion import actr as actr_mod
+    from ddf_b200.ops import fused
+    torch.manual_seed(5)
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        proj = nn.Sequential(nn.Conv2d(256, 128, kernel_size=1), nn.GroupNorm(32, 128)).cuda()
+
+        class Holder:
+            input_proj = [proj]
+        for dtype in (torch.float32, torch.bfloat16):
+            x = torch.randn(4, 256, 40, 50, device="cuda").to(dtype)
+            go = torch.randn(4, 128, 40, 50, device="cuda")
+            proj.zero_grad()
+            want = proj(x.float())
+            want.backward(go)
+            gw, gb, ggw = proj[0].weight.grad.clone(), proj[0].bias.grad.clone(), proj[1].weight.grad.clone()
+            proj.zero_grad()
+            got = actr_mod._project_map(Holder, 0, x)
+            assert got.shape == want.shape
+            got.backward(go)
+            assert rel(got.detach(), want.detach().cpu()) < 1e-5
+            assert rel(proj[0].weight.grad, gw.cpu()) < 2e-3          # xty reads tf32 operands
+            assert rel(proj[0].bias.grad, gb.cpu()) < 1e-4
+            assert rel(proj[1].weight.grad, ggw.cpu()) < 1e-4
+            # a wrapper that already holds the rows passes them in
+            got2 = actr_mod._project_map(Holder, 0, fused.nchw_to_rows(x))
+            assert torch.equal(got2, got)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
