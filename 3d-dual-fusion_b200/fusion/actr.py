@@ -98,7 +98,8 @@ def _project_map(self, lvl, src):
     t = src.rows if rows_in else src
     fast = (t.is_cuda and isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
             and conv.padding == (0, 0) and conv.groups == 1 and conv.weight.dtype == torch.float32
-            and not t.requires_grad and _fused.group_norm_rows_ok(gn, conv.out_channels))
+            and (rows_in or t.dtype == torch.float32 or not t.requires_grad)
+            and (rows_in or t.is_contiguous()) and _fused.group_norm_rows_ok(gn, conv.out_channels))
     if not fast:
         x = src.nchw() if rows_in else src
         return proj(x if x.dtype == conv.weight.dtype else x.to(conv.weight.dtype))

@@ -325,9 +325,9 @@ class VoxelWithPointProjection(nn.Module):
         order = torch.sort(group, stable=True)[1]            # keeps voxel order inside a (sample, camera)
         cam_id, vox, group = cam_id[order], vox[order], group[order]
         qx, qy = gx[cam_id, vox], gy[cam_id, vox]
-        if img.is_cuda and not img.requires_grad and fuse_mode == "pfat":
-            # frozen camera features: token-major once - the feature under a query is one contiguous row, and ACTR's
-            # input projection runs on the same rows
+        if img.is_cuda and img.dtype == torch.float32 and fuse_mode == "pfat":
+            # camera features (frozen, or the output of the IFAT gate: the conversion carries the gradient): token-major
+            # once - the feature under a query is one contiguous row, and ACTR's input projection runs on the same rows
             img = _fused.nchw_to_rows(img.contiguous())
             v_i = img.rows.view(-1, img.rows.shape[-1]).index_select(0, (group * Hf + qy.remainder(Hf)) * Wf + qx.remainder(Wf))
         else:

@@ -245,8 +245,8 @@ class ACTR(nn.Module):
         cam, grid, grid_o, sid = (torch.cat(x) for x in (cams, grids, grids_o, sids))
         xyz = torch.cat([p[:, :3] for p in pts])
         if (pts_feats.is_cuda and len(img_feats) == 1 and torch.is_tensor(img_feats[0])
-                and not img_feats[0].requires_grad and not os.environ.get("DDF_NO_CAMERA_ROWS")):
-            # frozen camera features (fp32, or bf16 straight from a bf16 camera branch): token-major once, for the
+                and not os.environ.get("DDF_NO_CAMERA_ROWS")):
+            # camera features (fp32, or bf16 straight from a frozen bf16 camera branch): token-major once, for the
             # per-query gather here and for ACTR's input projection
             img_feats = [_fused.nchw_to_rows(img_feats[0])]
         else:

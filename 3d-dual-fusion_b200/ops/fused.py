@@ -315,18 +315,43 @@ class CameraRows:
         return self.rows.view(n, self.H, self.W, c).permute(0, 3, 1, 2)
 
 
+def _transpose_last2(x3, dtype_code):
+    """[N, A, B] -> [N, B, A] fp32 through ddf_nchw_to_rows (a batched 2-D transpose; widens bf16)."""
+    N, A, B = x3.shape
+    out = torch.empty((N, B, A), dtype=torch.float32, device=x3.device)
+    with _lib.on_device(x3.device):
+        rc = _lib.get_lib().ddf_nchw_to_rows(_lib.ptr(x3), dtype_code, _lib.ptr(out), N, A, B, _lib.current_stream())
+    _lib.check(rc, "nchw_to_rows")
+    return out
+
+
+class _NchwToRows(Function):
+    """(N, C, H, W) -> rows [N, H*W, C] for maps that carry a gradient (CenterPoint's gated camera features): the
+    backward is the same transposing kernel the other way round."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        ctx.hw = (H, W)
+        return _transpose_last2(x.view(N, C, H * W), 0)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        N, HW, C = g.shape
+        return _transpose_last2(g.contiguous(), 0).view(N, C, *ctx.hw)
+
+
 def nchw_to_rows(x):
     """(N, C, H, W) fp32 / bf16 -> CameraRows with rows [N, H*W, C] fp32 in one transposing pass (ddf_nchw_to_rows)."""
     N, C, H, W = x.shape
-    if (not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or x.requires_grad or N >= 65536
-            or not x.is_contiguous()):
+    if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or N >= 65536 or not x.is_contiguous():
         return CameraRows(x.flatten(2).transpose(1, 2).float().contiguous(), H, W)
-    rows = torch.empty((N, H * W, C), dtype=torch.float32, device=x.device)
-    with _lib.on_device(x.device):
-        rc = _lib.get_lib().ddf_nchw_to_rows(_lib.ptr(x), 1 if x.dtype == torch.bfloat16 else 0, _lib.ptr(rows), N, C,
-                                             H * W, _lib.current_stream())
-    _lib.check(rc, "nchw_to_rows")
-    return CameraRows(rows, H, W)
+    if x.requires_grad and torch.is_grad_enabled():
+        if x.dtype != torch.float32:
+            return CameraRows(x.flatten(2).transpose(1, 2).float().contiguous(), H, W)
+        return CameraRows(_NchwToRows.apply(x), H, W)
+    return CameraRows(_transpose_last2(x.detach().view(N, C, H * W), 1 if x.dtype == torch.bfloat16 else 0), H, W)
 
 
 class _GroupNormRows(Function):

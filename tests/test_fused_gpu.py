@@ -443,3 +443,16 @@ def test_actr_projects_camera_rows_like_the_module_chain():
             assert torch.equal(got2, got)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_nchw_to_rows_carries_the_gradient():
+    """Maps that require grad (CenterPoint's gated camera features) go through the same kernel; the backward is the
+    transpose back, bit-exact."""
+    from ddf_b200.ops import fused
+    torch.manual_seed(9)
+    x = torch.randn(3, 40, 17, 23, device="cuda", requires_grad=True)
+    cam = fused.nchw_to_rows(x)
+    assert cam.rows.requires_grad and torch.equal(cam.rows.detach(), x.detach().flatten(2).transpose(1, 2))
+    g = torch.randn_like(cam.rows)
+    cam.rows.backward(g)
+    assert torch.equal(x.grad, g.transpose(1, 2).reshape(x.shape))
