@@ -6,5 +6,6 @@ Layout
   build.py   in-tree nvcc build of the library
   ops/       host-side mirrors of the reference's op packages (same names / argument meaning)
   fusion/    the 3D-DF fusion encoder modules with the reference's state-dict layout
+  data_parallel.py  gradient averaging over the ranks: one flat NCCL all-reduce per step
 """
 __version__ = "0.1.0"
