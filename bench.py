@@ -764,6 +764,8 @@ def run_ours(args):
             "dtype": "f32 storage/accumulate; sparse convs bf16x3 (hi/lo split operands, 16-bit significand products) on "
                      "tcgen05, wgrad tf32; library GEMMs " + ("f32" if args.fp32_gemm else "tf32"),
             "data": "synthetic", "config": wl.describe(world),
+            "grad_sync": ("none (one GPU)" if world == 1 else "torch DistributedDataParallel" if args.ddp
+                          else "ddf_b200.data_parallel.GradientExchange: one flat all-reduce per step"),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "every step copies its inputs from pinned host memory (side stream, two persistent device "
