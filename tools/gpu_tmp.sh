@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-DDF_STEPS=1 NCU_COUNT=9 bash tools/gpu_ncu_one.sh "gn_rows|nchw_to_rows" prof_rows2 python tools/step_only.py --config tf > gpurun_out/prof_rows2.out 2>&1
-head -30 gpurun_out/prof_rows2.md
+timeout 200 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_tf_last.err | tee gpurun_out/bench_tf_last.json | python tools/print_bench.py | cut -c1-120
+python -c "
+import json; d=json.load(open('gpurun_out/bench_tf_last.json')); print(d['grad_sync'], d['clocks'], d['gpu_launches'])"
