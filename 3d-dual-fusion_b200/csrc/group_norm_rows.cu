@@ -234,7 +234,8 @@ extern "C" int ddf_group_norm_rows_supported(int64_t C, int64_t G) {
 // src [N, C, HW] (dtype 0: fp32, 1: bf16) -> dst [N, HW, C] fp32
 extern "C" int ddf_nchw_to_rows(const void* src, int dtype, float* dst, int64_t N, int64_t C, int64_t HW, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DDF_CHECK_ARG(N >= 0 && C > 0 && HW > 0 && N < 65536 && (dtype == 0 || dtype == 1), "nchw_to_rows: bad arguments");
+  DDF_CHECK_ARG(N >= 0 && C > 0 && HW > 0 && N < 65536 && C <= 65535ll * 32 && HW < (1ll << 31) && (dtype == 0 || dtype == 1),
+                "nchw_to_rows: bad arguments (N < 65536, C <= 2097120)");
   if (N == 0) return DDF_OK;
   DDF_CHECK_ARG(src && dst, "nchw_to_rows: null pointer");
   const dim3 grid((unsigned)ddf::cdiv(HW, 32), (unsigned)ddf::cdiv(C, 32), (unsigned)N);

@@ -339,6 +339,8 @@ class _NchwToRows(Function):
     @once_differentiable
     def backward(ctx, g):
         N, HW, C = g.shape
+        if HW > 65535 * 32:      # the kernel's grid.y covers the source's middle dimension in tiles of 32
+            return g.transpose(1, 2).reshape(N, C, *ctx.hw)
         return _transpose_last2(g.contiguous(), 0).view(N, C, *ctx.hw)
 
 
