@@ -5,7 +5,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "3d-dual-fusion_b200", "libddf_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "UTCATOM", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "REDG", "RED.", "ATOMG", "ATOMS", "HMMA", "FFMA", "DFMA", "DADD", "SHFL", "LDG", "STG", "LDS", "STS"]
+KEYS = ["ACQBULK", "PREEXIT", "UTCHMMA", "UTCBAR", "LDTM", "UTCATOM", "UTMALDG", "UBLKCP", "LDGSTS", "SYNCS", "REDG", "RED.", "ATOMG", "ATOMS", "HMMA", "FFMA", "DFMA", "DADD", "SHFL", "LDG", "STG", "LDS", "STS"]
 cur = None
 hist = collections.OrderedDict()
 variants = collections.Counter()
@@ -45,3 +45,7 @@ for name, c in hist.items():
 print("\nTotals over the listed kernels: " + ", ".join("%s %d" % (k, tot[k]) for k in cols if tot[k]))
 print("\nVariants: " + ", ".join("%s x%d" % kv for kv in sorted(variants.items())))
 print("\n%d kernels in the library." % len(hist))
+n_wait = sum(1 for c in hist.values() if c["ACQBULK"])
+n_trig = sum(1 for c in hist.values() if c["PREEXIT"])
+print("\nProgrammatic dependent launch: ACQBULK (griddepcontrol.wait) in %d of %d kernels, PREEXIT "
+      "(griddepcontrol.launch_dependents) in %d." % (n_wait, len(hist), n_trig))
